@@ -1,0 +1,158 @@
+/*
+ * vppstereo_b200.h -- C ABI of the B200-native (sm_100a) VPP + rSGM hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one callable of the reference's two native modules
+ * (`pyrSGM`, thirdparty/stereo-vision/reconstruction/base/rSGM/pyrSGM.cpp:761-774, and `vpp_core_opt`,
+ * vpp_core/vpp_core_opt.pyx) or one Python-level stage of models/rsgm/rsgm.py / vpp_standalone.py.
+ * Citations are relative to the reference root; RSGM/ = thirdparty/stereo-vision/reconstruction/base/rSGM/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all image / volume pointers are DEVICE pointers unless named *_host;
+ *   - every op takes a frame batch: `n` frames stored back to back (frame stride = the natural array size);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous on it;
+ *   - no hidden allocation on the data path: ops that need scratch take a caller-provided workspace
+ *     (size from the matching *_workspace_bytes query);
+ *   - return value: VPPB200_OK or a negative status.  The argument-validation statuses mirror the TypeError
+ *     classes of the reference wrapper (RSGM/pyrSGM.cpp:31-35,:206-222,:330-334,:673-677);
+ *   - layouts: images row-major [H][W] or [H][W][C] uint8; cost volumes [H][W][D] uint16, d fastest
+ *     (RSGM/StereoBMHelper.h:138-141); disparities float32 [H][W].
+ * There is no CPU implementation behind this ABI.
+ */
+#ifndef VPPSTEREO_B200_H
+#define VPPSTEREO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPPB200_OK 0
+#define VPPB200_ERR_WIDTH (-1)       /* width % 16 != 0                      (pyrSGM.cpp:31-35)   */
+#define VPPB200_ERR_DISP (-2)        /* D % 8 != 0 or D > 256                (pyrSGM.cpp:212-216) */
+#define VPPB200_ERR_THREADS (-3)     /* numThreads not in {1,2,4}            (pyrSGM.cpp:218-222) */
+#define VPPB200_ERR_UNIQUENESS (-4)  /* uniqueness not in (0,1]              (pyrSGM.cpp:330-334) */
+#define VPPB200_ERR_METHOD (-5)      /* sub-pixel method not in {0,1}        (pyrSGM.cpp:673-677) */
+#define VPPB200_ERR_WORKSPACE (-6)   /* workspace missing or too small */
+#define VPPB200_ERR_ARG (-7)         /* null pointer / non-positive size / unsupported combination */
+#define VPPB200_ERR_CUDA (-100)      /* a CUDA runtime call failed; see vppb200_last_cuda_error() */
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char *vppb200_version(void);
+/* name of the last failing CUDA call + cudaGetErrorString, thread-local; "" if none */
+const char *vppb200_last_cuda_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t vppb200_launch_count(void);
+/* 65536-entry table lut[k] = rcp_nz_ss(-2k) evaluated with the HOST CPU's RCPSS instruction
+ * (RSGM/StereoBMHelper.cpp:752-756, used by subPixelRefine :1088-1096).  Host pointer. */
+int vppb200_rcp_lut_host(float *lut_host);
+
+/* Host-side restatement of glibc srand()/rand() (TYPE_3 additive feedback generator, r[i] = r[i-3] + r[i-31]) so that
+ * `init_rand(seed)` + scans (vpp_core_opt.pyx:33-35,:93,:102) reproduce the reference's libc pattern stream without
+ * touching the process-global libc state.  state: 34 x uint32 owned by the caller.  vppb200_glibc_rand_fill writes
+ * n values of rand() % 256 to out_host and advances the state. */
+int vppb200_glibc_srand(uint32_t *state34, uint32_t seed);
+int vppb200_glibc_rand_fill(uint32_t *state34, uint8_t *out_host, int64_t n);
+
+/* Per-stage device timing of vppb200_compute_rsgm (CUDA events recorded on the call's stream at the stage boundaries).
+ * Stages: 0 pad+gray, 1 census, 2 cost volume, 3 SGM aggregation, 4 WTA L/R + sub-pixel, 5 median + interpolation, 6 tail.
+ * vppb200_stage_timing(1) enables and resets; vppb200_stage_times synchronises the pending events, writes the
+ * accumulated milliseconds per stage to ms_out[7] and the number of timed calls to *calls_out. */
+#define VPPB200_N_STAGES 7
+int vppb200_stage_timing(int enable);
+int vppb200_stage_times(float *ms_out, int *calls_out);
+
+/* ---- pyrSGM operators ----------------------------------------------------------------------------------- */
+/* census5x5_SSE(src u8[H,W], dst u32[H,W], W, H)                       RSGM/pyrSGM.cpp:14, FastFilters.cpp:181-442.
+ * Pixels the reference leaves unwritten (rows 0,1,H-2,H-1 and (H-3,{W-16,W-15,W-2,W-1})) are written as 0. */
+int vppb200_census5x5(const uint8_t *src, uint32_t *dst, int W, int H, int n, void *stream);
+
+/* costMeasureCensus5x5_xyd_SSE(cl, cr, dsi u16[H,W,D], W, H, D, nthreads) RSGM/pyrSGM.cpp:180, StereoBMHelper.cpp:29-140 */
+int vppb200_cost_census5x5_xyd(const uint32_t *cl, const uint32_t *cr, uint16_t *dsi, int W, int H, int D,
+                               int num_threads, int n, void *stream);
+
+/* aggregate_SSE(img u8, dsi, dsiAgg, W, H, D, P1, P2min, Alpha, Gamma)     RSGM/pyrSGM.cpp:504, StereoSGM_SSE.hpp:13-515.
+ * The reference parses P1..Gamma and then ignores them (pyrSGM.cpp:519 vs :557-560): the effective values are
+ * P1=7, P2min=17, Alpha=0.25, Gamma=50.  honor_params=0 reproduces that; honor_params=1 uses the arguments.
+ * `img` = the first W*H bytes of the guide image buffer, read as a flat byte stream (pyrSGM.cpp:586-588). */
+int vppb200_aggregate(const uint8_t *img, const uint16_t *dsi, uint16_t *dsi_agg, int W, int H, int D,
+                      int P1, int P2min, float alpha, int gamma, int honor_params, int n, void *stream);
+
+/* matchWTA_SSE / matchWTARight_SSE(dsiAgg, disp f32[H,W], W, H, D, uniqueness)  RSGM/pyrSGM.cpp:296,:399,
+ * StereoBMHelper.cpp:634-750,:893-1015.  First arg-min; uniqueness is validated and otherwise dead, as upstream. */
+int vppb200_match_wta(const uint16_t *dsi_agg, float *disp, int W, int H, int D, float uniqueness, int n, void *stream);
+int vppb200_match_wta_right(const uint16_t *dsi_agg, float *disp, int W, int H, int D, float uniqueness, int n, void *stream);
+
+/* subPixelRefine(dsi, disp, W, H, D, method)                             RSGM/pyrSGM.cpp:639, StereoBMHelper.cpp:1065-1135.
+ * rcp_lut: DEVICE copy of the vppb200_rcp_lut_host table (method 0); NULL = the library's own table for this host. */
+int vppb200_subpixel_refine(const uint16_t *dsi, float *disp, int W, int H, int D, int method, const float *rcp_lut,
+                            int n, void *stream);
+
+/* median3x3_SSE(src f32, dst f32, W, H)                                   RSGM/pyrSGM.cpp:97, FastFilters.cpp:701-757 */
+int vppb200_median3x3(const float *src, float *dst, int W, int H, int n, void *stream);
+
+/* ---- compute_rsgm: whole pipeline on device ----------------------------------------------------------------
+ * compute_rsgm(left, left_vpp, right_vpp, hints, validhints, dmax, ..., subpixel)   models/rsgm/rsgm.py:250-294.
+ * Inputs uint8 [n][H][W][C] (C = 1 or 3; `left` is the adaptive-P2 guide), optional hints/validhints float32
+ * [n][H][W] (both NULL = unguided), output float32 [n][H][W].  p1/p2min/alpha/gamma do not exist here because
+ * the reference ignores them.  flags: bit0 = subpixel. */
+size_t vppb200_rsgm_workspace_bytes(int H, int W, int C, int D, int n);
+int vppb200_compute_rsgm(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp,
+                         const float *hints, const float *validhints, float *disp_out,
+                         int H, int W, int C, int D, int flags, const float *rcp_lut,
+                         void *workspace, size_t workspace_bytes, int n, void *stream);
+
+/* Stage taps of the same pipeline for tests (any pointer may be NULL): padded census L/R u32 [n][Hp][Wp], aggregated
+ * volume u16 [n][Hp][Wp][D], left/right disparities after median+interpolation+clip f32 [n][Hp][Wp].  Set before the
+ * call, valid after the stream is synchronised. */
+typedef struct {
+    uint32_t *census_l, *census_r;
+    uint16_t *dsi_agg;
+    float *disp_l, *disp_r;
+} vppb200_rsgm_taps;
+int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp,
+                                const float *hints, const float *validhints, float *disp_out,
+                                int H, int W, int C, int D, int flags, const float *rcp_lut,
+                                void *workspace, size_t workspace_bytes, int n, void *stream,
+                                const vppb200_rsgm_taps *taps);
+
+/* ---- vpp_core_opt operators ---------------------------------------------------------------------------------
+ * virtual_projection_scan_rnd(l, r, g, width, height, channels, uniform_color, wsize, direction, c, c_occ, g_occ,
+ *                             discard_occluded, interpolate) -> #hints                vpp_core_opt.pyx:53-131
+ * l, r uint8 [n][H][W][C] are modified in place; g float32 [n][H][W] (0 = no hint); g_occ uint8 [n][H][W].
+ * arith: 0 = Cython arithmetic (c as float32, vpp_core_opt.pyx), 1 = numba arithmetic (all float64,
+ *        vpp_standalone.py:243-369; round half to even).
+ * The reference draws the pattern from libc rand() / numba's generator while scanning; here the caller passes the
+ * pre-drawn values: pattern[] (uint8) holds all frames' streams, frame f starts at pattern_offsets[f] (int64, n+1
+ * entries) and is consumed in the reference's call order (pyx:92-93,:101-102).
+ * pattern == NULL selects on-device pattern generation instead: value = hash(rng_seed, frame, stream position) & 255
+ * (counter based, no pattern memory; pattern_offsets may then be NULL too).
+ * n_hints_out: int32 [n] device, may be NULL. */
+size_t vppb200_vpp_workspace_bytes(int H, int W, int C, int n);
+int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                         int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                         int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                         uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream);
+
+/* virtual_projection_scan_max_dist(l, r, g, width, height, channels, uniform_color, wsize, wsize_agg_x, wsize_agg_y,
+ *                                  direction, c, c_occ, g_occ, discard_occluded, interpolate) -> #hints  pyx:133-341 */
+int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                              int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                              const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
+                              int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream);
+
+/* gt_reshape(gt f32[H,W]) -> f32[N,4] = (x, y, d, 1) in raster order           vpp_core_opt.pyx:352-371.
+ * out must hold W*H rows; count_out int32 [1] device. */
+int vppb200_gt_reshape(const float *gt, int W, int H, float *out, int32_t *count_out, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* ---- hand-off to the networks (test.py:179-200): uint8 [n][H][W][C] -> float32 [n][C][H+pt+pb][W+pl+pr],
+ * value = float32(u8 / 255.0) (test.py:179-180), replicate padding as F.pad(..., mode='replicate') (test.py:192-197). */
+int vppb200_u8hwc_to_f32chw(const uint8_t *src, float *dst, int H, int W, int C, int pad_top, int pad_bottom,
+                            int pad_left, int pad_right, int n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPPSTEREO_B200_H */

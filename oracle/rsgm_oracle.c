@@ -489,15 +489,18 @@ ORC_API void orc_interpolate_background(float *dmap, int W, int H)
     }
 }
 
-/* _guided_dsi rsgm.py:115-127: dsi[y,x,:] = (uint16)( (double)dsi * k*(1-exp(-(h-d)^2/(2c^2))) ), k=10, c=1 */
+/* _guided_dsi rsgm.py:115-127.  numba fuses `k * (1-np.exp((-(hints[y,x]-np.arange(dmax))**2)/(2*c**2)))` into one
+ * element loop evaluated in float64 whose RESULT ARRAY is float32 (float32 scalar with int64 array), verified against
+ * numba 0.65: the weight is rounded to float32 once, then multiplies the float64 cost; the cast back to uint16
+ * truncates (k=10, c=1). */
 ORC_API void orc_guided_dsi(uint16_t *dsi, const float *hints, const float *valid, int W, int H, int D)
 {
     for (size_t p = 0; p < (size_t)W * H; p++)
         if (valid[p] > 0)
             for (int d = 0; d < D; d++) {
                 double t = (double)hints[p] - (double)d;
-                double w = 10.0 * (1.0 - exp(-(t * t) / 2.0));
-                dsi[p * D + d] = (uint16_t)((double)dsi[p * D + d] * w);
+                float w = (float)(10.0 * (1.0 - exp(-(t * t) / 2.0)));
+                dsi[p * D + d] = (uint16_t)((double)dsi[p * D + d] * (double)w);
             }
 }
 

@@ -1,0 +1,122 @@
+"""CPU: host-side logic -- the C-ABI library loads and exports every symbol the header declares, the reference-shaped
+front-ends validate arguments exactly like the reference wrapper (before touching any device), compute calls fail loudly
+without a GPU (there is no CPU fallback), and frame sharding covers every frame exactly once."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_header_symbols():
+    from vppstereo_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "vppstereo_b200.h")).read()
+    declared = set(re.findall(r"\b(vppb200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), f"{s} not exported"
+    lib.vppb200_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.vppb200_version()
+
+
+def test_no_torch_types_in_header():
+    header = open(os.path.join(ROOT, "include", "vppstereo_b200.h")).read()
+    assert "torch" not in header.lower() and "at::" not in header and "#include <cuda" not in header
+
+
+def test_status_codes_without_gpu():
+    """validation happens before any CUDA call, so it is testable here through the raw C ABI"""
+    from vppstereo_b200 import _lib
+    L = _lib.lib()
+    one = ctypes.c_void_p(16)         # never dereferenced: validation fails first
+    assert L.vppb200_census5x5(one, one, 24, 8, 1, None) == _lib.ERR_WIDTH
+    assert L.vppb200_cost_census5x5_xyd(one, one, one, 32, 8, 12, 1, 1, None) == _lib.ERR_DISP
+    assert L.vppb200_cost_census5x5_xyd(one, one, one, 32, 8, 264, 1, 1, None) == _lib.ERR_DISP
+    assert L.vppb200_cost_census5x5_xyd(one, one, one, 32, 8, 8, 3, 1, None) == _lib.ERR_THREADS
+    assert L.vppb200_match_wta(one, one, 32, 8, 8, ctypes.c_float(0.0), 1, None) == _lib.ERR_UNIQUENESS
+    assert L.vppb200_match_wta_right(one, one, 32, 8, 8, ctypes.c_float(1.5), 1, None) == _lib.ERR_UNIQUENESS
+    assert L.vppb200_subpixel_refine(one, one, 32, 8, 8, 2, None, 1, None) == _lib.ERR_METHOD
+    assert L.vppb200_census5x5(None, one, 32, 8, 1, None) == _lib.ERR_ARG
+    assert L.vppb200_compute_rsgm(one, one, one, None, None, one, 8, 32, 3, 12, 1, None, None, ctypes.c_size_t(0), 1, None) == _lib.ERR_DISP
+    assert L.vppb200_compute_rsgm(one, one, one, None, None, one, 8, 32, 3, 16, 1, None, None, ctypes.c_size_t(0), 1, None) == _lib.ERR_WORKSPACE
+    assert L.vppb200_rsgm_workspace_bytes(375, 1242, 3, 192, 1) > 2 * 1248 * 384 * 192
+    assert L.vppb200_vpp_workspace_bytes(375, 1242, 3, 1) >= 2 * 375 * 1242
+
+
+def test_front_end_errors_match_reference():
+    from vppstereo_b200 import pyrSGM, rsgm, vpp_standalone
+    z8, z32 = np.zeros((8, 24), np.uint8), np.zeros((8, 24), np.uint32)
+    with pytest.raises(TypeError, match="multiple of 16"):
+        pyrSGM.census5x5_SSE(z8, z32, 24, 8)
+    with pytest.raises(TypeError, match="multiple of 16"):
+        pyrSGM.median3x3_SSE(z8.astype(np.float32), z8.astype(np.float32), 24, 8)
+    a32 = np.zeros((8, 32), np.uint32)
+    with pytest.raises(TypeError, match="multiple of 8"):
+        pyrSGM.costMeasureCensus5x5_xyd_SSE(a32, a32, np.zeros((8, 32, 12), np.uint16), 32, 8, 12, 1)
+    with pytest.raises(TypeError, match="NumThreads"):
+        pyrSGM.costMeasureCensus5x5_xyd_SSE(a32, a32, np.zeros((8, 32, 8), np.uint16), 32, 8, 8, 8)
+    with pytest.raises(TypeError, match="Uniqueness"):
+        pyrSGM.matchWTARight_SSE(np.zeros((8, 32, 8), np.uint16), np.zeros((8, 32), np.float32), 32, 8, 8, 0.0)
+    with pytest.raises(TypeError, match="method"):
+        pyrSGM.subPixelRefine(np.zeros((8, 32, 8), np.uint16), np.zeros((8, 32), np.float32), 32, 8, 8, 5)
+    img = np.zeros((20, 30, 3), np.uint8)
+    with pytest.raises(Exception, match="dmax % 8"):
+        rsgm.compute_rsgm(img, img, img, dmax=100)                       # models/rsgm/rsgm.py:31-32
+    with pytest.raises(Exception, match="dmax > 256"):
+        rsgm.compute_rsgm(img, img, img, dmax=512)                       # models/rsgm/rsgm.py:34-35
+    with pytest.raises(AssertionError):
+        vpp_standalone.vpp(img, img, np.zeros((20, 30), np.float32), method="nope")
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    from vppstereo_b200 import rsgm, vpp_standalone, pyrSGM
+    img = np.zeros((20, 32, 3), np.uint8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rsgm.compute_rsgm(img, img, img, dmax=16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vpp_standalone.vpp(img, img, np.ones((20, 32), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pyrSGM.census5x5_SSE(np.zeros((8, 32), np.uint8), np.zeros((8, 32), np.uint32), 32, 8)
+
+
+def test_product_never_imports_oracle():
+    """the oracle is test infrastructure: nothing under vppstereo_b200/ may reference it"""
+    pkg = os.path.join(ROOT, "vppstereo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_shard_ranges_cover_all_frames():
+    from vppstereo_b200 import dist
+    for n in (1, 7, 64, 1024, 1000):
+        for world in (1, 2, 3, 4, 8):
+            if n < world:
+                continue
+            ranges = [dist.shard_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1 and sizes == dist.shard_sizes(n, world)
+    assert dist.chunks(3, 20, 8) == [(3, 11), (11, 19), (19, 20)]
+
+
+def test_glibc_generator_state_continues():
+    """consecutive scans keep consuming one stream, like the process-global libc state (vpp_core_opt.pyx:33-35)"""
+    from vppstereo_b200 import vpp_core_opt as core
+    core.init_rand(42); a = core.draw_pattern(1000)
+    core.init_rand(42); b = np.concatenate([core.draw_pattern(300), core.draw_pattern(700)])
+    assert np.array_equal(a, b)
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(42)
+    assert np.array_equal(a[:64], np.array([libc.rand() % 256 for _ in range(64)], np.uint8))

@@ -1,0 +1,383 @@
+// capi.cu -- extern "C" entry points of include/vppstereo_b200.h: argument validation (mirroring the TypeError classes of
+// the reference wrapper RSGM/pyrSGM.cpp), workspace carving and the compute_rsgm stage pipeline
+// (models/rsgm/rsgm.py:250-294).  The VPP entry points live in vpp.cu.
+#include "common.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <xmmintrin.h>
+
+namespace vppb200 {
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[256] = "";
+
+void note_launch(int k) { g_launches.fetch_add((uint64_t)k, std::memory_order_relaxed); }
+
+int cuda_fail(const char *what, cudaError_t e)
+{
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return VPPB200_ERR_CUDA;
+}
+
+int launch_wta_both_subpix(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int n, cudaStream_t st);
+
+// rcp_nz_ss(-2k) on this host's CPU (RSGM/StereoBMHelper.cpp:752-756): RCPSS is a vendor-specific table instruction, so the
+// table is produced by the instruction itself and uploaded once per device.
+static void fill_rcp_lut(float *lut)
+{
+    lut[0] = 0.0f;
+    for (int k = 1; k < 65536; k++) lut[k] = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(2.0f * (float)(-k))));
+}
+
+static std::mutex g_lut_mutex;
+static float *g_dev_lut[64] = {nullptr};
+
+const float *device_rcp_lut(cudaStream_t st)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_lut_mutex);
+    if (!g_dev_lut[dev]) {
+        static float host[65536];
+        fill_rcp_lut(host);
+        float *d = nullptr;
+        if (cudaMalloc(&d, sizeof host) != cudaSuccess) return nullptr;
+        // synchronous one-time upload: the host table is static and the copy must be complete before first use
+        if (cudaMemcpy(d, host, sizeof host, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+        g_dev_lut[dev] = d;
+    }
+    (void)st;
+    return g_dev_lut[dev];
+}
+
+// ---- optional per-stage timing of compute_rsgm (bench.py's live roofline measurement) ----------------------------
+struct StageTimer {
+    bool enabled = false;
+    std::vector<cudaEvent_t> pending;      // groups of N_STAGES+1 events, one group per timed call
+    double acc[VPPB200_N_STAGES] = {0};
+    int calls = 0;
+};
+static StageTimer g_timer;
+static std::mutex g_timer_mutex;
+
+struct StageMarks {
+    cudaEvent_t ev[VPPB200_N_STAGES + 1];
+    bool on = false;
+    cudaStream_t st;
+    int next = 0;
+    void begin(cudaStream_t s)
+    {
+        std::lock_guard<std::mutex> lock(g_timer_mutex);
+        on = g_timer.enabled;
+        st = s;
+        if (!on) return;
+        for (auto &e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[next++], st);
+    }
+    void mark() { if (on && next <= VPPB200_N_STAGES) cudaEventRecord(ev[next++], st); }
+    void end()
+    {
+        if (!on) return;
+        std::lock_guard<std::mutex> lock(g_timer_mutex);
+        for (auto &e : ev) g_timer.pending.push_back(e);
+    }
+};
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct RsgmWs {
+    uint8_t *gray_l, *gray_r, *guide;
+    uint32_t *census_l, *census_r;
+    uint8_t *dsi;
+    uint16_t *S;
+    float *dl, *dlf, *dr, *drf;
+    TailBufs tail;
+};
+
+static size_t rsgm_ws_layout(const RsgmDims &d, int n, void *base, RsgmWs *ws)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? b + o : (char *)nullptr; };
+    const size_t np = (size_t)n * d.Hp * d.Wp, nc = (size_t)n * d.H * d.W;
+    RsgmWs w;
+    w.gray_l = (uint8_t *)take(np); w.gray_r = (uint8_t *)take(np); w.guide = (uint8_t *)take(np);
+    w.census_l = (uint32_t *)take(np * 4); w.census_r = (uint32_t *)take(np * 4);
+    w.dsi = (uint8_t *)take(np * d.D);
+    w.S = (uint16_t *)take(np * d.D * 2);
+    w.dl = (float *)take(np * 4); w.dlf = (float *)take(np * 4); w.dr = (float *)take(np * 4); w.drf = (float *)take(np * 4);
+    w.tail.u8 = (uint8_t *)take(nc); w.tail.label = (int *)take(nc * 4); w.tail.count = (int *)take(nc * 4);
+    if (ws) *ws = w;
+    return off;
+}
+
+}  // namespace vppb200
+
+using namespace vppb200;
+
+extern "C" const char *vppb200_version(void) { return "vppstereo_b200 0.1.0 (sm_100a)"; }
+extern "C" const char *vppb200_last_cuda_error(void) { return g_err; }
+extern "C" uint64_t vppb200_launch_count(void) { return g_launches.load(); }
+
+extern "C" int vppb200_rcp_lut_host(float *lut_host)
+{
+    if (!lut_host) return VPPB200_ERR_ARG;
+    fill_rcp_lut(lut_host);
+    return VPPB200_OK;
+}
+
+// glibc TYPE_3 random(): r[i] = r[i-3] + r[i-31] (mod 2^32), output r[i] >> 1.  state34 = the 31-word ring + cursor.
+extern "C" int vppb200_glibc_srand(uint32_t *st, uint32_t seed)
+{
+    if (!st) return VPPB200_ERR_ARG;
+    int32_t r[34];
+    r[0] = seed == 0 ? 1 : (int32_t)seed;
+    for (int i = 1; i < 31; i++) {
+        const int64_t hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        int64_t word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        r[i] = (int32_t)word;
+    }
+    uint32_t ring[31];
+    for (int i = 0; i < 31; i++) ring[i] = (uint32_t)r[i];
+    // ring is indexed modulo 31; position k holds r[k], next output index is 31 (i.e. slot 0), f = i-3, r = i-31
+    for (int i = 0; i < 31; i++) st[i] = ring[i];
+    st[31] = 0;    // cursor: slot of r[i-31] == slot to overwrite with r[i]
+    st[32] = st[33] = 0;
+    uint8_t sink[310];
+    // srandom discards 310 outputs; the first 3 steps of the textbook description (r[31..33] = r[i-31]) are the same
+    // additive step because glibc starts with fptr = &r[3], rptr = &r[0]:  r[3] += r[0] ...
+    // -> use the generic step from the start with the glibc pointer layout.
+    st[31] = 0;
+    return vppb200_glibc_rand_fill(st, sink, -310);
+}
+
+extern "C" int vppb200_glibc_rand_fill(uint32_t *st, uint8_t *out, int64_t n)
+{
+    if (!st) return VPPB200_ERR_ARG;
+    const bool discard = n < 0;
+    if (discard) n = -n;
+    if (!discard && !out && n > 0) return VPPB200_ERR_ARG;
+    uint32_t cur = st[31];            // rptr slot; fptr slot = (cur + 3) % 31
+    for (int64_t k = 0; k < n; k++) {
+        const uint32_t f = (cur + 3) % 31;
+        st[f] += st[cur];
+        const uint32_t result = st[f] >> 1;
+        if (!discard) out[k] = (uint8_t)(result % 256u);
+        cur = (cur + 1) % 31;
+    }
+    st[31] = cur;
+    return VPPB200_OK;
+}
+
+extern "C" int vppb200_stage_timing(int enable)
+{
+    std::lock_guard<std::mutex> lock(g_timer_mutex);
+    for (auto &e : g_timer.pending) cudaEventDestroy(e);
+    g_timer.pending.clear();
+    for (auto &a : g_timer.acc) a = 0;
+    g_timer.calls = 0;
+    g_timer.enabled = enable != 0;
+    return VPPB200_OK;
+}
+
+extern "C" int vppb200_stage_times(float *ms_out, int *calls_out)
+{
+    if (!ms_out) return VPPB200_ERR_ARG;
+    std::lock_guard<std::mutex> lock(g_timer_mutex);
+    const size_t group = VPPB200_N_STAGES + 1;
+    for (size_t g = 0; g + group <= g_timer.pending.size(); g += group) {
+        VPP_CUDA_TRY(cudaEventSynchronize(g_timer.pending[g + group - 1]));
+        for (int s = 0; s < VPPB200_N_STAGES; s++) {
+            float ms = 0;
+            VPP_CUDA_TRY(cudaEventElapsedTime(&ms, g_timer.pending[g + s], g_timer.pending[g + s + 1]));
+            g_timer.acc[s] += ms;
+        }
+        g_timer.calls++;
+    }
+    for (auto &e : g_timer.pending) cudaEventDestroy(e);
+    g_timer.pending.clear();
+    for (int s = 0; s < VPPB200_N_STAGES; s++) ms_out[s] = (float)g_timer.acc[s];
+    if (calls_out) *calls_out = g_timer.calls;
+    return VPPB200_OK;
+}
+
+static int check_wd(int W, int H, int D, int n)
+{
+    if (W <= 0 || H <= 0 || n <= 0) return VPPB200_ERR_ARG;
+    if (W % 16 != 0) return VPPB200_ERR_WIDTH;
+    if (D >= 0 && (D <= 0 || D % 8 != 0 || D > 256)) return VPPB200_ERR_DISP;
+    return VPPB200_OK;
+}
+
+extern "C" int vppb200_census5x5(const uint8_t *src, uint32_t *dst, int W, int H, int n, void *stream)
+{
+    int rc = check_wd(W, H, -1, n);
+    if (rc) return rc;
+    if (!src || !dst) return VPPB200_ERR_ARG;
+    return launch_census(src, dst, W, H, n, (cudaStream_t)stream);
+}
+
+extern "C" int vppb200_cost_census5x5_xyd(const uint32_t *cl, const uint32_t *cr, uint16_t *dsi, int W, int H, int D,
+                                          int num_threads, int n, void *stream)
+{
+    int rc = check_wd(W, H, D, n);
+    if (rc) return rc;
+    if (num_threads != 1 && num_threads != 2 && num_threads != 4) return VPPB200_ERR_THREADS;
+    if (!cl || !cr || !dsi) return VPPB200_ERR_ARG;
+    return launch_cost_u16(cl, cr, dsi, W, H, D, n, (cudaStream_t)stream);
+}
+
+extern "C" int vppb200_aggregate(const uint8_t *img, const uint16_t *dsi, uint16_t *dsi_agg, int W, int H, int D, int P1,
+                                 int P2min, float alpha, int gamma, int honor_params, int n, void *stream)
+{
+    int rc = check_wd(W, H, D, n);
+    if (rc) return rc;
+    if (!img || !dsi || !dsi_agg || H < 3) return VPPB200_ERR_ARG;
+    if (!honor_params) { P1 = 7; P2min = 17; alpha = 0.25f; gamma = 50; }    // RSGM/pyrSGM.cpp:519 vs :557-560
+    return launch_aggregate_generic(img, dsi, dsi_agg, W, H, D, P1, P2min, alpha, gamma, n, (cudaStream_t)stream);
+}
+
+static int check_uniq(float u) { return (u > 1.0f || u <= 0.0f) ? VPPB200_ERR_UNIQUENESS : VPPB200_OK; }
+
+extern "C" int vppb200_match_wta(const uint16_t *S, float *disp, int W, int H, int D, float uniqueness, int n, void *stream)
+{
+    int rc = check_wd(W, H, D, n);
+    if (rc) return rc;
+    if ((rc = check_uniq(uniqueness))) return rc;
+    if (!S || !disp) return VPPB200_ERR_ARG;
+    return launch_wta_left(S, disp, W, H, D, n, (cudaStream_t)stream);
+}
+
+extern "C" int vppb200_match_wta_right(const uint16_t *S, float *disp, int W, int H, int D, float uniqueness, int n, void *stream)
+{
+    int rc = check_wd(W, H, D, n);
+    if (rc) return rc;
+    if ((rc = check_uniq(uniqueness))) return rc;
+    if (!S || !disp) return VPPB200_ERR_ARG;
+    return launch_wta_right(S, disp, W, H, D, n, (cudaStream_t)stream);
+}
+
+extern "C" int vppb200_subpixel_refine(const uint16_t *dsi, float *disp, int W, int H, int D, int method, const float *rcp_lut,
+                                       int n, void *stream)
+{
+    int rc = check_wd(W, H, D, n);
+    if (rc) return rc;
+    if (method != 0 && method != 1) return VPPB200_ERR_METHOD;
+    if (!dsi || !disp) return VPPB200_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!rcp_lut) rcp_lut = device_rcp_lut(st);
+    if (!rcp_lut) return cuda_fail("device_rcp_lut", cudaGetLastError());
+    return launch_subpixel(dsi, disp, W, H, D, method, rcp_lut, n, st);
+}
+
+extern "C" int vppb200_median3x3(const float *src, float *dst, int W, int H, int n, void *stream)
+{
+    int rc = check_wd(W, H, -1, n);
+    if (rc) return rc;
+    if (!src || !dst) return VPPB200_ERR_ARG;
+    return launch_median(src, dst, W, H, n, (cudaStream_t)stream);
+}
+
+extern "C" size_t vppb200_rsgm_workspace_bytes(int H, int W, int C, int D, int n)
+{
+    if (H <= 0 || W <= 0 || n <= 0 || D <= 0 || D % 8 || D > 256 || (C != 1 && C != 3)) return 0;
+    return rsgm_ws_layout(make_dims(H, W, C, D), n, nullptr, nullptr);
+}
+
+extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp,
+                                           const float *hints, const float *validhints, float *disp_out, int H, int W, int C,
+                                           int D, int flags, const float *rcp_lut, void *workspace, size_t workspace_bytes,
+                                           int n, void *stream, const vppb200_rsgm_taps *taps)
+{
+    if (H <= 0 || W <= 0 || n <= 0 || (C != 1 && C != 3)) return VPPB200_ERR_ARG;
+    if (D <= 0 || D % 8 != 0 || D > 256) return VPPB200_ERR_DISP;      // models/rsgm/rsgm.py:31-35
+    if (!left || !left_vpp || !right_vpp || !disp_out) return VPPB200_ERR_ARG;
+    if ((hints == nullptr) != (validhints == nullptr)) return VPPB200_ERR_ARG;
+    const RsgmDims d = make_dims(H, W, C, D);
+    if (d.Hp < 8) return VPPB200_ERR_ARG;
+    if (!workspace || workspace_bytes < rsgm_ws_layout(d, n, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!rcp_lut) rcp_lut = device_rcp_lut(st);
+    if (!rcp_lut) return cuda_fail("device_rcp_lut", cudaGetLastError());
+    RsgmWs w;
+    rsgm_ws_layout(d, n, workspace, &w);
+    int rc;
+    StageMarks tm;
+    tm.begin(st);
+    // rsgm.py:258-262  pad (BORDER_REFLECT) + RGB2GRAY; the P2 guide is the raw byte stream of the padded `left`
+    if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, n, st))) return rc;
+    if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, st))) return rc;
+    if ((rc = launch_pad_flatbytes(left, w.guide, d, n, st))) return rc;
+    tm.mark();
+    if ((rc = launch_census(w.gray_l, w.census_l, d.Wp, d.Hp, n, st))) return rc;
+    if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, st))) return rc;
+    tm.mark();
+    // rsgm.py:263-268  Hamming volume (+ optional guided modulation)
+    if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
+    if (hints && (rc = launch_guided_u8(w.dsi, hints, validhints, d, n, st))) return rc;
+    tm.mark();
+    // rsgm.py:270  8-path aggregation (effective default parameters)
+    if ((rc = launch_aggregate_fast(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc;
+    tm.mark();
+    // rsgm.py:272-273  WTA left (+ equiangular sub-pixel) and right, median, gap interpolation, clip
+    if ((rc = launch_wta_both_subpix(w.S, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, n, st))) return rc;
+    tm.mark();
+    if ((rc = launch_median(w.dl, w.dlf, d.Wp, d.Hp, n, st))) return rc;
+    if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, st))) return rc;
+    if ((rc = launch_interp_clip(w.dlf, d.Wp, d.Hp, n, st))) return rc;
+    if ((rc = launch_interp_clip(w.drf, d.Wp, d.Hp, n, st))) return rc;
+    tm.mark();
+    // rsgm.py:275-292  crop, LR check, speckle filter, sub-pixel restore, background fill
+    if ((rc = launch_tail(w.dlf, w.drf, disp_out, d, flags & 1, w.tail, n, st))) return rc;
+    tm.mark();
+    tm.end();
+    if (taps) {
+        const size_t np = (size_t)n * d.Hp * d.Wp;
+        if (taps->census_l) VPP_CUDA_TRY(cudaMemcpyAsync(taps->census_l, w.census_l, np * 4, cudaMemcpyDeviceToDevice, st));
+        if (taps->census_r) VPP_CUDA_TRY(cudaMemcpyAsync(taps->census_r, w.census_r, np * 4, cudaMemcpyDeviceToDevice, st));
+        if (taps->dsi_agg) VPP_CUDA_TRY(cudaMemcpyAsync(taps->dsi_agg, w.S, np * D * 2, cudaMemcpyDeviceToDevice, st));
+        if (taps->disp_l) VPP_CUDA_TRY(cudaMemcpyAsync(taps->disp_l, w.dlf, np * 4, cudaMemcpyDeviceToDevice, st));
+        if (taps->disp_r) VPP_CUDA_TRY(cudaMemcpyAsync(taps->disp_r, w.drf, np * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return VPPB200_OK;
+}
+
+extern "C" int vppb200_compute_rsgm(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp, const float *hints,
+                                    const float *validhints, float *disp_out, int H, int W, int C, int D, int flags,
+                                    const float *rcp_lut, void *workspace, size_t workspace_bytes, int n, void *stream)
+{
+    return vppb200_compute_rsgm_tapped(left, left_vpp, right_vpp, hints, validhints, disp_out, H, W, C, D, flags, rcp_lut,
+                                       workspace, workspace_bytes, n, stream, nullptr);
+}
+
+// ---- hand-off to the networks (test.py:179-197) -----------------------------------------------------------
+namespace vppb200 {
+__global__ void u8hwc_to_f32chw_kernel(const uint8_t *__restrict__ src, float *__restrict__ dst, int H, int W, int C, int pt,
+                                       int pl, int Ho, int Wo, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = (int)(t % Wo), y = (int)((t / Wo) % Ho), c = (int)((t / ((long)Wo * Ho)) % C);
+    const long f = t / ((long)Wo * Ho * C);
+    const int sy = min(max(y - pt, 0), H - 1), sx = min(max(x - pl, 0), W - 1);       // replicate
+    const uint8_t v = src[((f * H + sy) * W + sx) * C + c];
+    dst[t] = (float)__ddiv_rn((double)v, 255.0);                                       // float32(u8 / 255.0)
+}
+}  // namespace vppb200
+
+extern "C" int vppb200_u8hwc_to_f32chw(const uint8_t *src, float *dst, int H, int W, int C, int pad_top, int pad_bottom,
+                                       int pad_left, int pad_right, int n, void *stream)
+{
+    if (!src || !dst || H <= 0 || W <= 0 || C <= 0 || n <= 0 || pad_top < 0 || pad_bottom < 0 || pad_left < 0 || pad_right < 0)
+        return VPPB200_ERR_ARG;
+    const int Ho = H + pad_top + pad_bottom, Wo = W + pad_left + pad_right;
+    const long total = (long)n * C * Ho * Wo;
+    u8hwc_to_f32chw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C, pad_top, pad_left, Ho, Wo, total);
+    VPP_LAUNCH_CHECK("u8hwc_to_f32chw_kernel");
+    return VPPB200_OK;
+}

@@ -1,0 +1,65 @@
+// common.cuh -- shared helpers for the sm_100a kernels behind include/vppstereo_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vppstereo_b200.h"
+
+namespace vppb200 {
+
+// kernel-launch accounting (vppb200_launch_count) and CUDA error capture (vppb200_last_cuda_error)
+void note_launch(int k = 1);
+int cuda_fail(const char *what, cudaError_t e);
+
+#define VPP_CUDA_TRY(expr)                                              \
+    do {                                                                \
+        cudaError_t _e = (expr);                                        \
+        if (_e != cudaSuccess) return ::vppb200::cuda_fail(#expr, _e);  \
+    } while (0)
+
+// check the launch that was just issued
+#define VPP_LAUNCH_CHECK(name)                                          \
+    do {                                                                \
+        ::vppb200::note_launch();                                       \
+        cudaError_t _e = cudaGetLastError();                            \
+        if (_e != cudaSuccess) return ::vppb200::cuda_fail(name, _e);   \
+    } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+struct RsgmDims {
+    int H, W, C, D;        // user frame
+    int pl, pr, pt, pb;    // BORDER_REFLECT padding to multiples of 16 (models/rsgm/rsgm.py:254-256)
+    int Hp, Wp;
+};
+
+static inline RsgmDims make_dims(int H, int W, int C, int D)
+{
+    RsgmDims d;
+    d.H = H; d.W = W; d.C = C; d.D = D;
+    int pad_h = (((H / 16) + 1) * 16 - H) % 16, pad_w = (((W / 16) + 1) * 16 - W) % 16;
+    d.pl = pad_w / 2; d.pr = pad_w - d.pl; d.pt = pad_h / 2; d.pb = pad_h - d.pt;
+    d.Hp = H + pad_h; d.Wp = W + pad_w;
+    return d;
+}
+
+// ---- stage launchers (defined in the .cu files, all asynchronous on `st`) -------------------------------
+int launch_pad_gray(const uint8_t *src, uint8_t *gray, const RsgmDims &d, int n, cudaStream_t st);
+int launch_pad_flatbytes(const uint8_t *src, uint8_t *guide, const RsgmDims &d, int n, cudaStream_t st);
+int launch_census(const uint8_t *src, uint32_t *dst, int W, int H, int n, cudaStream_t st);
+int launch_cost_u16(const uint32_t *cl, const uint32_t *cr, uint16_t *dsi, int W, int H, int D, int n, cudaStream_t st);
+int launch_cost_u8(const uint32_t *cl, const uint32_t *cr, uint8_t *dsi, int W, int H, int D, int n, cudaStream_t st);
+int launch_guided_u8(uint8_t *dsi, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st);
+// generic (saturating, u16 cost) and fast (u8 cost, default params) 8-path aggregation
+int launch_aggregate_generic(const uint8_t *img, const uint16_t *dsi, uint16_t *S, int W, int H, int D, int P1, int P2min,
+                             float alpha, int gamma, int n, cudaStream_t st);
+int launch_aggregate_fast(const uint8_t *img, const uint8_t *dsi, uint16_t *S, int W, int H, int D, int n, cudaStream_t st);
+int launch_wta_left(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st);
+int launch_wta_right(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st);
+int launch_subpixel(const uint16_t *S, float *disp, int W, int H, int D, int method, const float *lut, int n, cudaStream_t st);
+int launch_median(const float *src, float *dst, int W, int H, int n, cudaStream_t st);
+int launch_interp_clip(float *disp, int W, int H, int n, cudaStream_t st);   // _linear_interpolate(.,15,3) + clip>=0
+struct TailBufs { uint8_t *u8; int *label; int *count; };
+int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d, int subpixel, TailBufs tb, int n, cudaStream_t st);
+const float *device_rcp_lut(cudaStream_t st);   // library-owned table for this host CPU (lazy, per device)
+
+}  // namespace vppb200

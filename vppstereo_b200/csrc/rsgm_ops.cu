@@ -1,0 +1,594 @@
+// rsgm_ops.cu -- sm_100a kernels for every rSGM stage except the SGM aggregation itself (sgm.cu):
+// padding + gray, 5x5 census, Hamming cost volume, WTA left/right (+ fused sub-pixel), median, gap interpolation,
+// left-right check, speckle filter (connected components), background fill.
+// Reference semantics: SURVEY.md Appendix A; file:line citations are relative to the reference root,
+// RSGM/ = thirdparty/stereo-vision/reconstruction/base/rSGM/.  Compiled with -fmad=false (no FMA contraction).
+#include "common.cuh"
+
+namespace vppb200 {
+
+// ------------------------------------------------------------------------------------------------------------
+// padding (cv2.copyMakeBorder BORDER_REFLECT, models/rsgm/rsgm.py:258-260) fused with RGB2GRAY (rsgm.py:11-12)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p - 1 : 2 * len - 1 - p;
+    return p;
+}
+
+// gray[n][Hp][Wp]; OpenCV 4.13 RGB2GRAY = (R*9798 + G*19235 + B*3735 + 16384) >> 15
+__global__ void pad_gray_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ gray, RsgmDims d, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = (int)(t % d.Wp), y = (int)((t / d.Wp) % d.Hp);
+    const long f = t / ((long)d.Wp * d.Hp);
+    const int sy = reflect_idx(y - d.pt, d.H), sx = reflect_idx(x - d.pl, d.W);
+    const uint8_t *p = src + ((f * d.H + sy) * d.W + sx) * d.C;
+    uint32_t v;
+    if (d.C == 3) v = (p[0] * 9798u + p[1] * 19235u + p[2] * 3735u + 16384u) >> 15;
+    else v = p[0];
+    gray[t] = (uint8_t)v;
+}
+
+// guide[n][Hp*Wp] = the first Hp*Wp BYTES of the padded interleaved image (RSGM/pyrSGM.cpp:586-588 reads a colour
+// buffer as if it were gray).
+__global__ void pad_flatbytes_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ guide, RsgmDims d, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long np = (long)d.Wp * d.Hp;
+    const long f = t / np;
+    const long b = t % np;                     // byte index inside the padded interleaved buffer
+    const long px = b / d.C;
+    const int ch = (int)(b % d.C);
+    const int x = (int)(px % d.Wp), y = (int)(px / d.Wp);
+    const int sy = reflect_idx(y - d.pt, d.H), sx = reflect_idx(x - d.pl, d.W);
+    guide[t] = src[((f * d.H + sy) * d.W + sx) * d.C + ch];
+}
+
+int launch_pad_gray(const uint8_t *src, uint8_t *gray, const RsgmDims &d, int n, cudaStream_t st)
+{
+    long total = (long)n * d.Hp * d.Wp;
+    pad_gray_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, gray, d, total);
+    VPP_LAUNCH_CHECK("pad_gray_kernel");
+    return VPPB200_OK;
+}
+int launch_pad_flatbytes(const uint8_t *src, uint8_t *guide, const RsgmDims &d, int n, cudaStream_t st)
+{
+    long total = (long)n * d.Hp * d.Wp;
+    pad_flatbytes_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, guide, d, total);
+    VPP_LAUNCH_CHECK("pad_flatbytes_kernel");
+    return VPPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// census5x5  (RSGM/FastFilters.cpp:181-442).  The image is a flat byte stream: neighbours of the first/last two
+// columns wrap into the adjacent rows.  One thread produces 4 adjacent codes from 5 x 8 staged bytes.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t census_sse_order(const uint8_t (&win)[5][8], int o)
+{
+    // neighbours k = 0..23 in raster order, bit position 8*(k/8) + (7 - k%8)   (:273-281,:320-328,:352-359)
+    const uint32_t c = win[2][o + 2];
+    uint32_t v = 0;
+    int k = 0;
+#pragma unroll
+    for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 5; dx++) {
+            if (dy == 2 && dx == 2) continue;
+            v |= (uint32_t)(win[dy][o + dx] < c) << (8 * (k / 8) + (7 - k % 8));
+            k++;
+        }
+    return v;
+}
+__device__ __forceinline__ uint32_t census_tail_order(const uint8_t (&win)[5][8], int o)
+{
+    // scalar tail (:424-441): value = sum bit_k * 2^(23-k)
+    const uint32_t c = win[2][o + 2];
+    uint32_t v = 0;
+#pragma unroll
+    for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 5; dx++) {
+            if (dy == 2 && dx == 2) continue;
+            v = v * 2 + (uint32_t)(c > win[dy][o + dx]);
+        }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) census5x5_kernel(const uint8_t *__restrict__ src, uint32_t *__restrict__ dst, int W,
+                                                        int H, long quads_per_frame, long total_quads)
+{
+    long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total_quads) return;
+    const long f = q / quads_per_frame;
+    const long c0 = (q % quads_per_frame) * 4;         // flat index of the first of 4 centres (W % 16 == 0 => same row)
+    const long n = (long)W * H;
+    const uint8_t *img = src + f * n;
+    const long lo = 2L * W + 2, hi = (long)W * (H - 2) - 17;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    const int row = (int)(c0 / W), col = (int)(c0 % W);
+    const bool any_body = (c0 + 3 >= lo) && (c0 <= hi);
+    const bool tail_row = (row == H - 3) && (col >= W - 16);
+    if (any_body || tail_row) {
+        uint8_t win[5][8];
+#pragma unroll
+        for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 8; dx++) {
+                long a = c0 + (long)(dy - 2) * W + (dx - 2);     // flat neighbour, may wrap across row ends
+                win[dy][dx] = (a >= 0 && a < n) ? img[a] : 0;
+            }
+        uint32_t r[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            const long c = c0 + o;
+            const int cc = col + o;
+            if (c >= lo && c <= hi) r[o] = census_sse_order(win, o);
+            else if (row == H - 3 && cc >= W - 14 && cc <= W - 3) r[o] = census_tail_order(win, o);
+            else r[o] = 0;
+        }
+        out = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    reinterpret_cast<uint4 *>(dst + f * n)[c0 / 4] = out;
+}
+
+int launch_census(const uint8_t *src, uint32_t *dst, int W, int H, int n, cudaStream_t st)
+{
+    long qpf = (long)W * H / 4, total = qpf * n;
+    census5x5_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, dst, W, H, qpf, total);
+    VPP_LAUNCH_CHECK("census5x5_kernel");
+    return VPPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Hamming cost volume (RSGM/StereoBMHelper.cpp:29-140): rows 0,1,H-2,H-1 and d > x hold 12, else popc(L ^ R[x-d]).
+// One thread = one pixel x 8 disparities = one 16-byte (u16) or 8-byte (u8) store.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) cost_kernel(const uint32_t *__restrict__ cl, const uint32_t *__restrict__ cr,
+                                                   T *__restrict__ dsi, int W, int H, int D, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int d8 = D / 8;
+    const int g = (int)(t % d8);
+    const long px = t / d8;                    // pixel index over all frames
+    const int x = (int)(px % W), y = (int)((px / W) % H);
+    uint32_t v[8];
+    if (y < 2 || y >= H - 2) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = 12;
+    } else {
+        const uint32_t l = cl[px];
+        const uint32_t *rrow = cr + (px - x);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int d = g * 8 + k;
+            v[k] = d > x ? 12u : (uint32_t)__popc(l ^ rrow[x - d]);
+        }
+    }
+    if (sizeof(T) == 2) {
+        uint4 o = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+        reinterpret_cast<uint4 *>(dsi)[t] = o;
+    } else {
+        uint2 o = make_uint2(v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24), v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24));
+        reinterpret_cast<uint2 *>(dsi)[t] = o;
+    }
+}
+
+int launch_cost_u16(const uint32_t *cl, const uint32_t *cr, uint16_t *dsi, int W, int H, int D, int n, cudaStream_t st)
+{
+    long total = (long)n * H * W * (D / 8);
+    cost_kernel<uint16_t><<<cdiv(total, 256), 256, 0, st>>>(cl, cr, dsi, W, H, D, total);
+    VPP_LAUNCH_CHECK("cost_kernel<u16>");
+    return VPPB200_OK;
+}
+int launch_cost_u8(const uint32_t *cl, const uint32_t *cr, uint8_t *dsi, int W, int H, int D, int n, cudaStream_t st)
+{
+    long total = (long)n * H * W * (D / 8);
+    cost_kernel<uint8_t><<<cdiv(total, 256), 256, 0, st>>>(cl, cr, dsi, W, H, D, total);
+    VPP_LAUNCH_CHECK("cost_kernel<u8>");
+    return VPPB200_OK;
+}
+
+// _guided_dsi (models/rsgm/rsgm.py:115-127) on the u8 volume: numba evaluates the weight 10*(1-exp(-(h-d)^2/2)) in float64
+// and rounds it to float32 once (fused array expression with a float32 result); dsi = (u16)((double)dsi * (double)w).
+// Costs are <= 24 so the result is <= 240 and still fits uint8.  hints/valid are un-padded [n][H][W]; the padding
+// region has validhints = 0 (BORDER_CONSTANT, rsgm.py:266-267).
+__global__ void guided_u8_kernel(uint8_t *__restrict__ dsi, const float *__restrict__ hints, const float *__restrict__ valid,
+                                 RsgmDims d, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int dd = (int)(t % d.D);
+    const long px = t / d.D;
+    const int x = (int)(px % d.Wp) - d.pl, y = (int)((px / d.Wp) % d.Hp) - d.pt;
+    const long f = px / ((long)d.Wp * d.Hp);
+    if (x < 0 || x >= d.W || y < 0 || y >= d.H) return;
+    const long s = (f * d.H + y) * d.W + x;
+    if (!(valid[s] > 0)) return;
+    const double tt = __dsub_rn((double)hints[s], (double)dd);
+    const float w = (float)__dmul_rn(10.0, __dsub_rn(1.0, exp(__ddiv_rn(-__dmul_rn(tt, tt), 2.0))));
+    dsi[t] = (uint8_t)(uint16_t)__dmul_rn((double)dsi[t], (double)w);
+}
+int launch_guided_u8(uint8_t *dsi, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st)
+{
+    long total = (long)n * d.Hp * d.Wp * d.D;
+    guided_u8_kernel<<<cdiv(total, 256), 256, 0, st>>>(dsi, hints, valid, d, total);
+    VPP_LAUNCH_CHECK("guided_u8_kernel");
+    return VPPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Winner-takes-all.  One warp sweeps one image row from x = W-1 down to 0 and reads each S[y][x][:] exactly once
+// (coalesced, lane l holds disparities [2*NW*l, 2*NW*(l+1)) ).
+//   left  (RSGM/StereoBMHelper.cpp:634-750): first arg-min over d <= min(D-1, x): min over packed (cost<<16 | d).
+//   right (:893-1015): disp_r[x] = first arg-min_k S[y][x+k][k].  A bucket per in-flight target pixel rides the lanes:
+//          at column x' slot d holds target x'-d; after absorbing S[x'][d] every bucket moves one slot down, slot 0
+//          retires to disp_r[x'].  No atomics, no re-reads.
+//   sub-pixel (method 0, :1072-1102) optionally fused into the left result.
+// ------------------------------------------------------------------------------------------------------------
+template <int NW, bool LEFT, bool RIGHT, bool SUBPIX>
+__global__ void __launch_bounds__(128) wta_rows_kernel(const uint16_t *__restrict__ S, float *__restrict__ disp_l,
+                                                       float *__restrict__ disp_r, int W, int H, int D,
+                                                       const float *__restrict__ lut, long total_rows)
+{
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int d0 = 2 * NW * lane;
+    const uint16_t *Srow = S + row * (long)W * D;
+    const bool lane_valid = d0 < D;            // D % 8 == 0 and 2*NW in {2,4,6,8}: a lane is all-valid or partly valid
+    uint32_t bucket[2 * NW];
+#pragma unroll
+    for (int k = 0; k < 2 * NW; k++) bucket[k] = 0xFFFFFFFFu;
+    const bool last_image_row = false;
+    (void)last_image_row;
+    for (int x = W - 1; x >= 0; x--) {
+        uint32_t key[2 * NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const int d = d0 + 2 * k;
+            uint32_t w = 0xFFFFFFFFu;
+            if (lane_valid && d < D) w = *reinterpret_cast<const uint32_t *>(Srow + (long)x * D + d);
+            key[2 * k] = (d < D) ? ((w << 16) | (uint32_t)d) : 0xFFFFFFFFu;
+            key[2 * k + 1] = (d + 1 < D) ? ((w & 0xFFFF0000u) | (uint32_t)(d + 1)) : 0xFFFFFFFFu;
+        }
+        if (LEFT) {
+            const int end = min(D - 1, x);
+            uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < 2 * NW; k++) m = min(m, (d0 + k <= end) ? key[k] : 0xFFFFFFFFu);
+            m = __reduce_min_sync(0xFFFFFFFFu, m);
+            if (lane == 0) {
+                const int best = (int)(m & 0xFFFFu);
+                float out = (float)best;
+                if (SUBPIX && x >= 1 && x <= W - 2) {
+                    if (best > 0) {
+                        const uint16_t *c = Srow + (long)x * D + best;      // best = D-1 reads the next pixel's d = 0
+                        const int c0 = c[-1], c1 = (int)(m >> 16), c2 = c[1];
+                        const int lower = min(c1 - c0, c1 - c2);            // <= 0
+                        out = __fadd_rn((float)best, __fmul_rn((float)(c2 - c0), lut[-lower]));
+                    } else {
+                        out = -10.0f;
+                    }
+                }
+                disp_l[row * W + x] = out;
+            }
+        }
+        if (RIGHT) {
+#pragma unroll
+            for (int k = 0; k < 2 * NW; k++) bucket[k] = min(bucket[k], key[k]);
+            if (lane == 0) disp_r[row * W + x] = (float)(bucket[0] & 0xFFFFu);
+            // shift every bucket one disparity slot down; the top slot of the warp starts a new target
+            uint32_t from_up = __shfl_down_sync(0xFFFFFFFFu, bucket[0], 1);
+            if (lane == 31) from_up = 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < 2 * NW - 1; k++) bucket[k] = bucket[k + 1];
+            bucket[2 * NW - 1] = from_up;
+        }
+    }
+}
+
+template <bool LEFT, bool RIGHT, bool SUBPIX>
+static int launch_wta_t(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int n, cudaStream_t st)
+{
+    const long rows = (long)n * H;
+    const int blocks = cdiv(rows * 32, 128);
+    const int nw = (D + 63) / 64;
+    switch (nw) {
+        case 1: wta_rows_kernel<1, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+        case 2: wta_rows_kernel<2, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+        case 3: wta_rows_kernel<3, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+        default: wta_rows_kernel<4, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+    }
+    VPP_LAUNCH_CHECK("wta_rows_kernel");
+    return VPPB200_OK;
+}
+int launch_wta_left(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st)
+{
+    return launch_wta_t<true, false, false>(S, disp, nullptr, W, H, D, nullptr, n, st);
+}
+int launch_wta_right(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st)
+{
+    return launch_wta_t<false, true, false>(S, nullptr, disp, W, H, D, nullptr, n, st);
+}
+int launch_wta_both_subpix(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int n, cudaStream_t st)
+{
+    return launch_wta_t<true, true, true>(S, dl, dr, W, H, D, lut, n, st);
+}
+
+// subPixelRefine as a stand-alone operator (RSGM/StereoBMHelper.cpp:1065-1135), one thread per pixel
+__global__ void subpixel_kernel(const uint16_t *__restrict__ S, float *__restrict__ disp, int W, int H, int D, int method,
+                                const float *__restrict__ lut, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = (int)(t % W);
+    if (x < 1 || x > W - 2) return;
+    const float v = disp[t];
+    if (v > 0.0f) {
+        const int dm = (int)v;
+        const uint16_t *c = S + t * D + dm;
+        const int c0 = c[-1], c1 = c[0], c2 = c[1];
+        if (method == 0) {
+            const int lower = min(c1 - c0, c1 - c2);
+            // lower <= 0 whenever dm is the arg-min; for arbitrary input fall back to the table's 0 entry on positives
+            const float r = lower <= 0 ? lut[-lower] : 0.0f;
+            disp[t] = __fadd_rn((float)dm, __fmul_rn((float)(c2 - c0), r));
+        } else {
+            const int a = c0 + c0 - 4 * c1 + c2 + c2, b = c0 - c2;
+            disp[t] = __fadd_rn((float)dm, __fdiv_rn((float)b, (float)a));
+        }
+    } else {
+        disp[t] = -10.0f;
+    }
+}
+int launch_subpixel(const uint16_t *S, float *disp, int W, int H, int D, int method, const float *lut, int n, cudaStream_t st)
+{
+    long total = (long)n * W * H;
+    subpixel_kernel<<<cdiv(total, 256), 256, 0, st>>>(S, disp, W, H, D, method, lut, total);
+    VPP_LAUNCH_CHECK("subpixel_kernel");
+    return VPPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// median3x3 (RSGM/FastFilters.cpp:701-757): flat-stream 3x3 median for c in [W+1, WH-W-5], copy elsewhere.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(float &a, float &b) { float t = fminf(a, b); b = fmaxf(a, b); a = t; }
+
+__global__ void median3x3_kernel(const float *__restrict__ src, float *__restrict__ dst, int W, int H, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long n = (long)W * H;
+    const long c = t % n;
+    const float *s = src + (t - c);
+    if (c < W + 1 || c > n - W - 5) { dst[t] = s[c]; return; }
+    float v0 = s[c - W - 1], v1 = s[c - W], v2 = s[c - W + 1], v3 = s[c - 1], v4 = s[c], v5 = s[c + 1], v6 = s[c + W - 1],
+          v7 = s[c + W], v8 = s[c + W + 1];
+    cswap(v1, v2); cswap(v4, v5); cswap(v7, v8);
+    cswap(v0, v1); cswap(v3, v4); cswap(v6, v7);
+    cswap(v1, v2); cswap(v4, v5); cswap(v7, v8);
+    cswap(v0, v3); cswap(v5, v8); cswap(v4, v7);
+    cswap(v3, v6); cswap(v1, v4); cswap(v2, v5);
+    cswap(v4, v7); cswap(v4, v2); cswap(v6, v4);
+    cswap(v4, v2);
+    dst[t] = v4;
+}
+int launch_median(const float *src, float *dst, int W, int H, int n, cudaStream_t st)
+{
+    long total = (long)n * W * H;
+    median3x3_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, dst, W, H, total);
+    VPP_LAUNCH_CHECK("median3x3_kernel");
+    return VPPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// _linear_interpolate(dmap, 15, 3) + np.clip(., 0, None)   (models/rsgm/rsgm.py:66-113,:148-151)
+// The scan is sequential and in place (filled pixels become anchors for later gaps): one warp owns one row, stages
+// it in shared memory, lane 0 runs the scan, the warp writes the clipped row back coalesced.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) interp_clip_kernel(float *__restrict__ disp, int W, long total_rows)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= total_rows) return;
+    float *r = smem + (size_t)warp * W;
+    float *g = disp + row * W;
+    for (int x = lane; x < W; x += 32) r[x] = g[x];
+    __syncwarp();
+    if (lane == 0) {
+        const int n = 7;
+        for (int x = 0; x < W; x++) {
+            if (r[x] <= 0) {
+                double nl = 0, nr = 0;
+                int nlx = 0, nrx = 0;
+                for (int xw = -1; xw >= -n; xw--)
+                    if (x + xw >= 0 && r[x + xw] > 0) { nl = r[x + xw]; nlx = xw; break; }
+                for (int xw = 1; xw <= n; xw++)
+                    if (x + xw < W && r[x + xw] > 0) { nr = r[x + xw]; nrx = xw; break; }
+                if (nl > 0 && nr > 0 && fabs(nl - nr) < 3.0) {
+                    const double m = __ddiv_rn(nr - nl, (double)(nrx - nlx));
+                    const double q = __dsub_rn(nl, __dmul_rn(m, (double)nlx));
+                    for (int xw = nlx; xw <= nrx; xw++) r[x + xw] = (float)__dadd_rn(__dmul_rn(m, (double)xw), q);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int x = lane; x < W; x += 32) g[x] = fmaxf(r[x], 0.0f);
+}
+int launch_interp_clip(float *disp, int W, int H, int n, cudaStream_t st)
+{
+    const long rows = (long)n * H;
+    const int wpb = 4;
+    const size_t sm = (size_t)wpb * W * sizeof(float);
+    if (sm > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(interp_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    interp_clip_kernel<<<cdiv(rows, wpb), wpb * 32, sm, st>>>(disp, W, rows);
+    VPP_LAUNCH_CHECK("interp_clip_kernel");
+    return VPPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tail of compute_rsgm on the cropped H x W frame (models/rsgm/rsgm.py:275-292)
+// ------------------------------------------------------------------------------------------------------------
+// crop + _left_right_check(th=1) + zero mask==128 + astype(uint8); also seeds the component labels
+__global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__restrict__ dr, uint8_t *__restrict__ u8,
+                                  int *__restrict__ label, int *__restrict__ count, RsgmDims d, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = (int)(t % d.W), y = (int)((t / d.W) % d.H);
+    const long f = t / ((long)d.W * d.H);
+    const float *lrow = dl + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
+    const float *rrow = dr + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
+    float v = lrow[x];
+    if (v > 0) {
+        const int dd = __float2int_rn(v);            // numba round(): half to even (rsgm.py:237)
+        const int xd = x - dd;
+        if (xd >= 0 && xd <= d.W - 1) {
+            const float r = rrow[xd];
+            if (r > 0 && fabsf(__fsub_rn(v, r)) > 1.0f) v = 0.0f;
+        } else {
+            v = 0.0f;
+        }
+    }
+    const uint8_t b = (uint8_t)v;
+    u8[t] = b;
+    label[t] = b ? (int)t : -1;
+    count[t] = 0;
+}
+
+// cv2.filterSpeckles(img, 0, 200, 10) (rsgm.py:285): 4-connected components under |a-b| <= 10 among non-zero pixels,
+// components with <= 200 pixels are zeroed.  The relation is symmetric, so union-find labelling is order independent.
+__device__ __forceinline__ int uf_find(int *L, int i)
+{
+    int p = L[i];
+    while (p != i) { i = p; p = L[i]; }
+    return i;
+}
+__device__ __forceinline__ void uf_union(int *L, int a, int b)
+{
+    bool done = false;
+    while (!done) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a < b) { int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+        else if (b < a) { int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+        else done = true;
+    }
+}
+__global__ void speckle_merge_kernel(const uint8_t *__restrict__ u8, int *label, int W, int H, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int v = u8[t];
+    if (!v) return;
+    const int x = (int)(t % W), y = (int)((t / W) % H);
+    if (x + 1 < W) { const int q = u8[t + 1]; if (q && abs(q - v) <= 10) uf_union(label, (int)t, (int)t + 1); }
+    if (y + 1 < H) { const int q = u8[t + W]; if (q && abs(q - v) <= 10) uf_union(label, (int)t, (int)t + W); }
+}
+__global__ void speckle_count_kernel(const uint8_t *__restrict__ u8, int *label, int *count, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total || !u8[t]) return;
+    const int root = uf_find(label, (int)t);
+    label[t] = root;
+    atomicAdd(&count[root], 1);
+}
+// apply the speckle verdict, restore sub-pixel values (rsgm.py:286-290) and write the float frame
+__global__ void speckle_apply_kernel(const uint8_t *__restrict__ u8, const int *__restrict__ label, const int *__restrict__ count,
+                                     const float *__restrict__ dl, float *__restrict__ out, RsgmDims d, int subpixel, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int b = u8[t];
+    if (b && count[label[t]] <= 200) b = 0;
+    float v = (float)b;
+    if (subpixel && b) {
+        const int x = (int)(t % d.W), y = (int)((t / d.W) % d.H);
+        const long f = t / ((long)d.W * d.H);
+        v = dl[(f * d.Hp + y + d.pt) * d.Wp + d.pl + x];
+    }
+    out[t] = v;
+}
+
+// _interpolate_background rows (rsgm.py:188-213): warp per row staged in smem, lane 0 scans
+__global__ void __launch_bounds__(128) bg_rows_kernel(float *__restrict__ img, int W, long total_rows)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= total_rows) return;
+    float *r = smem + (size_t)warp * W;
+    float *g = img + row * W;
+    for (int x = lane; x < W; x += 32) r[x] = g[x];
+    __syncwarp();
+    if (lane == 0) {
+        int count = 0;
+        for (int u = 0; u < W; u++) {
+            if (r[u] > 0) {
+                if (count >= 1) {
+                    const int u1 = u - count, u2 = u - 1;
+                    if (u1 > 0 && u2 < W - 1) {
+                        const float dd = fminf(r[u1 - 1], r[u2 + 1]);
+                        for (int c = u1; c <= u2; c++) r[c] = dd;
+                    }
+                }
+                count = 0;
+            } else {
+                count++;
+            }
+        }
+        for (int u = 0; u < W; u++)
+            if (r[u] > 0) { for (int u2 = 0; u2 < u; u2++) r[u2] = r[u]; break; }
+        for (int u = W - 1; u >= 0; u--)
+            if (r[u] > 0) { for (int u2 = u + 1; u2 < W; u2++) r[u2] = r[u]; break; }
+    }
+    __syncwarp();
+    for (int x = lane; x < W; x += 32) g[x] = r[x];
+}
+// _interpolate_background columns (rsgm.py:215-227): thread per column (coalesced across the warp)
+__global__ void bg_cols_kernel(float *__restrict__ img, int W, int H, long total_cols)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_cols) return;
+    const int u = (int)(t % W);
+    float *col = img + (t / W) * (long)W * H + u;
+    for (int v = 0; v < H; v++)
+        if (col[(long)v * W] > 0) { const float f = col[(long)v * W]; for (int v2 = 0; v2 < v; v2++) col[(long)v2 * W] = f; break; }
+    for (int v = H - 1; v >= 0; v--)
+        if (col[(long)v * W] > 0) { const float f = col[(long)v * W]; for (int v2 = v + 1; v2 < H; v2++) col[(long)v2 * W] = f; break; }
+}
+
+int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d, int subpixel, TailBufs tb, int n, cudaStream_t st)
+{
+    const long total = (long)n * d.H * d.W;
+    if (total >= (1L << 31)) return VPPB200_ERR_ARG;
+    const int blocks = cdiv(total, 256);
+    lrcheck_u8_kernel<<<blocks, 256, 0, st>>>(dl, dr, tb.u8, tb.label, tb.count, d, total);
+    VPP_LAUNCH_CHECK("lrcheck_u8_kernel");
+    speckle_merge_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, d.W, d.H, total);
+    VPP_LAUNCH_CHECK("speckle_merge_kernel");
+    speckle_count_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, total);
+    VPP_LAUNCH_CHECK("speckle_count_kernel");
+    speckle_apply_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, dl, out, d, subpixel, total);
+    VPP_LAUNCH_CHECK("speckle_apply_kernel");
+    const long rows = (long)n * d.H;
+    const int wpb = 4;
+    const size_t sm = (size_t)wpb * d.W * sizeof(float);
+    if (sm > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(bg_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    bg_rows_kernel<<<cdiv(rows, wpb), wpb * 32, sm, st>>>(out, d.W, rows);
+    VPP_LAUNCH_CHECK("bg_rows_kernel");
+    const long cols = (long)n * d.W;
+    bg_cols_kernel<<<cdiv(cols, 128), 128, 0, st>>>(out, d.W, d.H, cols);
+    VPP_LAUNCH_CHECK("bg_cols_kernel");
+    return VPPB200_OK;
+}
+
+}  // namespace vppb200

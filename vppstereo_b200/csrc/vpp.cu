@@ -1,0 +1,466 @@
+// vpp.cu -- Virtual Pattern Projection on sm_100a: exact parallel restatements of the reference's sequential scans
+// (vpp_core/vpp_core_opt.pyx:53-341 and the numba twin vpp_standalone.py:14-369; semantics in SURVEY.md A.1).
+//
+// rnd mode.  Every read that feeds a write to image row yy (of L or R) is in row yy of the same channel
+// (SURVEY.md A.1.5), so the final row yy of channel j equals the ORDERED replay, over the hints of rows
+// yy-n..yy+n in scan order, of the yw = yy - y slice of each patch.  One thread owns one (frame, row, channel)
+// and replays its writers in order: no atomics, no races, bit-exact.  The random stream position of every draw
+// is closed-form (A.1.6) from per-row prefix sums, so the pre-drawn pattern is indexed, not consumed.
+//
+// maxDistance mode.  The colour of a patch pixel is a fold over a 64x3 window of the CURRENT images, so hints are
+// truly sequential per channel; channels are independent.  One warp owns one (frame, channel): the window samples
+// are fetched 32 at a time and folded with ballot skip-ahead (only samples strictly inside the shrinking (pa,pb)
+// interval can change it), lane 0 applies the blends.
+//
+// Blends are evaluated in the reference's mixed float32/float64 typing with truncation to uint8; this file is
+// compiled with -fmad=false and uses explicit _rn intrinsics so no FMA contraction can change a truncation.
+#include "common.cuh"
+
+namespace vppb200 {
+
+struct VppArgs {
+    int W, H, C;
+    int uniform, n, nax, nay, direction, discard, interpolate, arith;
+    float c32, cocc32;
+    double c64, cocc64;
+};
+
+struct VppWs {
+    uint16_t *hx;        // [n][H][W] hint columns of each row in scan order
+    int *cnt;            // [n][H]   hints per row
+    long long *draws;    // [n][H]   pattern draws per row and channel  (sum of in-image patch pixels)
+    long long *hbase;    // [n][H]   exclusive prefix of cnt
+    long long *dbase;    // [n][H]   exclusive prefix of draws
+};
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static size_t vpp_ws_layout(int H, int W, int n, void *base, VppWs *ws)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? b + o : (char *)nullptr; };
+    uint16_t *hx = (uint16_t *)take((size_t)n * H * W * 2);
+    int *cnt = (int *)take((size_t)n * H * 4);
+    long long *draws = (long long *)take((size_t)n * H * 8);
+    long long *hbase = (long long *)take((size_t)n * H * 8);
+    long long *dbase = (long long *)take((size_t)n * H * 8);
+    if (ws) { ws->hx = hx; ws->cnt = cnt; ws->draws = draws; ws->hbase = hbase; ws->dbase = dbase; }
+    return off;
+}
+
+// ---- per-row ordered hint compaction: one warp per (frame, row) ---------------------------------------------
+__global__ void __launch_bounds__(128) vpp_compact_rows_kernel(const float *__restrict__ g, VppWs ws, int W, int H, int n_patch,
+                                                               int direction, long total_rows)
+{
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int y = (int)(row % H);
+    const float *grow = g + row * W;
+    uint16_t *out = ws.hx + row * W;
+    const int ny = min(y + n_patch, H - 1) - max(y - n_patch, 0) + 1;
+    int count = 0;
+    long long draws = 0;
+    for (int base = 0; base < W; base += 32) {
+        const int s = base + lane;                       // position in scan order
+        const int x = direction != 0 ? s : W - 1 - s;
+        const bool hit = s < W && grow[x] > 0.0f;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hit) out[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)x;
+        int nx = hit ? (min(x + n_patch, W - 1) - max(x - n_patch, 0) + 1) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nx += __shfl_xor_sync(0xFFFFFFFFu, nx, o);
+        draws += (long long)nx * ny;
+        count += __popc(m);
+    }
+    if (lane == 0) { ws.cnt[row] = count; ws.draws[row] = draws; }
+}
+
+// exclusive prefix over the rows of each frame (one thread per frame; H is a few thousand at most)
+__global__ void vpp_scan_rows_kernel(VppWs ws, int H, int n, int32_t *n_hints_out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    long long hb = 0, db = 0;
+    for (int y = 0; y < H; y++) {
+        const long r = (long)f * H + y;
+        ws.hbase[r] = hb; ws.dbase[r] = db;
+        hb += ws.cnt[r]; db += ws.draws[r];
+    }
+    if (n_hints_out) n_hints_out[f] = (int32_t)hb;
+}
+
+// ---- the blend of one patch pixel (vpp_core_opt.pyx:104-124 / :315-335; vpp_standalone.py:342-363 / :206-226) -----
+__device__ __forceinline__ uint8_t tr8(double v) { return (uint8_t)(int)v; }     // truncation; values are in [0,256)
+
+struct Splat {
+    const VppArgs &a;
+    uint8_t *lrow, *rrow;      // row pointers at channel j (pixel stride = C)
+    __device__ __forceinline__ uint8_t &L(int x) const { return lrow[(long)x * a.C]; }
+    __device__ __forceinline__ uint8_t &R(int x) const { return rrow[(long)(x < 0 ? x + a.W : x) * a.C]; }  // negative index wraps
+};
+
+// pv: pattern value (rnd: the drawn uint8; maxDistance: (pa+pb)/2 as double)
+template <bool RND>
+__device__ __forceinline__ void splat_pixel(const Splat &s, double pv, int xl, int x0, int x1, int xr, bool occluded,
+                                            float b32, double b64)
+{
+    const VppArgs &a = s.a;
+    const int W = a.W;
+    // colour term and (1 - c) in the reference's typing
+    auto colour = [&](bool occ) -> double {
+        if (a.arith == 0) {
+            const float c = occ ? a.cocc32 : a.c32;
+            if (RND) return (double)__fmul_rn((float)pv, c);          // uint8 * float -> float
+            return __dmul_rn(pv, (double)c);                          // double * float -> double
+        }
+        return __dmul_rn(pv, occ ? a.cocc64 : a.c64);
+    };
+    auto omc = [&](bool occ) -> double {
+        if (a.arith == 0) return __dsub_rn(1.0, (double)(occ ? a.cocc32 : a.c32));
+        return __dsub_rn(1.0, occ ? a.cocc64 : a.c64);
+    };
+    const double b = a.arith == 0 ? (double)b32 : b64;
+    const double omb = __dsub_rn(1.0, b);
+    // r * b: uint8 * float32 -> float32 in the Cython build, double in numba
+    auto r_times_b = [&](uint8_t r) -> double {
+        if (a.arith == 0) return (double)__fmul_rn((float)r, b32);
+        return __dmul_rn((double)r, b64);
+    };
+    auto blend = [&](double rc, uint8_t old, double om) -> double { return __dadd_rn(rc, __dmul_rn((double)old, om)); };
+
+    if (0 <= x0 && x0 <= W - 1) {
+        if (!occluded) {
+            const double rc = colour(false), om = omc(false);
+            s.L(xl) = tr8(blend(rc, s.L(xl), om));
+            if (a.interpolate) {
+                const uint8_t r0 = s.R(x0);
+                s.R(x0) = tr8(__dadd_rn(__dmul_rn(blend(rc, r0, om), omb), r_times_b(r0)));
+                if (0 <= x1 && x1 <= W - 1) {
+                    const uint8_t r1 = s.R(x1);
+                    s.R(x1) = tr8(__dadd_rn(__dmul_rn(blend(rc, r1, om), b), __dmul_rn((double)r1, omb)));
+                }
+            } else {
+                s.R(xr) = tr8(blend(rc, s.R(xr), om));
+            }
+        } else if (!a.discard) {
+            const double rc = colour(true), omo = omc(true), om = omc(false);
+            if (a.interpolate) {
+                const uint8_t r0 = s.R(x0);
+                s.R(x0) = tr8(__dadd_rn(__dmul_rn(blend(rc, r0, omo), omb), r_times_b(r0)));
+                if (0 <= x1 && x1 <= W - 1) {
+                    const uint8_t r1 = s.R(x1);
+                    s.R(x1) = tr8(__dadd_rn(__dmul_rn(blend(rc, r1, omo), b), __dmul_rn((double)r1, omb)));
+                }
+                const double mix = __dadd_rn(__dmul_rn((double)s.R(x0), omb), r_times_b(s.R(x1)));
+                const double cc = a.arith == 0 ? (double)a.c32 : a.c64;
+                s.L(xl) = tr8(__dadd_rn(__dmul_rn(mix, cc), __dmul_rn((double)s.L(xl), om)));
+            } else {
+                s.R(xr) = tr8(blend(rc, s.R(xr), omo));
+                const double rcl = a.arith == 0 ? (double)__fmul_rn((float)s.R(xr), a.c32) : __dmul_rn((double)s.R(xr), a.c64);
+                s.L(xl) = tr8(__dadd_rn(rcl, __dmul_rn((double)s.L(xl), om)));
+            }
+        }
+    } else {
+        s.L(xl) = tr8(blend(colour(false), s.L(xl), omc(false)));    // left-side occlusion (pyx:123-124)
+    }
+}
+
+struct HintGeom {
+    int xd, xd0, xd1;
+    float b32;
+    double b64;
+};
+__device__ __forceinline__ HintGeom hint_geom(const VppArgs &a, float gv, int x)
+{
+    HintGeom h;
+    const int d0 = (int)floorf(gv), d1 = (int)ceilf(gv);
+    // (int)round(g): C round = half away from zero (pyx:82); numba round = half to even (vpp_standalone.py:304)
+    const int d = a.arith == 0 ? (int)roundf(gv) : __float2int_rn(gv);
+    h.xd = x - d; h.xd0 = x - d0; h.xd1 = x - d1;
+    h.b32 = __fsub_rn(gv, (float)d0);
+    h.b64 = __dsub_rn((double)gv, (double)d0);
+    return h;
+}
+
+// on-device pattern generation (pattern == NULL): splitmix64 finaliser of (seed, frame, stream position)
+__device__ __forceinline__ uint8_t counter_pattern(uint64_t frame_key, uint64_t idx)
+{
+    uint64_t z = frame_key + (idx + 1) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (uint8_t)((z ^ (z >> 31)) >> 24);
+}
+
+// ---- rnd: ordered replay, one thread per (frame, row yy, channel j) ------------------------------------------
+__global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict__ l, uint8_t *__restrict__ r,
+                                                             const float *__restrict__ g, const uint8_t *__restrict__ g_occ,
+                                                             const uint8_t *__restrict__ pattern,
+                                                             const int64_t *__restrict__ pattern_offsets, uint64_t rng_seed,
+                                                             VppWs ws, VppArgs a, long total)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int j = (int)(t % a.C);
+    const int yy = (int)((t / a.C) % a.H);
+    const long f = t / ((long)a.C * a.H);
+    const int W = a.W, H = a.H, n = a.n;
+    Splat s{a, l + ((f * H + yy) * W) * a.C + j, r + ((f * H + yy) * W) * a.C + j};
+    const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
+    const long long pat_len = pattern ? pattern_offsets[f + 1] - pattern_offsets[f] : 0;
+    const uint64_t frame_key = rng_seed ^ ((uint64_t)f * 0x9E3779B97F4A7C15ull);
+    for (int y = max(0, yy - n); y <= min(H - 1, yy + n); y++) {
+        const long row = f * H + y;
+        const int cnt = ws.cnt[row];
+        const uint16_t *hx = ws.hx + row * W;
+        const int ylo = max(y - n, 0);                        // first in-image patch row
+        const int ny = min(y + n, H - 1) - ylo + 1;
+        const int rows_before = yy - ylo;                     // in-image patch rows above the slice
+        long long draw_prefix = ws.dbase[row];                // draws (per channel) of earlier hints
+        const long long hint_prefix = ws.hbase[row];
+        for (int k = 0; k < cnt; k++) {
+            const int x = hx[k];
+            const float gv = g[row * W + x];
+            const bool occ = g_occ[row * W + x] != 0;
+            const HintGeom hg = hint_geom(a, gv, x);
+            const int xlo = max(x - n, 0), xhi = min(x + n, W - 1);
+            const int nx = xhi - xlo + 1;
+            const long long inb = (long long)nx * ny;
+            // stream index of the first pixel of my slice
+            long long idx = a.uniform ? (long long)a.C * (hint_prefix + k) + j
+                                      : (long long)a.C * draw_prefix + (long long)j * inb + (long long)rows_before * nx;
+            for (int xx = xlo; xx <= xhi; xx++) {
+                const int xw = xx - x;
+                const uint8_t rv = pat ? ((idx >= 0 && idx < pat_len) ? pat[idx] : 0) : counter_pattern(frame_key, (uint64_t)idx);
+                if (!a.uniform) idx++;
+                splat_pixel<true>(s, (double)rv, xx, hg.xd0 + xw, hg.xd1 + xw, hg.xd + xw, occ, hg.b32, hg.b64);
+            }
+            draw_prefix += inb;
+        }
+    }
+}
+
+// ---- maxDistance: one warp per (frame, channel), sequential over hints ------------------------------------------
+// fold of the ordered window samples into (pa, pb)  (pyx:216-313): lane p of a chunk holds window position
+// chunk*32+p with up to two samples (left first, then right).
+struct MaxDistState { int pa, pb, zeros; };
+
+__device__ __forceinline__ void fold_chunk(MaxDistState &st, bool has_l, int vl, bool has_r, int vr, int lane)
+{
+    // book-keeping of zero samples (n_bins); which samples count is decided by the caller through has_* flags
+    // ordered fold with skip-ahead: order index = 2*lane + side
+    int done = -1;                                             // last consumed order index
+    while (true) {
+        const bool pl = has_l && (2 * lane > done) && vl > st.pa && vl < st.pb;
+        const bool pr = has_r && (2 * lane + 1 > done) && vr > st.pa && vr < st.pb;
+        const unsigned bl = __ballot_sync(0xFFFFFFFFu, pl), br = __ballot_sync(0xFFFFFFFFu, pr);
+        const unsigned any = bl | br;
+        if (!any) break;
+        const int src = __ffs(any) - 1;
+        const bool left_first = (bl >> src) & 1u;
+        const int v = __shfl_sync(0xFFFFFFFFu, left_first ? vl : vr, src);
+        done = 2 * src + (left_first ? 0 : 1);
+        if (v - st.pa > st.pb - v) st.pb = v;
+        else if (v - st.pa < st.pb - v) st.pa = v;
+    }
+}
+
+__device__ double max_dist_colour(const VppArgs &a, const uint8_t *limg, const uint8_t *rimg, int j, int cy, int cx, int shift,
+                                  bool occ, bool uniform_branch, int lane)
+{
+    const int W = a.W, H = a.H, C = a.C;
+    const int wx = 2 * a.nax + 1, wy = 2 * a.nay + 1, npos = wx * wy;
+    MaxDistState st{0, 255, 0};
+    // Cython's uniform branch only counts samples that pass the range test (pyx:235-237,:248-250); a zero sample never
+    // does, so n_bins cannot reach 0 there.  Everywhere else every sample is counted.
+    const bool count_all = !(a.arith == 0 && uniform_branch);
+    for (int base = 0; base < npos; base += 32) {
+        const int p = base + lane;
+        bool has_l = false, has_r = false;
+        int vl = 0, vr = 0;
+        if (p < npos) {
+            const int yy = cy + p / wx - a.nay, xx = cx + p % wx - a.nax;
+            if (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1) {
+                const int xr = xx - shift;
+                has_r = (0 <= xr && xr <= W - 1);
+                has_l = (!occ) || !has_r;
+                if (has_l) vl = limg[((long)yy * W + xx) * C + j];
+                if (has_r) vr = rimg[((long)yy * W + xr) * C + j];
+            }
+        }
+        if (count_all)
+            st.zeros += __popc(__ballot_sync(0xFFFFFFFFu, has_l && vl == 0)) + __popc(__ballot_sync(0xFFFFFFFFu, has_r && vr == 0));
+        fold_chunk(st, has_l, vl, has_r, vr, lane);
+    }
+    if (count_all && st.zeros == 256) {
+        // n_bins == 0 (exactly 256 zero samples): pa = pb = first index of the minimum bin count (pyx:252-260,:305-313).
+        // Rare; recount the window per candidate value.  Cython bins are int, numba bins are uint8 (wrap at 256).
+        int best_k = 0, best_v = 0x7FFFFFFF;
+        for (int k0 = 0; k0 < 256; k0 += 32) {
+            const int k = k0 + lane;
+            int cntk = 0;
+            for (int p = 0; p < npos; p++) {
+                const int yy = cy + p / wx - a.nay, xx = cx + p % wx - a.nax;
+                if (yy < 0 || yy > H - 1 || xx < 0 || xx > W - 1) continue;
+                const int xr = xx - shift;
+                const bool hr = (0 <= xr && xr <= W - 1);
+                if (((!occ) || !hr) && limg[((long)yy * W + xx) * C + j] == k) cntk++;
+                if (hr && rimg[((long)yy * W + xr) * C + j] == k) cntk++;
+            }
+            if (a.arith == 1) cntk &= 255;
+            // warp arg-min, first index on ties
+            int key_v = cntk, key_k = k;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ov = __shfl_xor_sync(0xFFFFFFFFu, key_v, o), ok = __shfl_xor_sync(0xFFFFFFFFu, key_k, o);
+                if (ov < key_v || (ov == key_v && ok < key_k)) { key_v = ov; key_k = ok; }
+            }
+            if (key_v < best_v) { best_v = key_v; best_k = key_k; }
+        }
+        st.pa = st.pb = best_k;
+    }
+    return (double)(st.pa + st.pb) / 2.0;
+}
+
+__global__ void __launch_bounds__(32) vpp_max_dist_kernel(uint8_t *l, uint8_t *r, const float *__restrict__ g,
+                                                          const uint8_t *__restrict__ g_occ, VppWs ws, VppArgs a, int total)
+{
+    const int unit = blockIdx.x;                      // one warp per block
+    if (unit >= total) return;
+    const int lane = threadIdx.x;
+    const int j = unit % a.C;
+    const long f = unit / a.C;
+    const int W = a.W, H = a.H, n = a.n;
+    uint8_t *limg = l + f * (long)H * W * a.C, *rimg = r + f * (long)H * W * a.C;
+    for (int y = 0; y < H; y++) {
+        const long row = f * H + y;
+        const int cnt = ws.cnt[row];
+        const uint16_t *hx = ws.hx + row * W;
+        for (int k = 0; k < cnt; k++) {
+            const int x = hx[k];
+            const float gv = g[row * W + x];
+            const bool occ = g_occ[row * W + x] != 0;
+            const HintGeom hg = hint_geom(a, gv, x);
+            double pv = 0.0;
+            if (a.uniform) pv = max_dist_colour(a, limg, rimg, j, y, x, x - hg.xd, occ, true, lane);
+            for (int yw = -n; yw <= n; yw++) {
+                if (y + yw < 0 || y + yw > H - 1) continue;
+                for (int xw = -n; xw <= n; xw++) {
+                    if (x + xw < 0 || x + xw > W - 1) continue;
+                    if (!a.uniform) pv = max_dist_colour(a, limg, rimg, j, y + yw, x + xw, x - hg.xd, occ, false, lane);
+                    if (lane == 0) {
+                        Splat s{a, limg + ((long)(y + yw) * W) * a.C + j, rimg + ((long)(y + yw) * W) * a.C + j};
+                        splat_pixel<false>(s, pv, x + xw, hg.xd0 + xw, hg.xd1 + xw, hg.xd + xw, occ, hg.b32, hg.b64);
+                    }
+                    __syncwarp();                     // lane 0's stores are visible to the next window fetch
+                }
+            }
+        }
+    }
+}
+
+// gt_reshape (pyx:352-371): raster-order compaction to (x, y, d, 1); reuses the per-row lists (direction = 1)
+__global__ void gt_reshape_kernel(const float *__restrict__ gt, VppWs ws, int W, int H, float *__restrict__ out, int32_t *count_out)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= H) return;
+    const long long base = ws.hbase[y];
+    const int cnt = ws.cnt[y];
+    for (int k = 0; k < cnt; k++) {
+        const int x = ws.hx[(long)y * W + k];
+        float4 v = make_float4((float)x, (float)y, gt[(long)y * W + x], 1.0f);
+        reinterpret_cast<float4 *>(out)[base + k] = v;
+    }
+    if (y == H - 1 && count_out) *count_out = (int32_t)(base + cnt);
+}
+
+static int prepare_hints(const float *g, int W, int H, int n_patch, int direction, const VppWs &ws, int32_t *n_hints_out, int n,
+                         cudaStream_t st)
+{
+    const long rows = (long)n * H;
+    vpp_compact_rows_kernel<<<cdiv(rows * 32, 128), 128, 0, st>>>(g, ws, W, H, n_patch, direction, rows);
+    VPP_LAUNCH_CHECK("vpp_compact_rows_kernel");
+    vpp_scan_rows_kernel<<<cdiv(n, 64), 64, 0, st>>>(ws, H, n, n_hints_out);
+    VPP_LAUNCH_CHECK("vpp_scan_rows_kernel");
+    return VPPB200_OK;
+}
+
+static VppArgs make_args(int W, int H, int C, int uniform, int wsize, int wax, int way, int direction, double c, double c_occ,
+                         int discard, int interpolate, int arith)
+{
+    VppArgs a;
+    a.W = W; a.H = H; a.C = C; a.uniform = uniform != 0; a.n = (wsize - 1) / 2; a.nax = (wax - 1) / 2; a.nay = (way - 1) / 2;
+    a.direction = direction; a.discard = discard != 0; a.interpolate = interpolate != 0; a.arith = arith;
+    a.c32 = (float)c; a.cocc32 = (float)c_occ; a.c64 = c; a.cocc64 = c_occ;
+    return a;
+}
+
+}  // namespace vppb200
+
+using namespace vppb200;
+
+extern "C" size_t vppb200_vpp_workspace_bytes(int H, int W, int C, int n)
+{
+    (void)C;
+    if (H <= 0 || W <= 0 || n <= 0) return 0;
+    return vpp_ws_layout(H, W, n, nullptr, nullptr);
+}
+
+extern "C" int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                    int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                                    int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                                    uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream)
+{
+    if (!l || !r || !g || !g_occ || (pattern && !pattern_offsets) || W <= 0 || H <= 0 || C <= 0 || n <= 0 || wsize < 1 || W > 65535 ||
+        (arith != 0 && arith != 1))
+        return VPPB200_ERR_ARG;
+    if (!workspace || workspace_bytes < vpp_ws_layout(H, W, n, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    VppWs ws;
+    vpp_ws_layout(H, W, n, workspace, &ws);
+    VppArgs a = make_args(W, H, C, uniform_color, wsize, 1, 1, direction, c, c_occ, discard_occluded, interpolate, arith);
+    int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st);
+    if (rc) return rc;
+    const long total = (long)n * H * C;
+    vpp_rnd_replay_kernel<<<cdiv(total, 128), 128, 0, st>>>(l, r, g, g_occ, pattern, pattern_offsets, rng_seed, ws, a, total);
+    VPP_LAUNCH_CHECK("vpp_rnd_replay_kernel");
+    return VPPB200_OK;
+}
+
+extern "C" int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                         int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                                         const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
+                                         int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream)
+{
+    if (!l || !r || !g || !g_occ || W <= 0 || H <= 0 || C <= 0 || n <= 0 || wsize < 1 || wsize_agg_x < 1 || wsize_agg_y < 1 ||
+        W > 65535 || (arith != 0 && arith != 1))
+        return VPPB200_ERR_ARG;
+    if (!workspace || workspace_bytes < vpp_ws_layout(H, W, n, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    VppWs ws;
+    vpp_ws_layout(H, W, n, workspace, &ws);
+    VppArgs a = make_args(W, H, C, uniform_color, wsize, wsize_agg_x, wsize_agg_y, direction, c, c_occ, discard_occluded,
+                          interpolate, arith);
+    int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st);
+    if (rc) return rc;
+    const int total = n * C;
+    vpp_max_dist_kernel<<<total, 32, 0, st>>>(l, r, g, g_occ, ws, a, total);
+    VPP_LAUNCH_CHECK("vpp_max_dist_kernel");
+    return VPPB200_OK;
+}
+
+extern "C" int vppb200_gt_reshape(const float *gt, int W, int H, float *out, int32_t *count_out, void *workspace,
+                                  size_t workspace_bytes, void *stream)
+{
+    if (!gt || !out || W <= 0 || H <= 0 || W > 65535) return VPPB200_ERR_ARG;
+    if (!workspace || workspace_bytes < vpp_ws_layout(H, W, 1, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    VppWs ws;
+    vpp_ws_layout(H, W, 1, workspace, &ws);
+    int rc = prepare_hints(gt, W, H, 0, 1, ws, nullptr, 1, st);
+    if (rc) return rc;
+    gt_reshape_kernel<<<cdiv(H, 128), 128, 0, st>>>(gt, ws, W, H, out, count_out);
+    VPP_LAUNCH_CHECK("gt_reshape_kernel");
+    return VPPB200_OK;
+}

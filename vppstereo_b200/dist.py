@@ -1,0 +1,72 @@
+"""Multi-GPU plumbing: the hot path shards by FRAME.  One process per GPU, contiguous frame
+ranges per rank, no communication while computing, one collective at the end to gather the disparities.
+
+Only torch.distributed is used (NCCL on GPUs, gloo in the CPU tests of this host logic); nothing here launches kernels.
+"""
+import numpy as np
+
+
+def shard_range(n_frames, rank, world_size):
+    """Contiguous, balanced frame range [lo, hi) of `rank`: the first n % world ranks own one extra frame."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank / world_size")
+    base, extra = divmod(int(n_frames), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_frames, world_size):
+    return [shard_range(n_frames, r, world_size)[1] - shard_range(n_frames, r, world_size)[0] for r in range(world_size)]
+
+
+def chunks(lo, hi, chunk):
+    """Sub-ranges of at most `chunk` frames (bounds the workspace: 368 MB of cost volumes per KITTI frame)."""
+    out = []
+    while lo < hi:
+        out.append((lo, min(hi, lo + chunk)))
+        lo += chunk
+    return out
+
+
+def gather_frames(local, n_frames, group=None, dst=None):
+    """All ranks pass their shard [n_local, ...] (contiguous frame range in rank order); returns the full
+    [n_frames, ...] tensor on every rank (dst=None, all_gather) or on rank `dst` only (gather; others get None).
+    Shards may be uneven: they are padded to the largest shard for the collective and trimmed afterwards."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = shard_sizes(n_frames, world)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} frames, expected {sizes[rank]}")
+    m = max(sizes)
+    padded = local
+    if local.shape[0] < m:
+        pad = torch.zeros((m - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        padded = torch.cat([local, pad], 0)
+    padded = padded.contiguous()
+    if dst is None:
+        out = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, padded, group=group)
+        parts = [out[r * m: r * m + sizes[r]] for r in range(world)]
+        return torch.cat(parts, 0) if any(s != m for s in sizes) else out
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][: sizes[r]] for r in range(world)], 0)
+
+
+def run_sharded(n_frames, make_inputs, process, chunk=16, group=None, gather=True):
+    """Frame-sharded driver.  make_inputs(lo, hi) -> inputs of frames [lo, hi); process(inputs) -> tensor [hi-lo, ...].
+    Returns the gathered [n_frames, ...] result (every rank) or the local shard when gather=False."""
+    import torch
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+    lo, hi = shard_range(n_frames, rank, world)
+    outs = [process(make_inputs(a, b)) for a, b in chunks(lo, hi, chunk)]
+    local = torch.cat(outs, 0) if outs else None
+    if local is None:
+        raise ValueError("a rank received no frames: use n_frames >= world_size")
+    return gather_frames(local, n_frames, group=group) if gather else local

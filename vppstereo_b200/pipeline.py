@@ -1,0 +1,82 @@
+"""The whole hot path as one object: VPP (rnd pattern, numba arithmetic as test.py uses it) followed by compute_rsgm on a
+batch of frames, with the images staying on the device between the two (test.py:158-225 without the host round-trips).
+
+    pipe = VppRsgmPipeline(H, W, batch=64, dmax=192)
+    disp = pipe.run_device(left_u8, right_u8, hints_f32)        # CUDA tensors in, CUDA float32 [N,H,W] out
+    disp = pipe.run_host(left_pinned, right_pinned, hints_pinned)  # host tensors in, pinned host float32 out
+
+run_host is the end-to-end path: host->device copies of the three inputs and the device->host copy of the disparities
+are part of the call.
+"""
+import ctypes as C
+
+from . import _lib
+from . import vpp_core_opt as _core
+
+
+class VppRsgmPipeline:
+    def __init__(self, H, W, channels=3, batch=64, dmax=192, wsize=3, blending=0.4, c_occ=0.0, left2right=True,
+                 interpolate=True, subpixel=True, device=None, seed=1234):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.H, self.W, self.C, self.N, self.D = int(H), int(W), int(channels), int(batch), int(dmax)
+        self.wsize, self.blending, self.c_occ = int(wsize), float(blending), float(c_occ)
+        self.direction = 1 if left2right else 0
+        self.interpolate, self.subpixel = bool(interpolate), bool(subpixel)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.seed = int(seed)
+        self.step = 0
+        L = _lib.lib()
+        self.lib = L
+        with torch.cuda.device(self.device):
+            self.ws_rsgm = torch.empty(L.vppb200_rsgm_workspace_bytes(self.H, self.W, self.C, self.D, self.N), dtype=torch.uint8,
+                                       device=self.device)
+            self.ws_vpp = torch.empty(L.vppb200_vpp_workspace_bytes(self.H, self.W, self.C, self.N), dtype=torch.uint8,
+                                      device=self.device)
+            self.occ = torch.zeros((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
+            self.lv = torch.empty((self.N, self.H, self.W, self.C), dtype=torch.uint8, device=self.device)
+            self.rv = torch.empty_like(self.lv)
+            self.disp = torch.empty((self.N, self.H, self.W), dtype=torch.float32, device=self.device)
+            # staging for run_host
+            self.d_left = torch.empty_like(self.lv)
+            self.d_right = torch.empty_like(self.lv)
+            self.d_hints = torch.empty((self.N, self.H, self.W), dtype=torch.float32, device=self.device)
+            self.h_disp = torch.empty((self.N, self.H, self.W), dtype=torch.float32).pin_memory()
+
+    def workspace_bytes(self):
+        return self.ws_rsgm.numel() + self.ws_vpp.numel()
+
+    def run_device(self, left, right, hints, out=None):
+        """VPP (in copies) + compute_rsgm; all operands CUDA tensors [N,H,W,C] uint8 / [N,H,W] float32."""
+        torch, L = self.torch, self.lib
+        N = left.shape[0]
+        assert N <= self.N and left.shape[1:] == (self.H, self.W, self.C)
+        out = self.disp[:N] if out is None else out
+        st = _lib.stream_ptr(self.device)
+        lv, rv = self.lv[:N], self.rv[:N]
+        lv.copy_(left); rv.copy_(right)              # vpp() returns copies (vpp_standalone.py:397)
+        self.step += 1
+        seed = (self.seed * 0x9E3779B97F4A7C15 + self.step) & (2**64 - 1)
+        rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), self.W, self.H, self.C, 0, self.wsize,
+                                    self.direction, C.c_double(self.blending), C.c_double(self.c_occ), _lib.ptr(self.occ),
+                                    0, int(self.interpolate), 1, None, None, C.c_uint64(seed), None, _lib.ptr(self.ws_vpp),
+                                    C.c_size_t(self.ws_vpp.numel()), N, st)
+        _lib.check(rc, "vpp_scan_rnd")
+        rc = L.vppb200_compute_rsgm(_lib.ptr(left), _lib.ptr(lv), _lib.ptr(rv), None, None, _lib.ptr(out), self.H, self.W,
+                                    self.C, self.D, 1 if self.subpixel else 0, None, _lib.ptr(self.ws_rsgm),
+                                    C.c_size_t(self.ws_rsgm.numel()), N, st)
+        _lib.check(rc, "compute_rsgm")
+        return out
+
+    def run_host(self, left, right, hints):
+        """Host tensors (ideally pinned) in, pinned host float32 [N,H,W] out; the copies are part of the call."""
+        torch = self.torch
+        N = left.shape[0]
+        with torch.cuda.device(self.device):
+            self.d_left[:N].copy_(left, non_blocking=True)
+            self.d_right[:N].copy_(right, non_blocking=True)
+            self.d_hints[:N].copy_(hints, non_blocking=True)
+            out = self.run_device(self.d_left[:N], self.d_right[:N], self.d_hints[:N])
+            self.h_disp[:N].copy_(out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return self.h_disp[:N]
