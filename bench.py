@@ -73,15 +73,9 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------- CPU reference arm
-def _cpu_worker_init():
-    os.environ["OMP_NUM_THREADS"] = "1"
-    sys.path.insert(0, ROOT)
-
-
-def _cpu_frame(args):
+def _cpu_frame(f, kind, shape, dmax):
     """VPP + compute_rsgm of one synthetic frame on one core with the reference's own code (oracle/_ref), or with the
     oracle port when the compiled reference is absent."""
-    f, kind, shape, warm = args
     import numpy as np
     from vppstereo_b200 import synth
     p = synth.make_pair(f, shape=shape, hints="lidar")
@@ -94,44 +88,81 @@ def _cpu_frame(args):
         r.vpp_core_opt.init_rand(1 + f)
         r.vpp_core_opt.virtual_projection_scan_rnd(l, rr, p["hints"], Ww, Hh, 3, False, 3, 1, 0.4, 0.0,
                                                    np.zeros((Hh, Ww), np.uint8), False, True)
-        out = r.rsgm.compute_rsgm(p["left"], l, rr, dmax=D if not warm else 32)
+        out = r.rsgm.compute_rsgm(p["left"], l, rr, dmax=dmax)
     else:
         from oracle import oracle as orc
         n = orc.stream_length(p["hints"], 3, 3, False)
         l, rr = orc.vpp(p["left"], p["right"], p["hints"], stream=np.zeros(n, np.uint8), mode=0)
-        out = orc.compute_rsgm(p["left"], l, rr, dmax=D if not warm else 32)
+        out = orc.compute_rsgm(p["left"], l, rr, dmax=dmax)
     return time.perf_counter() - t0, float(out.mean())
 
 
+def cpu_worker_main(kind):
+    """Worker process of the CPU arm: line protocol on stdin/stdout (pipes only: the GPU box has no /dev/shm semaphores).
+    'run <f0> <n>' -> runs n K-shape frames, answers '<seconds> <mean>'; 'quit' ends."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    _cpu_frame(0, kind, (48, 96), 32)                 # warm-up: numba JIT of the reference's tail functions (not timed)
+    print("ready", flush=True)
+    for line in sys.stdin:
+        parts = line.split()
+        if not parts or parts[0] == "quit":
+            break
+        f0, n = int(parts[1]), int(parts[2])
+        t0 = time.perf_counter()
+        m = 0.0
+        for i in range(n):
+            m += _cpu_frame(f0 + i, kind, "K", D)[1]
+        print(f"{time.perf_counter() - t0:.6f} {m / max(n, 1):.6f}", flush=True)
+
+
 class CpuBaseline:
+    """All host cores, one single-threaded worker process per core (the reference is single-threaded per frame:
+    models/rsgm/rsgm.py:44 passes numThreads=1), frame-parallel."""
+
     def __init__(self, cores=None):
-        import multiprocessing as mp
         from oracle import ref
         self.kind = "reference" if ref.available() else "port"
         if self.kind == "port":
             from oracle import oracle as orc
             orc.build()
-        self.cores = cores or len(os.sched_getaffinity(0))
-        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init)
-        # warm-up: numba JIT of the reference's tail functions in every worker (not timed)
-        self.pool.map(_cpu_frame, [(i, self.kind, (48, 96), True) for i in range(self.cores)], chunksize=1)
+        self.cores = cores or min(len(os.sched_getaffinity(0)), 64)
+        env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+        self.procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", self.kind], stdin=subprocess.PIPE,
+                                       stdout=subprocess.PIPE, text=True, env=env, cwd=ROOT) for _ in range(self.cores)]
+        for p in self.procs:
+            line = p.stdout.readline()
+            if line.strip() != "ready":
+                raise RuntimeError(f"cpu worker failed to start: {line!r}")
 
     def step(self, f0, frames=None):
-        """one bounded sample: `frames` K-shape frames spread over the pool; returns (frames, seconds, per-frame seconds)"""
+        """one bounded sample: `frames` K-shape frames spread over the workers; returns (frames, seconds, per-frame seconds)"""
         frames = frames or self.cores
+        per = [frames // self.cores + (1 if w < frames % self.cores else 0) for w in range(self.cores)]
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_frame, [(f0 + i, self.kind, "K", False) for i in range(frames)], chunksize=1)
+        off = 0
+        for p, n in zip(self.procs, per):
+            p.stdin.write(f"run {f0 + off} {n}\n"); p.stdin.flush()
+            off += n
+        lat = []
+        for p, n in zip(self.procs, per):
+            secs = float(p.stdout.readline().split()[0])
+            if n:
+                lat.append(secs / n)
         dt = time.perf_counter() - t0
-        return frames, dt, sum(r[0] for r in res) / len(res)
+        return frames, dt, sum(lat) / max(len(lat), 1)
 
     def close(self):
-        self.pool.close()
-        self.pool.join()
+        for p in self.procs:
+            try:
+                p.stdin.write("quit\n"); p.stdin.flush()
+                p.wait(timeout=30)
+            except Exception:
+                p.kill()
 
     def describe(self, frames_per_step, steps):
         what = "compiled reference (Cython vpp_core_opt + SSE pyrSGM + rsgm.py glue from oracle/_ref)" if self.kind == "reference" \
             else "C oracle port (oracle/*.c)"
-        return f"{what}; {steps} step(s) x {frames_per_step} K-shape frames (1242x375, D=192), one frame per worker process, {self.cores} processes"
+        return f"{what}; {steps} step(s) x {frames_per_step} K-shape frames (1242x375, D=192), frame-parallel over {self.cores} single-threaded worker processes"
 
 
 def run_reference_arm(args):
@@ -139,8 +170,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cb = CpuBaseline()
-    for w in range(args.warmup):
-        cb.step(10_000 + w * cb.cores, frames=min(cb.cores, 8))
+    for w in range(min(args.warmup, 1)):               # workers are already JIT-warm; one untimed sample is enough
+        cb.step(10_000 + w * cb.cores)
     tot_f, tot_t, lat = 0, 0.0, []
     for k in range(args.steps):
         f, dt, per = cb.step(k * cb.cores)
@@ -169,7 +200,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (default: one per core)")
+    ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_worker:
+        return cpu_worker_main(args.cpu_worker)
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -260,14 +294,13 @@ def main():
     for _ in range(2):
         pipe.run_host(left_h, right_h, hints_h)
     sync_all()
-    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
         res = pipe.run_host(left_h, right_h, hints_h)
     e1.record()
     sync_all()
-    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) * 0.0 + e0.elapsed_time(e1))
+    e2e_ms = e0.elapsed_time(e1)
     check_val = float(res[0].mean())
 
     # max over ranks

@@ -11,7 +11,7 @@ copied into the repo. Outputs (oracle/_ref/):
                             except -march=native -> -march=x86-64-v3 so the .so runs on the GPU box's host CPU)
   vpp_core_opt.<abi>.so  <- vpp_core/vpp_core_opt.pyx (cython -> C in a temp dir -> gcc -O2, baseline x86-64:
                             no FMA contraction, matching the reference's own default distutils build)
-  rsgm_ref.pyc, vpp_standalone_ref.pyc, filter_ref.pyc
+  rsgm_ref.pycode, vpp_standalone_ref.pycode, filter_ref.pycode
                          <- byte-compiled models/rsgm/rsgm.py, vpp_standalone.py, filter.py (glue + numba kernels)
 Run every process that calls pyrSGM with MALLOC_MMAP_THRESHOLD_=65536: the reference
 reads uninitialised malloc memory in census rows 0,1,H-2,H-1.
@@ -56,8 +56,8 @@ def build(force=False):
             _run([sys.executable, "-m", "cython", "-3", os.path.join(REF, "vpp_core/vpp_core_opt.pyx"), "-o", c_file])
             _run([CC, "-shared", "-fPIC", "-O2", "-fno-strict-overflow", "-DNDEBUG", "-w"] + inc + [c_file, "-o", so])
 
-    for src, dst in (("models/rsgm/rsgm.py", "rsgm_ref.pyc"), ("vpp_standalone.py", "vpp_standalone_ref.pyc"),
-                     ("filter.py", "filter_ref.pyc")):
+    for src, dst in (("models/rsgm/rsgm.py", "rsgm_ref.pycode"), ("vpp_standalone.py", "vpp_standalone_ref.pycode"),
+                     ("filter.py", "filter_ref.pycode")):
         d = os.path.join(OUT, dst)
         if force or not os.path.exists(d):
             py_compile.compile(os.path.join(REF, src), cfile=d, doraise=True)

@@ -44,11 +44,11 @@ def load():
     import cv2
     cv2.setNumThreads(0)  # as dataloaders/frame_utils.py:7 does
     ns = types.SimpleNamespace()
-    ns.pyrSGM = importlib.import_module("pyrSGM")          # rsgm_ref.pyc does `from pyrSGM import ...`
+    ns.pyrSGM = importlib.import_module("pyrSGM")          # rsgm_ref.pycode does `from pyrSGM import ...`
     ns.vpp_core_opt = importlib.import_module("vpp_core_opt")
-    ns.rsgm = _load_pyc("rsgm_ref", "rsgm_ref.pyc")
-    ns.vpp_standalone = _load_pyc("vpp_standalone_ref", "vpp_standalone_ref.pyc")
-    ns.filter = _load_pyc("filter_ref", "filter_ref.pyc")
+    ns.rsgm = _load_pyc("rsgm_ref", "rsgm_ref.pycode")
+    ns.vpp_standalone = _load_pyc("vpp_standalone_ref", "vpp_standalone_ref.pycode")
+    ns.filter = _load_pyc("filter_ref", "filter_ref.pycode")
     _cache = ns
     return ns
 

@@ -437,9 +437,9 @@ int launch_interp_clip(float *disp, int W, int H, int n, cudaStream_t st)
 // ------------------------------------------------------------------------------------------------------------
 // tail of compute_rsgm on the cropped H x W frame (models/rsgm/rsgm.py:275-292)
 // ------------------------------------------------------------------------------------------------------------
-// crop + _left_right_check(th=1) + zero mask==128 + astype(uint8); also seeds the component labels
+// crop + _left_right_check(th=1) + zero mask==128 + astype(uint8)
 __global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__restrict__ dr, uint8_t *__restrict__ u8,
-                                  int *__restrict__ label, int *__restrict__ count, RsgmDims d, long total)
+                                  RsgmDims d, long total)
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
@@ -458,19 +458,55 @@ __global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__r
             v = 0.0f;
         }
     }
-    const uint8_t b = (uint8_t)v;
-    u8[t] = b;
-    label[t] = b ? (int)t : -1;
-    count[t] = 0;
+    u8[t] = (uint8_t)v;
 }
 
 // cv2.filterSpeckles(img, 0, 200, 10) (rsgm.py:285): 4-connected components under |a-b| <= 10 among non-zero pixels,
-// components with <= 200 pixels are zeroed.  The relation is symmetric, so union-find labelling is order independent.
-__device__ __forceinline__ int uf_find(int *L, int i)
+// components with <= 200 pixels are zeroed.  The relation is symmetric, so the labelling is order independent.
+// Disparity maps are smooth: components are huge and rows consist of long runs.  Labelling therefore works on RUNS:
+//   rows   : every pixel gets the index of the first pixel of its horizontal run (warp max-scan per row)
+//   merge  : vertical links between runs by union-find (one union per pair of touching runs, not per pixel)
+//   count  : one atomicAdd per run (its length) on the root
+__device__ __forceinline__ bool spk_conn(int a, int b) { return a && b && abs(a - b) <= 10; }
+
+__global__ void __launch_bounds__(128) speckle_rows_kernel(const uint8_t *__restrict__ u8, int *__restrict__ label,
+                                                           int *__restrict__ count, int W, long total_rows)
+{
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const long base = row * W;
+    int carry = 0;                                   // run start of the last pixel of the previous chunk
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const int v = x < W ? u8[base + x] : 0;
+        const int left = (x > 0 && x < W) ? u8[base + x - 1] : 0;
+        int s = spk_conn(v, left) ? -1 : x;          // -1: continues the run of the pixel to the left
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if (lane >= o) s = max(s, t);
+        }
+        if (s < 0) s = carry;
+        carry = __shfl_sync(0xFFFFFFFFu, s, 31);
+        if (x < W) {
+            label[base + x] = v ? (int)(base + s) : -1;
+            count[base + x] = 0;
+        }
+    }
+}
+
+__device__ __forceinline__ int uf_find(const int *L, int i)
 {
     int p = L[i];
     while (p != i) { i = p; p = L[i]; }
     return i;
+}
+__device__ __forceinline__ int uf_find_compress(int *L, int i)
+{
+    const int r = uf_find(L, i);
+    while (i != r) { const int nx = L[i]; L[i] = r; i = nx; }   // only used when no union runs concurrently
+    return r;
 }
 __device__ __forceinline__ void uf_union(int *L, int a, int b)
 {
@@ -490,16 +526,31 @@ __global__ void speckle_merge_kernel(const uint8_t *__restrict__ u8, int *label,
     const int v = u8[t];
     if (!v) return;
     const int x = (int)(t % W), y = (int)((t / W) % H);
-    if (x + 1 < W) { const int q = u8[t + 1]; if (q && abs(q - v) <= 10) uf_union(label, (int)t, (int)t + 1); }
-    if (y + 1 < H) { const int q = u8[t + W]; if (q && abs(q - v) <= 10) uf_union(label, (int)t, (int)t + W); }
+    if (y + 1 >= H) return;
+    const int q = u8[t + W];
+    if (!spk_conn(v, q)) return;
+    if (x > 0) {
+        // the same pair of runs is already linked through the column to the left
+        const int vl = u8[t - 1], ql = u8[t + W - 1];
+        if (spk_conn(vl, v) && spk_conn(ql, q) && spk_conn(vl, ql)) return;
+    }
+    uf_union(label, label[t], label[t + W]);
 }
-__global__ void speckle_count_kernel(const uint8_t *__restrict__ u8, int *label, int *count, long total)
+__global__ void speckle_count_kernel(const uint8_t *__restrict__ u8, int *label, int *count, int W, long total)
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total || !u8[t]) return;
-    const int root = uf_find(label, (int)t);
-    label[t] = root;
-    atomicAdd(&count[root], 1);
+    if (t >= total) return;
+    const int v = u8[t];
+    if (!v) return;
+    const int x = (int)(t % W);
+    const bool run_end = (x == W - 1) || !spk_conn(v, u8[t + 1]);
+    if (!run_end) return;
+    // first pixel of this run: a non-start pixel still holds it (row kernel); a start pixel's own label may already
+    // point at another run's root, so a one-pixel run must not read its length from it
+    const bool is_start = (x == 0) || !spk_conn(u8[t - 1], v);
+    const int start = is_start ? (int)t : label[t];
+    const int root = uf_find_compress(label, start);
+    atomicAdd(&count[root], (int)(t - start) + 1);
 }
 // apply the speckle verdict, restore sub-pixel values (rsgm.py:286-290) and write the float frame
 __global__ void speckle_apply_kernel(const uint8_t *__restrict__ u8, const int *__restrict__ label, const int *__restrict__ count,
@@ -508,7 +559,11 @@ __global__ void speckle_apply_kernel(const uint8_t *__restrict__ u8, const int *
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     int b = u8[t];
-    if (b && count[label[t]] <= 200) b = 0;
+    if (b) {
+        const int start = label[t];                   // a non-start pixel still holds its run start
+        const int root = uf_find(label, start);
+        if (count[root] <= 200) b = 0;
+    }
     float v = (float)b;
     if (subpixel && b) {
         const int x = (int)(t % d.W), y = (int)((t / d.W) % d.H);
@@ -571,11 +626,16 @@ int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d,
     const long total = (long)n * d.H * d.W;
     if (total >= (1L << 31)) return VPPB200_ERR_ARG;
     const int blocks = cdiv(total, 256);
-    lrcheck_u8_kernel<<<blocks, 256, 0, st>>>(dl, dr, tb.u8, tb.label, tb.count, d, total);
+    lrcheck_u8_kernel<<<blocks, 256, 0, st>>>(dl, dr, tb.u8, d, total);
     VPP_LAUNCH_CHECK("lrcheck_u8_kernel");
+    {
+        const long nrows = (long)n * d.H;
+        speckle_rows_kernel<<<cdiv(nrows * 32, 128), 128, 0, st>>>(tb.u8, tb.label, tb.count, d.W, nrows);
+        VPP_LAUNCH_CHECK("speckle_rows_kernel");
+    }
     speckle_merge_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, d.W, d.H, total);
     VPP_LAUNCH_CHECK("speckle_merge_kernel");
-    speckle_count_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, total);
+    speckle_count_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, d.W, total);
     VPP_LAUNCH_CHECK("speckle_count_kernel");
     speckle_apply_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, dl, out, d, subpixel, total);
     VPP_LAUNCH_CHECK("speckle_apply_kernel");
