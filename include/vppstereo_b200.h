@@ -63,6 +63,16 @@ int vppb200_glibc_rand_fill(uint32_t *state34, uint8_t *out_host, int64_t n);
 int vppb200_stage_timing(int enable);
 int vppb200_stage_times(float *ms_out, int *calls_out);
 
+/* Tuning / test hooks (process-wide, not part of the reference's interface).  compute_rsgm aggregates with the
+ * cluster sweep of csrc/sgm_sweep.cu when the frame's strip state fits one cluster's shared memory and with the
+ * per-path kernels of csrc/sgm.cu otherwise; results are identical.
+ *   VPPB200_TUNE_SGM_MAX_STRIP: upper bound on columns per CTA strip (0 = as wide as shared memory allows); small
+ *                               values force multi-CTA clusters on small frames (parity tests of the halo exchange)
+ *   VPPB200_TUNE_SGM_SWEEP:     0 = always use the per-path kernels, 1 = default */
+#define VPPB200_TUNE_SGM_MAX_STRIP 0
+#define VPPB200_TUNE_SGM_SWEEP 1
+int vppb200_set_tuning(int key, int value);
+
 /* ---- pyrSGM operators ----------------------------------------------------------------------------------- */
 /* census5x5_SSE(src u8[H,W], dst u32[H,W], W, H)                       RSGM/pyrSGM.cpp:14, FastFilters.cpp:181-442.
  * Pixels the reference leaves unwritten (rows 0,1,H-2,H-1 and (H-3,{W-16,W-15,W-2,W-1})) are written as 0. */

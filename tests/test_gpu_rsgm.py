@@ -173,6 +173,35 @@ def test_compute_rsgm_vs_oracle(mods, orc, shape, D, channels, sub):
     assert_same(got, want, f"compute_rsgm {shape} D={D} C={channels}")
 
 
+@pytest.fixture
+def tuning(mods):
+    _lib = mods[3]
+    yield lambda key, value: _lib.set_tuning(key, value)
+    _lib.set_tuning(_lib.TUNE_SGM_MAX_STRIP, 0)
+    _lib.set_tuning(_lib.TUNE_SGM_SWEEP, 1)
+
+
+@pytest.mark.parametrize("strip", [1, 7, 16, 24, 50])
+@pytest.mark.parametrize("shape,D,channels", [((37, 70), 32, 3), ((40, 120), 64, 1), ((33, 200), 192, 3), ((30, 100), 72, 3),
+                                              ((24, 90), 256, 1)])
+def test_sweep_cluster_strips(mods, orc, tuning, strip, shape, D, channels):
+    """the cluster sweep with forced narrow strips (multi-CTA clusters, DSMEM halo exchange of the diagonal paths,
+    ring wrap-around) against the oracle, stage tap of the aggregated volume included"""
+    rsgm, synth, _lib = mods[1], mods[2], mods[3]
+    tuning(_lib.TUNE_SGM_MAX_STRIP, strip)
+    frames = [synth.make_pair(shape[0] + D + f, shape=shape, hints="random", channels=channels) for f in range(3)]
+    left = np.stack([p["left"] for p in frames]); right = np.stack([p["right"] for p in frames])
+    st = rsgm.compute_rsgm_stages(left, left, right, dmax=D)
+    for f, p in enumerate(frames):
+        want = orc.compute_rsgm(p["left"], p["left"], p["right"], dmax=D)
+        assert_same(st["out"][f], want, f"sweep strip={strip} {shape} D={D} frame {f}")
+    # the aggregated volume itself, against the stand-alone operator (generic per-path kernel) on the same inputs
+    tuning(_lib.TUNE_SGM_SWEEP, 0)
+    st0 = rsgm.compute_rsgm_stages(left, left, right, dmax=D)
+    assert_same(st["dsi_agg"], st0["dsi_agg"], f"aggregated volume, sweep strip={strip} vs per-path kernels")
+    assert_same(st["out"], st0["out"], "sweep vs per-path kernels, final disparity")
+
+
 def test_compute_rsgm_guided_and_batch(mods, orc):
     rsgm, synth = mods[1], mods[2]
     frames = [synth.make_pair(f, shape=(45, 100), hints="random") for f in range(3)]

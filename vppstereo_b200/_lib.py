@@ -23,7 +23,7 @@ SYMBOLS = [
     "vppb200_match_wta_right", "vppb200_subpixel_refine", "vppb200_median3x3",
     "vppb200_rsgm_workspace_bytes", "vppb200_compute_rsgm", "vppb200_compute_rsgm_tapped",
     "vppb200_vpp_workspace_bytes", "vppb200_vpp_scan_rnd", "vppb200_vpp_scan_max_dist", "vppb200_gt_reshape",
-    "vppb200_u8hwc_to_f32chw",
+    "vppb200_u8hwc_to_f32chw", "vppb200_set_tuning",
 ]
 
 _lib = None
@@ -48,6 +48,14 @@ def lib():
         l.vppb200_vpp_workspace_bytes.restype = C.c_size_t
         _lib = l
     return _lib
+
+
+TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP = 0, 1
+
+
+def set_tuning(key, value):
+    """Process-wide tuning / test hook (include/vppstereo_b200.h: vppb200_set_tuning)."""
+    check(lib().vppb200_set_tuning(int(key), int(value)), "set_tuning")
 
 
 def launch_count():

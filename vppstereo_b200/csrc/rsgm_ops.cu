@@ -231,7 +231,15 @@ int launch_guided_u8(uint8_t *dsi, const float *hints, const float *valid, const
 //          retires to disp_r[x'].  No atomics, no re-reads.
 //   sub-pixel (method 0, :1072-1102) optionally fused into the left result.
 // ------------------------------------------------------------------------------------------------------------
-template <int NW, bool LEFT, bool RIGHT, bool SUBPIX>
+// PLANE: S is in the internal plane layout of sgm_sweep.cu (word k*32 + lane of a pixel = disparities 2*NW*lane + 2k, +1)
+template <int NW, bool PLANE>
+__device__ __forceinline__ int s_at(const uint16_t *Srow, int x, int d, int D)
+{
+    if (PLANE) return Srow[((long)x * (NW * 32) + ((d % (2 * NW)) >> 1) * 32 + d / (2 * NW)) * 2 + (d & 1)];
+    return Srow[(long)x * D + d];
+}
+
+template <int NW, bool LEFT, bool RIGHT, bool SUBPIX, bool PLANE>
 __global__ void __launch_bounds__(128) wta_rows_kernel(const uint16_t *__restrict__ S, float *__restrict__ disp_l,
                                                        float *__restrict__ disp_r, int W, int H, int D,
                                                        const float *__restrict__ lut, long total_rows)
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(128) wta_rows_kernel(const uint16_t *__restric
     if (row >= total_rows) return;
     const int lane = threadIdx.x & 31;
     const int d0 = 2 * NW * lane;
-    const uint16_t *Srow = S + row * (long)W * D;
+    const uint16_t *Srow = S + row * (long)W * (PLANE ? NW * 64 : D);
     const bool lane_valid = d0 < D;            // D % 8 == 0 and 2*NW in {2,4,6,8}: a lane is all-valid or partly valid
     uint32_t bucket[2 * NW];
 #pragma unroll
@@ -253,7 +261,9 @@ __global__ void __launch_bounds__(128) wta_rows_kernel(const uint16_t *__restric
         for (int k = 0; k < NW; k++) {
             const int d = d0 + 2 * k;
             uint32_t w = 0xFFFFFFFFu;
-            if (lane_valid && d < D) w = *reinterpret_cast<const uint32_t *>(Srow + (long)x * D + d);
+            if (lane_valid && d < D)
+                w = PLANE ? reinterpret_cast<const uint32_t *>(Srow)[(long)x * (NW * 32) + k * 32 + lane]
+                          : *reinterpret_cast<const uint32_t *>(Srow + (long)x * D + d);
             key[2 * k] = (d < D) ? ((w << 16) | (uint32_t)d) : 0xFFFFFFFFu;
             key[2 * k + 1] = (d + 1 < D) ? ((w & 0xFFFF0000u) | (uint32_t)(d + 1)) : 0xFFFFFFFFu;
         }
@@ -268,8 +278,9 @@ __global__ void __launch_bounds__(128) wta_rows_kernel(const uint16_t *__restric
                 float out = (float)best;
                 if (SUBPIX && x >= 1 && x <= W - 2) {
                     if (best > 0) {
-                        const uint16_t *c = Srow + (long)x * D + best;      // best = D-1 reads the next pixel's d = 0
-                        const int c0 = c[-1], c1 = (int)(m >> 16), c2 = c[1];
+                        // best = D-1 reads the next pixel's d = 0 (xyd stream order)
+                        const int c0 = s_at<NW, PLANE>(Srow, x, best - 1, D), c1 = (int)(m >> 16);
+                        const int c2 = best + 1 < D ? s_at<NW, PLANE>(Srow, x, best + 1, D) : s_at<NW, PLANE>(Srow, x + 1, 0, D);
                         const int lower = min(c1 - c0, c1 - c2);            // <= 0
                         out = __fadd_rn((float)best, __fmul_rn((float)(c2 - c0), lut[-lower]));
                     } else {
@@ -293,32 +304,34 @@ __global__ void __launch_bounds__(128) wta_rows_kernel(const uint16_t *__restric
     }
 }
 
-template <bool LEFT, bool RIGHT, bool SUBPIX>
+template <bool LEFT, bool RIGHT, bool SUBPIX, bool PLANE>
 static int launch_wta_t(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int n, cudaStream_t st)
 {
     const long rows = (long)n * H;
     const int blocks = cdiv(rows * 32, 128);
     const int nw = (D + 63) / 64;
     switch (nw) {
-        case 1: wta_rows_kernel<1, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
-        case 2: wta_rows_kernel<2, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
-        case 3: wta_rows_kernel<3, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
-        default: wta_rows_kernel<4, LEFT, RIGHT, SUBPIX><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+        case 1: wta_rows_kernel<1, LEFT, RIGHT, SUBPIX, PLANE><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+        case 2: wta_rows_kernel<2, LEFT, RIGHT, SUBPIX, PLANE><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+        case 3: wta_rows_kernel<3, LEFT, RIGHT, SUBPIX, PLANE><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
+        default: wta_rows_kernel<4, LEFT, RIGHT, SUBPIX, PLANE><<<blocks, 128, 0, st>>>(S, dl, dr, W, H, D, lut, rows); break;
     }
     VPP_LAUNCH_CHECK("wta_rows_kernel");
     return VPPB200_OK;
 }
 int launch_wta_left(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st)
 {
-    return launch_wta_t<true, false, false>(S, disp, nullptr, W, H, D, nullptr, n, st);
+    return launch_wta_t<true, false, false, false>(S, disp, nullptr, W, H, D, nullptr, n, st);
 }
 int launch_wta_right(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st)
 {
-    return launch_wta_t<false, true, false>(S, nullptr, disp, W, H, D, nullptr, n, st);
+    return launch_wta_t<false, true, false, false>(S, nullptr, disp, W, H, D, nullptr, n, st);
 }
-int launch_wta_both_subpix(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int n, cudaStream_t st)
+int launch_wta_both_subpix(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int plane, int n,
+                           cudaStream_t st)
 {
-    return launch_wta_t<true, true, true>(S, dl, dr, W, H, D, lut, n, st);
+    if (plane) return launch_wta_t<true, true, true, true>(S, dl, dr, W, H, D, lut, n, st);
+    return launch_wta_t<true, true, true, false>(S, dl, dr, W, H, D, lut, n, st);
 }
 
 // subPixelRefine as a stand-alone operator (RSGM/StereoBMHelper.cpp:1065-1135), one thread per pixel
