@@ -191,87 +191,173 @@ int launch_unplane_s(const uint32_t *Sp, uint16_t *S, int W, int H, int D, int n
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// per-warp operand ring: the next pixels' costs (and S words) are brought into shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx) several steps ahead of the warp that consumes them, so that no sweep step
+// waits on HBM latency.  One lane produces, the whole warp consumes; a slot is refilled right after it was read.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // h-sweep: path r0 of one pass, one warp per image row (RSGM/StereoSGM_SSE.hpp:100-113,:219-236 for the recursion;
 // the line starts with L = C at the pass's first column and every pixel is summed into S).
-// P2 of 32 consecutive pixels is computed lane-parallel and broadcast per step.
+// Operands arrive through the ring in chunks of HCH pixels; P2 of 32 consecutive pixels is computed lane-parallel one
+// block ahead and broadcast per step.
 // ------------------------------------------------------------------------------------------------------------
+static constexpr int HCH = 4;      // pixels per ring slot
+static constexpr int HST = 2;      // ring slots per warp
+static constexpr int HWARPS = 4;   // warps per CTA
+
+template <int NW, bool STORE>
+__host__ __device__ constexpr int h_slot_bytes() { return HCH * NW * 32 * (STORE ? 2 : 6); }
+
 template <int NW, bool PAD, bool STORE>
-__global__ void __launch_bounds__(128) sgm_h_kernel(const uint8_t *__restrict__ img, const uint16_t *__restrict__ cost,
-                                                    uint32_t *__restrict__ S, int W, int D, int dirn, long total_rows)
+__global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__restrict__ img, const uint16_t *__restrict__ cost,
+                                                            uint32_t *__restrict__ S, int W, int D, int dirn, long total_rows)
 {
-    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    extern __shared__ __align__(16) uint8_t hsm[];
+    constexpr int PW = NW * 32;
+    constexpr int SLOTB = h_slot_bytes<NW, STORE>();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * HWARPS + warp;
     if (row >= total_rows) return;
-    const int lane = threadIdx.x & 31;
+    uint8_t *ring = hsm + warp * (HST * SLOTB);
+    const uint32_t ring_a = smem_u32(ring);
+    const uint32_t bars = smem_u32(hsm + HWARPS * HST * SLOTB) + warp * (HST * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < HST; q++) mbar_init(bars + q * 8, 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
     const uint8_t *irow = img + row * W;
-    const uint16_t *crow = cost + row * (long)W * (NW * 32) + lane;
-    uint32_t *srow = S + row * (long)W * (NW * 32) + lane;
+    const uint16_t *crow = cost + row * (long)W * PW;
+    uint32_t *srow = S + row * (long)W * PW;
     bool wv[NW];
 #pragma unroll
     for (int k = 0; k < NW; k++) wv[k] = !PAD || (2 * NW * lane + 2 * k < D);
-
-    uint32_t w[NW], cn[NW], sn[NW];
-    auto load_px = [&](int x, uint32_t (&c)[NW], uint32_t (&s)[NW]) {
-        const int o = x * (NW * 32);
-#pragma unroll
-        for (int k = 0; k < NW; k++) {
-            c[k] = __byte_perm((uint32_t)crow[o + k * 32], 0, 0x4140);        // two uint8 costs -> u16x2
-            if (!STORE) s[k] = srow[o + k * 32];
+    const int nchunks = W / HCH;
+    const int xs = dirn > 0 ? 0 : W - 1;
+    // chunk c covers pixels [xlo, xlo + HCH): forwards xlo = c*HCH, backwards xlo = W - (c+1)*HCH
+    auto produce = [&](int c) {
+        if (lane == 0 && c < nchunks) {
+            const int xlo = dirn > 0 ? c * HCH : W - (c + 1) * HCH;
+            const uint32_t slot = (uint32_t)c % HST;
+            const uint32_t dst = ring_a + slot * SLOTB, bar = bars + slot * 8;
+            mbar_expect_tx(bar, SLOTB);
+            tma_load_1d(dst, crow + (long)xlo * PW, HCH * PW * 2, bar);
+            if (!STORE) tma_load_1d(dst + HCH * PW * 2, srow + (long)xlo * PW, HCH * PW * 4, bar);
         }
     };
-    const int xs = dirn > 0 ? 0 : W - 1;
-    load_px(xs, cn, sn);
-    uint32_t p2v = 0;
-    for (int t = 0; t < W; t++) {
-        const int x = xs + dirn * t;
-        if ((t & 31) == 0) {
-            // P2 for steps t .. t+31: |I(x) - I(x - dirn)| inside the row (step 0 has no predecessor)
-            const int xx = xs + dirn * (t + lane);
-            int p2 = SW_P2MIN;
-            if (t + lane > 0 && t + lane < W) p2 = sw_adapt_p2(irow[xx], irow[xx - dirn]);
-            p2v = (uint32_t)(p2 - SW_P1) * 0x10001u;
-        }
-        uint32_t c[NW], s[NW];
 #pragma unroll
-        for (int k = 0; k < NW; k++) { c[k] = cn[k]; s[k] = sn[k]; }
-        if (t + 1 < W) load_px(x + dirn, cn, sn);
-        const uint32_t p2m = __shfl_sync(0xFFFFFFFFu, p2v, t & 31);
-        uint32_t nw[NW];
-        if (t == 0) {
-#pragma unroll
-            for (int k = 0; k < NW; k++) nw[k] = c[k];
-        } else {
-            sw_step<NW>(w, c, p2m, lane, nw);
+    for (int q = 0; q < HST; q++) produce(q);
+
+    auto p2_block = [&](int t0) -> uint32_t {
+        // (P2 - P1) * 0x10001 for step t0 + lane: |I(x) - I(x - dirn)| inside the row (step 0 has no predecessor)
+        const int t = t0 + lane;
+        int p2 = SW_P2MIN;
+        if (t > 0 && t < W) {
+            const int xx = xs + dirn * t;
+            p2 = sw_adapt_p2(irow[xx], irow[xx - dirn]);
         }
-        if (PAD) {
+        return (uint32_t)(p2 - SW_P1) * 0x10001u;
+    };
+    uint32_t p2v = p2_block(0), p2n = p2_block(32);
+    uint32_t w[NW];
 #pragma unroll
-            for (int k = 0; k < NW; k++) if (!wv[k]) nw[k] = SW_BIG2;
-        }
-        const uint32_t m2 = sw_min<NW>(nw) * 0x10001u;
-        const int o = x * (NW * 32);
+    for (int k = 0; k < NW; k++) w[k] = 0;
+    int t = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const uint32_t slot = (uint32_t)c % HST;
+        mbar_wait(bars + slot * 8, ((uint32_t)c / HST) & 1u);
+        const uint16_t *rc = reinterpret_cast<const uint16_t *>(ring + slot * SLOTB) + lane;
+        const uint32_t *rs = reinterpret_cast<const uint32_t *>(ring + slot * SLOTB + HCH * PW * 2) + lane;
+        const int xlo = dirn > 0 ? c * HCH : W - (c + 1) * HCH;
 #pragma unroll
-        for (int k = 0; k < NW; k++) {
-            w[k] = nw[k] - m2;
-            if (wv[k]) srow[o + k * 32] = STORE ? nw[k] : s[k] + nw[k];
+        for (int pp = 0; pp < HCH; pp++, t++) {
+            const int p = dirn > 0 ? pp : HCH - 1 - pp;
+            if ((t & 31) == 0 && t > 0) { p2v = p2n; p2n = p2_block(t + 32); }
+            uint32_t cc[NW], sv[NW];
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                cc[k] = __byte_perm((uint32_t)rc[p * PW + k * 32], 0, 0x4140);      // two uint8 costs -> u16x2
+                if (!STORE) sv[k] = rs[p * PW + k * 32];
+            }
+            const uint32_t p2m = __shfl_sync(0xFFFFFFFFu, p2v, t & 31);
+            uint32_t nw[NW];
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < NW; k++) nw[k] = cc[k];
+            } else {
+                sw_step<NW>(w, cc, p2m, lane, nw);
+            }
+            if (PAD) {
+#pragma unroll
+                for (int k = 0; k < NW; k++) if (!wv[k]) nw[k] = SW_BIG2;
+            }
+            const uint32_t m2 = sw_min<NW>(nw) * 0x10001u;
+            uint32_t *so = srow + (long)(xlo + p) * PW + lane;
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                w[k] = nw[k] - m2;
+                if (wv[k]) so[k * 32] = STORE ? nw[k] : sv[k] + nw[k];
+            }
         }
+        __syncwarp();
+        produce(c + HST);
     }
+}
+
+template <int NW, bool PAD, bool STORE>
+static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, int W, int H, int D, int dirn, int n, cudaStream_t st)
+{
+    const long rows = (long)n * H;
+    const int blocks = cdiv(rows, HWARPS);
+    const size_t smem = (size_t)HWARPS * HST * h_slot_bytes<NW, STORE>() + HWARPS * HST * 8;
+    auto kern = sgm_h_kernel<NW, PAD, STORE>;
+    if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, W, D, dirn, rows);
+    VPP_LAUNCH_CHECK("sgm_h_kernel");
+    return VPPB200_OK;
 }
 
 template <int NW>
 static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, int W, int H, int D, int dirn, bool store, int n,
                  cudaStream_t st)
 {
-    const long rows = (long)n * H;
-    const int blocks = cdiv(rows * 32, 128);
     const bool pad = (D != 64 * NW);
-    if (store) {
-        if (pad) sgm_h_kernel<NW, true, true><<<blocks, 128, 0, st>>>(img, cost, S, W, D, dirn, rows);
-        else sgm_h_kernel<NW, false, true><<<blocks, 128, 0, st>>>(img, cost, S, W, D, dirn, rows);
-    } else {
-        if (pad) sgm_h_kernel<NW, true, false><<<blocks, 128, 0, st>>>(img, cost, S, W, D, dirn, rows);
-        else sgm_h_kernel<NW, false, false><<<blocks, 128, 0, st>>>(img, cost, S, W, D, dirn, rows);
-    }
-    VPP_LAUNCH_CHECK("sgm_h_kernel");
-    return VPPB200_OK;
+    if (store) return pad ? run_h_t<NW, true, true>(img, cost, S, W, H, D, dirn, n, st)
+                          : run_h_t<NW, false, true>(img, cost, S, W, H, D, dirn, n, st);
+    return pad ? run_h_t<NW, true, false>(img, cost, S, W, H, D, dirn, n, st)
+               : run_h_t<NW, false, false>(img, cost, S, W, H, D, dirn, n, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -285,18 +371,20 @@ struct VArgs {
 };
 
 static constexpr int SWV_WARPS = 16;
+static constexpr int VRING = 4;    // operand ring slots (pixels in flight) per warp
 
 template <int NW, bool PAD>
 __global__ void __launch_bounds__(SWV_WARPS * 32, 1) sgm_v_kernel(const uint8_t *__restrict__ img_all,
                                                                   const uint16_t *__restrict__ cost_all,
                                                                   uint32_t *__restrict__ S_all, VArgs a)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / a.csize, nclusters = gridDim.x / a.csize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int PW = NW * 32;                    // words per pixel-path state
+    constexpr int SLOTB = 6 * PW;                  // ring slot: PW u16 costs + PW u32 S words
     const int W = a.W, H = a.H;
     const int x0 = rank * a.SC;
     const int nc = min(a.SC, W - x0);              // columns of this strip (>= 1, checked by the launcher)
@@ -307,6 +395,9 @@ __global__ void __launch_bounds__(SWV_WARPS * 32, 1) sgm_v_kernel(const uint8_t 
     uint32_t *halo1 = st + 3 * a.SC * PW;           // [2][PW]  r1 state of the line entering this strip
     uint32_t *halo3 = halo1 + 2 * PW;               // [2][PW]  r3 state of the line entering this strip
     uint4 *p2tab = reinterpret_cast<uint4 *>(halo3 + 2 * PW);   // [2][SC]  (P2 - P1) * 0x10001 for r1, r2, r3
+    uint8_t *ring = reinterpret_cast<uint8_t *>(p2tab + 2 * a.SC) + warp * (VRING * SLOTB);
+    const uint32_t ring_a = smem_u32(ring);
+    const uint32_t bars = smem_u32(reinterpret_cast<uint8_t *>(p2tab + 2 * a.SC) + SWV_WARPS * VRING * SLOTB) + warp * (VRING * 8);
     // r1 lines move by +dj per row, r3 lines by -dj: where a leaving line's state goes
     uint32_t *push1 = (rank + dj >= 0 && rank + dj < a.csize) ? cluster.map_shared_rank(halo1, rank + dj) : nullptr;
     uint32_t *push3 = (rank - dj >= 0 && rank - dj < a.csize) ? cluster.map_shared_rank(halo3, rank - dj) : nullptr;
@@ -316,10 +407,41 @@ __global__ void __launch_bounds__(SWV_WARPS * 32, 1) sgm_v_kernel(const uint8_t 
     for (int k = 0; k < NW; k++) wv[k] = !PAD || (2 * NW * lane + 2 * k < a.D);
 
     const long npx = (long)W * H;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < VRING; q++) mbar_init(bars + q * 8, 1);
+        mbar_init_fence();
+    }
+    __syncwarp();
+    // this warp's pixel stream: frames f = cid, cid + nclusters, ...; rows in sweep order; columns warp, warp + 16, ...
+    int pf = cid, ps = 0, pjl = warp;               // producer position
+    unsigned pq = 0, cq = 0;                        // pixels produced / consumed
+    auto produce = [&]() {
+        if (pf < a.n) {
+            if (lane == 0) {
+                const long px = (long)pf * npx + (long)(i1 + ps * di) * W + x0 + pjl;
+                const uint32_t slot = pq % VRING;
+                const uint32_t dst = ring_a + slot * SLOTB, bar = bars + slot * 8;
+                mbar_expect_tx(bar, SLOTB);
+                tma_load_1d(dst, cost_all + px * PW, 2 * PW, bar);
+                tma_load_1d(dst + 2 * PW, S_all + px * PW, 4 * PW, bar);
+            }
+            pq++;
+            pjl += SWV_WARPS;
+            if (pjl >= nc) {
+                pjl = warp;
+                if (++ps == H) { ps = 0; pf += nclusters; }
+            }
+        }
+    };
+    if (warp < nc) {
+#pragma unroll
+        for (int q = 0; q < VRING; q++) produce();
+    }
+
     unsigned gstep = 0;                             // rows processed by this cluster so far (halo / P2 double-buffer parity)
     for (int f = cid; f < a.n; f += nclusters) {
         const uint8_t *img = img_all + f * npx;
-        const uint16_t *cost = cost_all + f * npx * PW + lane;
         uint32_t *S = S_all + f * npx * PW + lane;
         int sh = 0;                                 // s mod nc
         for (int s = 0; s < H; s++, gstep++) {
@@ -329,21 +451,20 @@ __global__ void __launch_bounds__(SWV_WARPS * 32, 1) sgm_v_kernel(const uint8_t 
             const uint4 *p2row = p2tab + par * a.SC;
             const uint32_t *h1in = halo1 + (par ^ 1u) * PW, *h3in = halo3 + (par ^ 1u) * PW;
 
-            uint32_t cn[NW], sn[NW];
-            auto load_px = [&](int jl, uint32_t (&c)[NW], uint32_t (&sv)[NW]) {
-                const int o = (i * W + x0 + jl) * PW;
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    c[k] = __byte_perm((uint32_t)cost[o + k * 32], 0, 0x4140);
-                    sv[k] = s > 0 ? S[o + k * 32] : 0u;
-                }
-            };
-            if (warp < nc) load_px(warp, cn, sn);
             for (int jl = warp; jl < nc; jl += SWV_WARPS) {
+                const uint32_t slot = cq % VRING;
+                mbar_wait(bars + slot * 8, (cq / VRING) & 1u);
+                cq++;
+                const uint16_t *rc = reinterpret_cast<const uint16_t *>(ring + slot * SLOTB) + lane;
+                const uint32_t *rs = reinterpret_cast<const uint32_t *>(ring + slot * SLOTB + 2 * PW) + lane;
                 uint32_t c[NW], sv[NW];
 #pragma unroll
-                for (int k = 0; k < NW; k++) { c[k] = cn[k]; sv[k] = sn[k]; }
-                if (jl + SWV_WARPS < nc) load_px(jl + SWV_WARPS, cn, sn);
+                for (int k = 0; k < NW; k++) {
+                    c[k] = __byte_perm((uint32_t)rc[k * 32], 0, 0x4140);
+                    sv[k] = rs[k * 32];
+                }
+                __syncwarp();
+                produce();                          // refill the slot that was just read
                 const int j = x0 + jl;
                 // ring slots: a line moving +1 column per row sits in slot (jl - s) mod nc, one moving -1 in (jl + s) mod nc
                 int slotA = jl - sh; if (slotA < 0) slotA += nc;
@@ -440,7 +561,8 @@ __global__ void __launch_bounds__(SWV_WARPS * 32, 1) sgm_v_kernel(const uint8_t 
     if (gstep > 0) cluster.barrier_wait();          // nobody leaves while a neighbour may still push into its halo
 }
 
-static size_t v_smem_bytes(int NW, int SC) { return (size_t)(3 * SC * NW * 32 + 4 * NW * 32) * 4 + (size_t)2 * SC * 16; }
+static size_t v_fixed_bytes(int NW) { return (size_t)4 * NW * 32 * 4 + (size_t)SWV_WARPS * VRING * (6 * NW * 32 + 8); }
+static size_t v_smem_bytes(int NW, int SC) { return (size_t)3 * SC * NW * 32 * 4 + (size_t)2 * SC * 16 + v_fixed_bytes(NW); }
 
 // tuning / test hook: upper bound on the strip width (0 = as wide as shared memory allows)
 static int g_max_strip = 0;
@@ -455,7 +577,8 @@ static int plan_v(int W, int n, VPlan *plan)
     int dev = 0, smem_optin = 0;
     VPP_CUDA_TRY(cudaGetDevice(&dev));
     VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    int sc_max = (int)(((size_t)smem_optin - (size_t)4 * NW * 32 * 4) / ((size_t)3 * NW * 32 * 4 + 32));
+    if ((size_t)smem_optin <= v_fixed_bytes(NW)) return 1;
+    int sc_max = (int)(((size_t)smem_optin - v_fixed_bytes(NW)) / ((size_t)3 * NW * 32 * 4 + 32));
     if (g_max_strip > 0 && g_max_strip < sc_max) sc_max = g_max_strip;
     if (sc_max < 1) return VPPB200_ERR_ARG;
     int csize = 1;
