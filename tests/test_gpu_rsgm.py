@@ -181,9 +181,9 @@ def tuning(mods):
     _lib.set_tuning(_lib.TUNE_SGM_SWEEP, 1)
 
 
-@pytest.mark.parametrize("strip", [1, 7, 16, 24, 50])
+@pytest.mark.parametrize("strip", [32, 64, 100])
 @pytest.mark.parametrize("shape,D,channels", [((37, 70), 32, 3), ((40, 120), 64, 1), ((33, 200), 192, 3), ((30, 100), 72, 3),
-                                              ((24, 90), 256, 1)])
+                                              ((24, 90), 256, 1), ((20, 150), 8, 1), ((26, 330), 16, 3)])
 def test_sweep_cluster_strips(mods, orc, tuning, strip, shape, D, channels):
     """the cluster sweep with forced narrow strips (multi-CTA clusters, DSMEM halo exchange of the diagonal paths,
     ring wrap-around) against the oracle, stage tap of the aggregated volume included"""

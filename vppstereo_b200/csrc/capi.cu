@@ -105,10 +105,10 @@ static size_t rsgm_ws_layout(const RsgmDims &d, int n, void *base, RsgmWs *ws)
     RsgmWs w;
     w.gray_l = (uint8_t *)take(np); w.gray_r = (uint8_t *)take(np); w.guide = (uint8_t *)take(np);
     w.census_l = (uint32_t *)take(np * 4); w.census_r = (uint32_t *)take(np * 4);
-    const size_t Dp = (size_t)((d.D + 63) / 64) * 64;        // the plane layout pads a pixel to 64-disparity groups
-    w.dsi = (uint8_t *)take(np * Dp);
-    w.S = (uint16_t *)take(np * Dp * 2);
-    w.S_xyd = (uint16_t *)take(np * d.D * 2);               // un-permuted copy for the test tap / scratch
+    const size_t tv = tile_volume_elems(d.Wp, d.Hp, d.D, n);  // layout T pads the width to 32-column groups
+    w.dsi = (uint8_t *)take(tv > np * d.D ? tv : np * d.D);
+    w.S = (uint16_t *)take((tv > np * d.D ? tv : np * d.D) * 2);
+    w.S_xyd = (uint16_t *)take(np * d.D * 2);                 // the reference's xyd order (WTA input, test tap)
     w.dl = (float *)take(np * 4); w.dlf = (float *)take(np * 4); w.dr = (float *)take(np * 4); w.drf = (float *)take(np * 4);
     w.tail.u8 = (uint8_t *)take(nc); w.tail.label = (int *)take(nc * 4); w.tail.count = (int *)take(nc * 4);
     if (ws) *ws = w;
@@ -328,22 +328,24 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
     tm.mark();
     // rsgm.py:263-268  Hamming volume (+ optional guided modulation); rsgm.py:270  8-path aggregation (effective default
     // parameters); rsgm.py:272-273  WTA left (+ equiangular sub-pixel) and right
-    const bool plane = aggregate_plane_supported(d.Wp, d.Hp, D, n);
-    if (plane) {
-        if ((rc = launch_cost_plane(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
-        if (hints && (rc = launch_guided_plane(w.dsi, hints, validhints, d, n, st))) return rc;
+    const bool tiled = aggregate_tile_supported(d.Wp, d.Hp, D, n);
+    const uint16_t *S_final = w.S;
+    if (tiled) {
+        if ((rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
+        if (hints && (rc = launch_guided_tile(w.dsi, hints, validhints, d, n, st))) return rc;
         tm.mark();
-        if ((rc = launch_aggregate_plane(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, 1, st))) return rc < 0 ? rc : VPPB200_ERR_ARG;
+        if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc < 0 ? rc : VPPB200_ERR_ARG;
         tm.mark();
-        if ((rc = launch_wta_both_subpix(w.S, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 1, n, st))) return rc;
+        if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
+        S_final = w.S_xyd;
     } else {
         if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
         if (hints && (rc = launch_guided_u8(w.dsi, hints, validhints, d, n, st))) return rc;
         tm.mark();
         if ((rc = launch_aggregate_fast(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc;
         tm.mark();
-        if ((rc = launch_wta_both_subpix(w.S, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
     }
+    if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
     tm.mark();
     if ((rc = launch_median(w.dl, w.dlf, d.Wp, d.Hp, n, st))) return rc;
     if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, st))) return rc;
@@ -358,14 +360,7 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
         const size_t np = (size_t)n * d.Hp * d.Wp;
         if (taps->census_l) VPP_CUDA_TRY(cudaMemcpyAsync(taps->census_l, w.census_l, np * 4, cudaMemcpyDeviceToDevice, st));
         if (taps->census_r) VPP_CUDA_TRY(cudaMemcpyAsync(taps->census_r, w.census_r, np * 4, cudaMemcpyDeviceToDevice, st));
-        if (taps->dsi_agg) {
-            const uint16_t *src = w.S;
-            if (plane) {
-                if ((rc = launch_unplane_s(reinterpret_cast<const uint32_t *>(w.S), w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
-                src = w.S_xyd;
-            }
-            VPP_CUDA_TRY(cudaMemcpyAsync(taps->dsi_agg, src, np * D * 2, cudaMemcpyDeviceToDevice, st));
-        }
+        if (taps->dsi_agg) VPP_CUDA_TRY(cudaMemcpyAsync(taps->dsi_agg, S_final, np * D * 2, cudaMemcpyDeviceToDevice, st));
         if (taps->disp_l) VPP_CUDA_TRY(cudaMemcpyAsync(taps->disp_l, w.dlf, np * 4, cudaMemcpyDeviceToDevice, st));
         if (taps->disp_r) VPP_CUDA_TRY(cudaMemcpyAsync(taps->disp_r, w.drf, np * 4, cudaMemcpyDeviceToDevice, st));
     }

@@ -53,13 +53,13 @@ int launch_guided_u8(uint8_t *dsi, const float *hints, const float *valid, const
 int launch_aggregate_generic(const uint8_t *img, const uint16_t *dsi, uint16_t *S, int W, int H, int D, int P1, int P2min,
                              float alpha, int gamma, int n, cudaStream_t st);
 int launch_aggregate_fast(const uint8_t *img, const uint8_t *dsi, uint16_t *S, int W, int H, int D, int n, cudaStream_t st);
-// sgm_sweep.cu: plane-layout cost volume + 4-sweep aggregation with on-chip path state (cluster per frame)
-bool aggregate_plane_supported(int W, int H, int D, int n);
-int launch_cost_plane(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st);
-int launch_guided_plane(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st);
-int launch_aggregate_plane(const uint8_t *img, const uint8_t *cost, uint16_t *S, int W, int H, int D, int n, int h_bwd,
-                           cudaStream_t st);
-int launch_unplane_s(const uint32_t *Sp, uint16_t *S, int W, int H, int D, int n, cudaStream_t st);
+// sgm_sweep.cu: layout-T cost volume + 4-sweep aggregation with on-chip path state (cluster per frame)
+bool aggregate_tile_supported(int W, int H, int D, int n);
+size_t tile_volume_elems(int W, int H, int D, int n);
+int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st);
+int launch_guided_tile(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st);
+int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost, uint16_t *S, int W, int H, int D, int n, cudaStream_t st);
+int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, int n, cudaStream_t st);
 void sweep_set_max_strip(int cols);
 void sweep_set_enabled(int on);
 int launch_wta_both_subpix(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int plane, int n,

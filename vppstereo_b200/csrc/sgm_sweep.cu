@@ -7,26 +7,29 @@
 //   h-sweep fwd  : r0 of pass 0, one warp per image row, path state in registers, S  = L          (store)
 //   v-sweep down : r1+r2+r3 of pass 0 together, S += L1+L2+L3                                      (one RMW)
 //   v-sweep up   : r1+r2+r3 of pass 1 together, S += L1+L2+L3                                      (one RMW)
-//   h-sweep bwd  : r0 of pass 1, S += L  (stand-alone), or fused into the WTA row sweep (rsgm_ops.cu) so that the
-//                  final S is never written
-// v-sweep: a thread-block CLUSTER owns one frame; CTA c owns a strip of columns and keeps the three paths' previous-row
-// state L_r(.,d) for its strip in shared memory (3 x strip x D x 2 B, ~180 KB at D=192 / 156 columns).  Rows are swept
-// in order; a warp handles one pixel at a time (lane l holds disparities [2*NW*l, 2*NW*(l+1)) as u16x2 words).
-// Diagonal state is stored per LINE in a ring (slot = (column -/+ row) mod strip) so a line's state never moves;
-// only the line that leaves the strip is pushed into the neighbour CTA's halo through distributed shared memory,
-// one cluster barrier per row (arrive after the row, wait before the next one).
+//   h-sweep bwd  : r0 of pass 1, S += L
+//
+// v-sweep (the heavy one: 6 of the 8 paths).  A thread-block CLUSTER owns one frame; CTA c owns a strip of 32-column
+// groups and keeps the three paths' previous-row values L_r(x, d) of its strip in shared memory (~188 KB at D = 192 /
+// 160 columns).  LANE = COLUMN: a warp owns 32 adjacent columns x one third of the disparity range and walks the
+// disparities sequentially, so L[d-1], L[d], L[d+1] are a register window, min_d is a running minimum, P2 is per lane --
+// no shuffles, no warp reductions, ~30 instructions per (32 pixels x 2 disparities x 3 paths).
+// Diagonal state is stored per LINE (ring slot = (column -/+ row) mod strip) so a line's state never moves; only the
+// line that leaves the strip is pushed into the neighbour CTA's halo slot through distributed shared memory, one
+// cluster barrier per row.  Lines that enter through the image border read a constant "border slot".
 //
 // Arithmetic: the "fast" domain of sgm.cu -- uint8 costs, the effective default parameters (P1=7, P2min=17,
-// Alpha=0.25, Gamma=50 => P2 in [17,50]), so no uint16 saturation is reachable (L <= 255+50, S <= 8*305).
-// State is kept NORMALISED (L - min_d L): L_new = C + min(L'[d], min(L'[d-1], L'[d+1]) + P1, P2) is the reference's
-// C + min(L[d], L[d+-1]+P1, minL+P2) - minL.
+// Alpha=0.25, Gamma=50 => P2 in [17,50]), so no uint16 saturation is reachable (L <= 255+50, S <= 8*305); packed
+// u16x2 DPX min/add (VIMNMX3 / VIADDMNMX).
 //
-// Internal "plane" layouts (per pixel, NW = ceil(D/64) words per lane): word index k*32 + lane holds disparities
-// d = 2*NW*lane + 2k (low half) and d+1 (high half); costs 1 byte per disparity (u16 words), S 2 bytes (u32 words).
-// Every warp-wide access is one contiguous 64 B / 128 B segment.  For D = 64*NW this is a permutation of the
-// reference's xyd order inside a pixel; vppb200 un-permutes it for the test tap only.
+// Internal "tile" layout T of the cost volume and of S (K2 = D/2 disparity pairs, G = ceil(W/32) column groups):
+//   word (y, x, k) = (((y*G + x/32)*K2 + k)*32 + x%32), low half = disparity 2k, high half = 2k+1;
+//   costs are uint8 (uint16 words), S is uint16 (uint32 words).  A v-sweep warp reads/writes 64 B / 128 B rows of a
+//   tile; an h-sweep warp (lane = disparity chunk) gathers 8-column chunks of a tile with cp.async into a padded
+//   shared-memory transpose.  vppb200 converts S to the reference's xyd order for WTA / the test tap.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -38,12 +41,150 @@ static constexpr int SW_P1 = 7, SW_P2MIN = 17, SW_GAMMA = 50;
 static constexpr float SW_ALPHA = 0.25f;
 static constexpr uint32_t SW_P1X2 = 0x00070007u;
 
+struct TL {
+    int W, H, D, K2, G;
+    long frame;        // words per frame = H*G*K2*32
+};
+static TL make_tl(int W, int H, int D)
+{
+    TL t;
+    t.W = W; t.H = H; t.D = D; t.K2 = D / 2; t.G = (W + 31) / 32;
+    t.frame = (long)H * t.G * t.K2 * 32;
+    return t;
+}
+
 __device__ __forceinline__ int sw_adapt_p2(int ip, int ipr)
 {
     // (sint32)(-alpha * abs(I_p - I_pr) + gamma), clamped below by P2min  (RSGM/StereoSGM.hpp:92-99)
     const int r = (int)__fadd_rn(__fmul_rn(-SW_ALPHA, (float)abs(ip - ipr)), (float)SW_GAMMA);
     return r < SW_P2MIN ? SW_P2MIN : r;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// cost volume in layout T: popc(L ^ R[x-d]) for d <= x on rows 2..H-3, 12 elsewhere (RSGM/StereoBMHelper.cpp:29-140).
+// One warp per tile, lane = column; padding columns (x >= W) hold 0.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cost_tile_kernel(const uint32_t *__restrict__ cl, const uint32_t *__restrict__ cr,
+                                                        uint16_t *__restrict__ cost, TL t, long total_tiles)
+{
+    const long tile = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (tile >= total_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int g = (int)(tile % t.G);
+    const long row = tile / t.G;                   // row over all frames
+    const int y = (int)(row % t.H);
+    const int x = g * 32 + lane;
+    uint16_t *out = cost + tile * t.K2 * 32 + lane;
+    if (x >= t.W) {
+        for (int k = 0; k < t.K2; k++) out[k * 32] = 0;
+        return;
+    }
+    if (y < 2 || y >= t.H - 2) {
+        for (int k = 0; k < t.K2; k++) out[k * 32] = 0x0C0Cu;
+        return;
+    }
+    const uint32_t l = cl[row * t.W + x];
+    const uint32_t *rp = cr + row * t.W + x;
+#pragma unroll 4
+    for (int k = 0; k < t.K2; k++) {
+        const int dlo = 2 * k;
+        const uint32_t vlo = dlo > x ? 12u : (uint32_t)__popc(l ^ rp[-dlo]);
+        const uint32_t vhi = dlo + 1 > x ? 12u : (uint32_t)__popc(l ^ rp[-dlo - 1]);
+        out[k * 32] = (uint16_t)(vlo | (vhi << 8));
+    }
+}
+
+int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st)
+{
+    const TL t = make_tl(W, H, D);
+    const long tiles = (long)n * H * t.G;
+    cost_tile_kernel<<<cdiv(tiles * 32, 256), 256, 0, st>>>(cl, cr, reinterpret_cast<uint16_t *>(cost), t, tiles);
+    VPP_LAUNCH_CHECK("cost_tile_kernel");
+    return VPPB200_OK;
+}
+
+// _guided_dsi (models/rsgm/rsgm.py:115-127) on the layout-T u8 volume; arithmetic as guided_u8_kernel (rsgm_ops.cu)
+__global__ void guided_tile_kernel(uint8_t *__restrict__ cost, const float *__restrict__ hints, const float *__restrict__ valid,
+                                   RsgmDims d, TL t, long total)
+{
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int dd = (int)(i % d.D);
+    const long px = i / d.D;
+    const int xp = (int)(px % d.Wp), yp = (int)((px / d.Wp) % d.Hp);
+    const int x = xp - d.pl, y = yp - d.pt;
+    const long f = px / ((long)d.Wp * d.Hp);
+    if (x < 0 || x >= d.W || y < 0 || y >= d.H) return;
+    const long s = (f * d.H + y) * d.W + x;
+    if (!(valid[s] > 0)) return;
+    const double tt = __dsub_rn((double)hints[s], (double)dd);
+    const float w = (float)__dmul_rn(10.0, __dsub_rn(1.0, exp(__ddiv_rn(-__dmul_rn(tt, tt), 2.0))));
+    const long word = f * t.frame + (((long)yp * t.G + xp / 32) * t.K2 + dd / 2) * 32 + xp % 32;
+    uint8_t *p = cost + word * 2 + (dd & 1);
+    *p = (uint8_t)(uint16_t)__dmul_rn((double)*p, (double)w);
+}
+int launch_guided_tile(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st)
+{
+    const TL t = make_tl(d.Wp, d.Hp, d.D);
+    long total = (long)n * d.Hp * d.Wp * d.D;
+    guided_tile_kernel<<<cdiv(total, 256), 256, 0, st>>>(cost, hints, valid, d, t, total);
+    VPP_LAUNCH_CHECK("guided_tile_kernel");
+    return VPPB200_OK;
+}
+
+// layout-T S -> the reference's xyd order (uint16 [px][D]); one warp per tile through a padded shared-memory transpose
+__global__ void __launch_bounds__(128) s_tile_to_xyd_kernel(const uint32_t *__restrict__ St, uint32_t *__restrict__ Sx, TL t,
+                                                            long total_tiles)
+{
+    extern __shared__ uint32_t tsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long tile = (long)blockIdx.x * 4 + warp;
+    if (tile >= total_tiles) return;
+    uint32_t *sm = tsm + (size_t)warp * t.K2 * 33;
+    const uint32_t *src = St + tile * t.K2 * 32 + lane;
+    for (int k = 0; k < t.K2; k++) sm[k * 33 + lane] = src[k * 32];
+    __syncwarp();
+    const int g = (int)(tile % t.G);
+    const long row = tile / t.G;
+    for (int c = 0; c < 32; c++) {
+        const int x = g * 32 + c;
+        if (x >= t.W) break;
+        uint32_t *dst = Sx + (row * t.W + x) * t.K2;
+        for (int k = lane; k < t.K2; k += 32) dst[k] = sm[k * 33 + c];
+    }
+}
+int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, int n, cudaStream_t st)
+{
+    const TL t = make_tl(W, H, D);
+    const long tiles = (long)n * H * t.G;
+    const size_t smem = (size_t)4 * t.K2 * 33 * 4;
+    if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(s_tile_to_xyd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    s_tile_to_xyd_kernel<<<cdiv(tiles, 4), 128, smem, st>>>(reinterpret_cast<const uint32_t *>(St),
+                                                            reinterpret_cast<uint32_t *>(Sx), t, tiles);
+    VPP_LAUNCH_CHECK("s_tile_to_xyd_kernel");
+    return VPPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// h-sweep: path r0 of one pass, one warp per image row, lane l owns disparity pairs [NW*l, NW*(l+1))
+// (RSGM/StereoSGM_SSE.hpp:100-113,:219-236 for the recursion; the line starts with L = C at the pass's first column and
+// every pixel is summed into S).  State is kept NORMALISED (L - min_d L): L_new = C + min(L'[d], min(L'[d-1], L'[d+1])
+// + P1, P2).  Operands arrive in 8-column chunks: cp.async gathers the chunk's K2 rows of a tile into shared memory
+// with odd row strides (bank-conflict-free transposed reads), two chunks in flight per warp; results go back through
+// the same chunk buffer so that the global stores are full 32-byte sectors.
+// ------------------------------------------------------------------------------------------------------------
+static constexpr int HWARPS = 4;   // warps per CTA
+static constexpr int HCROW = 16;   // bytes of a staged cost row: 8 columns x uint16 (16-byte pieces, dense)
+static constexpr int HSROW = 48;   // bytes of a staged S row: 8 columns x uint32 + 16 B pad (3 pieces: odd => LDS.128 conflict-free)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // one SGM step on normalised state: nw = c + min(w[d], min(w[d-1], w[d+1]) + P1, P2);  p2m = (P2 - P1) * 0x10001
 template <int NW>
@@ -81,603 +222,572 @@ __device__ __forceinline__ uint32_t sw_min(const uint32_t (&v)[NW])
     return __reduce_min_sync(0xFFFFFFFFu, mm);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// cost volume in plane layout: popc(L ^ R[x-d]) for d <= x on rows 2..H-3, 12 elsewhere (RSGM/StereoBMHelper.cpp:29-140)
-// One warp produces PX adjacent pixels of a row; lane l owns disparities [2*NW*l, 2*NW*(l+1)) and keeps the
-// PX + 2*NW - 1 right-census words it needs in registers.
-// ------------------------------------------------------------------------------------------------------------
-template <int NW, int PX>
-__global__ void __launch_bounds__(256) cost_plane_kernel(const uint32_t *__restrict__ cl, const uint32_t *__restrict__ cr,
-                                                         uint16_t *__restrict__ cost, int W, int H, int D, long total_groups)
-{
-    const long grp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (grp >= total_groups) return;
-    const int lane = threadIdx.x & 31;
-    const int gpr = W / PX;                        // W % 16 == 0, PX divides 16
-    const long row = grp / gpr;                    // row over all frames
-    const int x0 = (int)(grp % gpr) * PX;
-    const int y = (int)(row % H);
-    const int d0 = 2 * NW * lane;
-    uint16_t *out = cost + (row * W + x0) * (long)(NW * 32) + lane;
-    if (y < 2 || y >= H - 2) {
-#pragma unroll
-        for (int p = 0; p < PX; p++)
-#pragma unroll
-            for (int k = 0; k < NW; k++) out[(p * NW + k) * 32] = 0x0C0Cu;
-        return;
-    }
-    const uint32_t *lrow = cl + row * W, *rrow = cr + row * W;
-    // window: rr[t] = R[x0 - d0 - (2NW-1) + t], t in [0, PX + 2NW - 1)
-    uint32_t rr[PX + 2 * NW - 1];
-    const int base = x0 - d0 - (2 * NW - 1);
-#pragma unroll
-    for (int t = 0; t < PX + 2 * NW - 1; t++) rr[t] = (base + t >= 0) ? rrow[base + t] : 0u;
-#pragma unroll
-    for (int p = 0; p < PX; p++) {
-        const int x = x0 + p;
-        const uint32_t l = lrow[x];
-#pragma unroll
-        for (int k = 0; k < NW; k++) {
-            // d = d0 + 2k (+1): R[x - d] = rr[p + 2NW-1 - 2k (-1)]
-            const int dlo = d0 + 2 * k;
-            uint32_t vlo = dlo > x ? 12u : (uint32_t)__popc(l ^ rr[p + 2 * NW - 1 - 2 * k]);
-            uint32_t vhi = dlo + 1 > x ? 12u : (uint32_t)__popc(l ^ rr[p + 2 * NW - 2 - 2 * k]);
-            if (dlo >= D) { vlo = 0; vhi = 0; }
-            out[(p * NW + k) * 32] = (uint16_t)(vlo | (vhi << 8));
-        }
-    }
-}
+static size_t h_stage_bytes(int K2) { return (size_t)K2 * (HCROW + HSROW); }
 
-int launch_cost_plane(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st)
-{
-    constexpr int PX = 8;
-    const long groups = (long)n * H * (W / PX);
-    const int blocks = cdiv(groups * 32, 256);
-    uint16_t *c16 = reinterpret_cast<uint16_t *>(cost);
-    switch ((D + 63) / 64) {
-        case 1: cost_plane_kernel<1, PX><<<blocks, 256, 0, st>>>(cl, cr, c16, W, H, D, groups); break;
-        case 2: cost_plane_kernel<2, PX><<<blocks, 256, 0, st>>>(cl, cr, c16, W, H, D, groups); break;
-        case 3: cost_plane_kernel<3, PX><<<blocks, 256, 0, st>>>(cl, cr, c16, W, H, D, groups); break;
-        default: cost_plane_kernel<4, PX><<<blocks, 256, 0, st>>>(cl, cr, c16, W, H, D, groups); break;
-    }
-    VPP_LAUNCH_CHECK("cost_plane_kernel");
-    return VPPB200_OK;
-}
+__device__ __forceinline__ uint32_t &u4c(uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-// _guided_dsi (models/rsgm/rsgm.py:115-127) on the plane-layout u8 volume; arithmetic as guided_u8_kernel (rsgm_ops.cu)
-__global__ void guided_plane_kernel(uint8_t *__restrict__ cost, const float *__restrict__ hints, const float *__restrict__ valid,
-                                    RsgmDims d, int NW, long total)
-{
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int dd = (int)(t % d.D);
-    const long px = t / d.D;
-    const int x = (int)(px % d.Wp) - d.pl, y = (int)((px / d.Wp) % d.Hp) - d.pt;
-    const long f = px / ((long)d.Wp * d.Hp);
-    if (x < 0 || x >= d.W || y < 0 || y >= d.H) return;
-    const long s = (f * d.H + y) * d.W + x;
-    if (!(valid[s] > 0)) return;
-    const double tt = __dsub_rn((double)hints[s], (double)dd);
-    const float w = (float)__dmul_rn(10.0, __dsub_rn(1.0, exp(__ddiv_rn(-__dmul_rn(tt, tt), 2.0))));
-    const int lane = dd / (2 * NW), k = (dd % (2 * NW)) >> 1;
-    uint8_t *p = cost + px * (long)(NW * 64) + (k * 32 + lane) * 2 + (dd & 1);
-    *p = (uint8_t)(uint16_t)__dmul_rn((double)*p, (double)w);
-}
-int launch_guided_plane(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st)
-{
-    long total = (long)n * d.Hp * d.Wp * d.D;
-    guided_plane_kernel<<<cdiv(total, 256), 256, 0, st>>>(cost, hints, valid, d, (d.D + 63) / 64, total);
-    VPP_LAUNCH_CHECK("guided_plane_kernel");
-    return VPPB200_OK;
-}
-
-// plane-layout S -> the reference's xyd order (test tap only)
-__global__ void unplane_s_kernel(const uint32_t *__restrict__ Sp, uint16_t *__restrict__ S, int D, int NW, long total)
-{
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over pixels * D/2
-    if (t >= total) return;
-    const int h = D / 2;
-    const int dp = (int)(t % h) * 2;
-    const long px = t / h;
-    const int lane = dp / (2 * NW), k = (dp % (2 * NW)) >> 1;
-    reinterpret_cast<uint32_t *>(S)[t] = Sp[px * (long)(NW * 32) + k * 32 + lane];
-}
-int launch_unplane_s(const uint32_t *Sp, uint16_t *S, int W, int H, int D, int n, cudaStream_t st)
-{
-    long total = (long)n * W * H * (D / 2);
-    unplane_s_kernel<<<cdiv(total, 256), 256, 0, st>>>(Sp, S, D, (D + 63) / 64, total);
-    VPP_LAUNCH_CHECK("unplane_s_kernel");
-    return VPPB200_OK;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// per-warp operand ring: the next pixels' costs (and S words) are brought into shared memory by TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx) several steps ahead of the warp that consumes them, so that no sweep step
-// waits on HBM latency.  One lane produces, the whole warp consumes; a slot is refilled right after it was read.
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_init_fence()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// h-sweep: path r0 of one pass, one warp per image row (RSGM/StereoSGM_SSE.hpp:100-113,:219-236 for the recursion;
-// the line starts with L = C at the pass's first column and every pixel is summed into S).
-// Operands arrive through the ring in chunks of HCH pixels; P2 of 32 consecutive pixels is computed lane-parallel one
-// block ahead and broadcast per step.
-// ------------------------------------------------------------------------------------------------------------
-static constexpr int HCH = 4;      // pixels per ring slot
-static constexpr int HST = 2;      // ring slots per warp
-static constexpr int HWARPS = 4;   // warps per CTA
-
-template <int NW, bool STORE>
-__host__ __device__ constexpr int h_slot_bytes() { return HCH * NW * 32 * (STORE ? 2 : 6); }
-
-template <int NW, bool PAD, bool STORE>
+template <int NW, bool STORE, int DIR>
 __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__restrict__ img, const uint16_t *__restrict__ cost,
-                                                            uint32_t *__restrict__ S, int W, int D, int dirn, long total_rows)
+                                                            uint32_t *__restrict__ S, TL t, long total_rows)
 {
     extern __shared__ __align__(16) uint8_t hsm[];
-    constexpr int PW = NW * 32;
-    constexpr int SLOTB = h_slot_bytes<NW, STORE>();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * HWARPS + warp;
     if (row >= total_rows) return;
-    uint8_t *ring = hsm + warp * (HST * SLOTB);
-    const uint32_t ring_a = smem_u32(ring);
-    const uint32_t bars = smem_u32(hsm + HWARPS * HST * SLOTB) + warp * (HST * 8);
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < HST; q++) mbar_init(bars + q * 8, 1);
-        mbar_init_fence();
-    }
-    __syncwarp();
+    const int K2 = t.K2, W = t.W;
+    const int stage_b = K2 * (HCROW + HSROW);
+    uint8_t *base = hsm + (size_t)warp * 2 * stage_b;
     const uint8_t *irow = img + row * W;
-    const uint16_t *crow = cost + row * (long)W * PW;
-    uint32_t *srow = S + row * (long)W * PW;
+    const uint16_t *crow = cost + row * (long)t.G * K2 * 32;     // tiles of this row (rows run over all frames)
+    uint32_t *srow = S + row * (long)t.G * K2 * 32;
     bool wv[NW];
 #pragma unroll
-    for (int k = 0; k < NW; k++) wv[k] = !PAD || (2 * NW * lane + 2 * k < D);
-    const int nchunks = W / HCH;
-    const int xs = dirn > 0 ? 0 : W - 1;
-    // chunk c covers pixels [xlo, xlo + HCH): forwards xlo = c*HCH, backwards xlo = W - (c+1)*HCH
-    auto produce = [&](int c) {
-        if (lane == 0 && c < nchunks) {
-            const int xlo = dirn > 0 ? c * HCH : W - (c + 1) * HCH;
-            const uint32_t slot = (uint32_t)c % HST;
-            const uint32_t dst = ring_a + slot * SLOTB, bar = bars + slot * 8;
-            mbar_expect_tx(bar, SLOTB);
-            tma_load_1d(dst, crow + (long)xlo * PW, HCH * PW * 2, bar);
-            if (!STORE) tma_load_1d(dst + HCH * PW * 2, srow + (long)xlo * PW, HCH * PW * 4, bar);
+    for (int j = 0; j < NW; j++) wv[j] = NW * lane + j < K2;
+    const int nchunks = W / 8;                      // W % 16 == 0
+    const int xs = DIR > 0 ? 0 : W - 1;
+
+    // gather chunk q (sweep order) into stage q & 1: 16-byte pieces, one per cost row, two per S row
+    auto issue = [&](int q) {
+        if (q < nchunks) {
+            const int xc = DIR > 0 ? q : nchunks - 1 - q;
+            const int toff = ((xc >> 2) * K2) * 32 + (xc & 3) * 8;       // tile start + first column of the chunk
+            uint8_t *sb = base + (q & 1) * stage_b;
+            {
+                const uint16_t *src = crow + toff + lane * 32;
+                const uint32_t dst = smem_u32(sb) + lane * HCROW;
+                for (int r0 = 0; r0 < K2; r0 += 32)
+                    if (r0 + lane < K2) cp_async16(dst + r0 * HCROW, src + r0 * 32);
+            }
+            if (!STORE) {
+                const uint32_t *src = srow + toff + (lane >> 1) * 32 + (lane & 1) * 4;
+                const uint32_t dst = smem_u32(sb + K2 * HCROW) + (lane >> 1) * HSROW + (lane & 1) * 16;
+                for (int r0 = 0; r0 < K2; r0 += 16)
+                    if (r0 + (lane >> 1) < K2) cp_async16(dst + r0 * HSROW, src + r0 * 32);
+            }
         }
+        cp_async_commit();
     };
-#pragma unroll
-    for (int q = 0; q < HST; q++) produce(q);
+    issue(0);
+    issue(1);
 
     auto p2_block = [&](int t0) -> uint32_t {
         // (P2 - P1) * 0x10001 for step t0 + lane: |I(x) - I(x - dirn)| inside the row (step 0 has no predecessor)
-        const int t = t0 + lane;
+        const int tt = t0 + lane;
         int p2 = SW_P2MIN;
-        if (t > 0 && t < W) {
-            const int xx = xs + dirn * t;
-            p2 = sw_adapt_p2(irow[xx], irow[xx - dirn]);
+        if (tt > 0 && tt < W) {
+            const int xx = xs + DIR * tt;
+            p2 = sw_adapt_p2(irow[xx], irow[xx - DIR]);
         }
         return (uint32_t)(p2 - SW_P1) * 0x10001u;
     };
     uint32_t p2v = p2_block(0), p2n = p2_block(32);
     uint32_t w[NW];
 #pragma unroll
-    for (int k = 0; k < NW; k++) w[k] = 0;
-    int t = 0;
-    for (int c = 0; c < nchunks; c++) {
-        const uint32_t slot = (uint32_t)c % HST;
-        mbar_wait(bars + slot * 8, ((uint32_t)c / HST) & 1u);
-        const uint16_t *rc = reinterpret_cast<const uint16_t *>(ring + slot * SLOTB) + lane;
-        const uint32_t *rs = reinterpret_cast<const uint32_t *>(ring + slot * SLOTB + HCH * PW * 2) + lane;
-        const int xlo = dirn > 0 ? c * HCH : W - (c + 1) * HCH;
+    for (int j = 0; j < NW; j++) w[j] = 0;
+    int step = 0;
+    for (int q = 0; q < nchunks; q++) {
+        cp_async_wait<1>();
+        __syncwarp();
+        uint8_t *sb = base + (q & 1) * stage_b;
+        uint8_t *ssb = sb + K2 * HCROW;
+        // this lane's rows of the chunk: 8 pixels x NW disparity pairs, costs (uint16) and S words
+        uint4 cv[NW], s0[NW], s1[NW];
 #pragma unroll
-        for (int pp = 0; pp < HCH; pp++, t++) {
-            const int p = dirn > 0 ? pp : HCH - 1 - pp;
-            if ((t & 31) == 0 && t > 0) { p2v = p2n; p2n = p2_block(t + 32); }
-            uint32_t cc[NW], sv[NW];
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                cc[k] = __byte_perm((uint32_t)rc[p * PW + k * 32], 0, 0x4140);      // two uint8 costs -> u16x2
-                if (!STORE) sv[k] = rs[p * PW + k * 32];
+        for (int j = 0; j < NW; j++) {
+            cv[j] = make_uint4(0, 0, 0, 0); s0[j] = cv[j]; s1[j] = cv[j];
+            if (wv[j]) {
+                cv[j] = *reinterpret_cast<const uint4 *>(sb + (NW * lane + j) * HCROW);
+                if (!STORE) {
+                    s0[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW);
+                    s1[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW + 16);
+                }
             }
-            const uint32_t p2m = __shfl_sync(0xFFFFFFFFu, p2v, t & 31);
-            uint32_t nw[NW];
-            if (t == 0) {
+        }
 #pragma unroll
-                for (int k = 0; k < NW; k++) nw[k] = cc[k];
+        for (int pp = 0; pp < 8; pp++, step++) {
+            const int p = DIR > 0 ? pp : 7 - pp;
+            if ((step & 31) == 0 && step > 0) { p2v = p2n; p2n = p2_block(step + 32); }
+            uint32_t cc[NW];
+#pragma unroll
+            for (int j = 0; j < NW; j++)
+                cc[j] = __byte_perm(u4c(cv[j], p >> 1), 0, (p & 1) ? 0x4342 : 0x4140);       // two uint8 costs -> u16x2
+            const uint32_t p2m = __shfl_sync(0xFFFFFFFFu, p2v, step & 31);
+            uint32_t nw[NW];
+            if (step == 0) {
+#pragma unroll
+                for (int j = 0; j < NW; j++) nw[j] = cc[j];
             } else {
                 sw_step<NW>(w, cc, p2m, lane, nw);
             }
-            if (PAD) {
 #pragma unroll
-                for (int k = 0; k < NW; k++) if (!wv[k]) nw[k] = SW_BIG2;
-            }
+            for (int j = 0; j < NW; j++) if (!wv[j]) nw[j] = SW_BIG2;
             const uint32_t m2 = sw_min<NW>(nw) * 0x10001u;
-            uint32_t *so = srow + (long)(xlo + p) * PW + lane;
 #pragma unroll
-            for (int k = 0; k < NW; k++) {
-                w[k] = nw[k] - m2;
-                if (wv[k]) so[k * 32] = STORE ? nw[k] : sv[k] + nw[k];
+            for (int j = 0; j < NW; j++) {
+                w[j] = nw[j] - m2;
+                uint32_t &acc = p < 4 ? u4c(s0[j], p) : u4c(s1[j], p - 4);
+                acc = STORE ? nw[j] : acc + nw[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            if (wv[j]) {
+                *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW) = s0[j];
+                *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW + 16) = s1[j];
             }
         }
         __syncwarp();
-        produce(c + HST);
+        {
+            // write the chunk's S rows back: two 16-byte pieces = one 32-byte sector per row
+            const int xc = DIR > 0 ? q : nchunks - 1 - q;
+            const int toff = ((xc >> 2) * K2) * 32 + (xc & 3) * 8;
+            uint32_t *dst = srow + toff + (lane >> 1) * 32 + (lane & 1) * 4;
+            const uint8_t *src = ssb + (lane >> 1) * HSROW + (lane & 1) * 16;
+            for (int r0 = 0; r0 < K2; r0 += 16)
+                if (r0 + (lane >> 1) < K2)
+                    *reinterpret_cast<uint4 *>(dst + r0 * 32) = *reinterpret_cast<const uint4 *>(src + r0 * HSROW);
+        }
+        __syncwarp();
+        issue(q + 2);
     }
+    cp_async_wait<0>();
 }
 
-template <int NW, bool PAD, bool STORE>
-static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, int W, int H, int D, int dirn, int n, cudaStream_t st)
+template <int NW, bool STORE, int DIR>
+static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int n, cudaStream_t st)
 {
-    const long rows = (long)n * H;
+    const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
-    const size_t smem = (size_t)HWARPS * HST * h_slot_bytes<NW, STORE>() + HWARPS * HST * 8;
-    auto kern = sgm_h_kernel<NW, PAD, STORE>;
+    const size_t smem = (size_t)HWARPS * 2 * h_stage_bytes(t.K2);
+    auto kern = sgm_h_kernel<NW, STORE, DIR>;
     if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, W, D, dirn, rows);
+    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows);
     VPP_LAUNCH_CHECK("sgm_h_kernel");
     return VPPB200_OK;
 }
 
-template <int NW>
-static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, int W, int H, int D, int dirn, bool store, int n,
-                 cudaStream_t st)
+// forward sweep stores S = L, backward sweep adds
+static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int dirn, int n, cudaStream_t st)
 {
-    const bool pad = (D != 64 * NW);
-    if (store) return pad ? run_h_t<NW, true, true>(img, cost, S, W, H, D, dirn, n, st)
-                          : run_h_t<NW, false, true>(img, cost, S, W, H, D, dirn, n, st);
-    return pad ? run_h_t<NW, true, false>(img, cost, S, W, H, D, dirn, n, st)
-               : run_h_t<NW, false, false>(img, cost, S, W, H, D, dirn, n, st);
+    switch ((t.K2 + 31) / 32) {
+        case 1: return dirn > 0 ? run_h_t<1, true, 1>(img, cost, S, t, n, st) : run_h_t<1, false, -1>(img, cost, S, t, n, st);
+        case 2: return dirn > 0 ? run_h_t<2, true, 1>(img, cost, S, t, n, st) : run_h_t<2, false, -1>(img, cost, S, t, n, st);
+        case 3: return dirn > 0 ? run_h_t<3, true, 1>(img, cost, S, t, n, st) : run_h_t<3, false, -1>(img, cost, S, t, n, st);
+        default: return dirn > 0 ? run_h_t<4, true, 1>(img, cost, S, t, n, st) : run_h_t<4, false, -1>(img, cost, S, t, n, st);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// v-sweep: paths r1, r2, r3 of one pass, cluster per frame, state in (distributed) shared memory
+// v-sweep: paths r1, r2, r3 of one pass, cluster per frame, lane = column, state in (distributed) shared memory
 // ------------------------------------------------------------------------------------------------------------
 struct VArgs {
-    int W, H, D, n;
+    TL t;
+    int n;
     int pass;          // 0: top-down (di = dj = +1), 1: bottom-up (di = dj = -1)
     int csize;         // CTAs per cluster
-    int SC;            // strip width (columns per CTA), ceil(W / csize)
+    int GC;            // 32-column groups per CTA, ceil(G / csize)
 };
 
-static constexpr int SWV_WARPS = 16;
-static constexpr int VRING = 4;    // operand ring slots (pixels in flight) per warp
+static constexpr int VPARTS = 3;   // warps per column group (each owns a third of the disparity pairs)
+static constexpr int VU = 8;       // disparity pairs per operand block (software pipelined)
 
-template <int NW, bool PAD>
-__global__ void __launch_bounds__(SWV_WARPS * 32, 1) sgm_v_kernel(const uint8_t *__restrict__ img_all,
-                                                                  const uint16_t *__restrict__ cost_all,
-                                                                  uint32_t *__restrict__ S_all, VArgs a)
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("{\n\t.reg .u32 t;\n\tadd.u32 t, %1, %2;\n\tadd.u32 %0, t, %3;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// per-path registers of the disparity walk
+struct VPath {
+    uint32_t cur;      // L[2k], L[2k+1] of the predecessor (un-normalised)
+    uint32_t lo;       // L[2k-1], L[2k]
+    uint32_t q;        // (minL + P2 - P1) x2
+    uint32_t ng;       // -(minL x2)
+    uint32_t mr;       // running min of the new values
+};
+
+// One block of up to VU disparity pairs for the three paths.  s* = predecessor state rows of the block (stride NS),
+// w* = this row's state rows (same slots except for entering lines), Sg = the block's S words (stride 32).
+// GUARD: only the first `cnt` pairs exist; `last`: the block ends this warp's third, whose right neighbour pair was
+// read before the column group's barrier (wr*).
+template <int NS, bool GUARD>
+__device__ __forceinline__ void v_block(const uint32_t (&cb)[VU], const uint32_t (&sb)[VU], const uint32_t *s1,
+                                        const uint32_t *s2, const uint32_t *s3, uint32_t *w1, uint32_t *w2, uint32_t *w3,
+                                        uint32_t wr1, uint32_t wr2, uint32_t wr3, VPath &p1, VPath &p2, VPath &p3,
+                                        uint32_t *Sg, int cnt, bool last)
+{
+    uint32_t nx1[VU], nx2[VU], nx3[VU];
+#pragma unroll
+    for (int u = 0; u < VU; u++) {
+        if (u + 1 < VU) {
+            if (!GUARD || u + 1 < cnt) { nx1[u] = s1[(u + 1) * NS]; nx2[u] = s2[(u + 1) * NS]; nx3[u] = s3[(u + 1) * NS]; }
+            else { nx1[u] = wr1; nx2[u] = wr2; nx3[u] = wr3; }
+        } else {
+            if (last) { nx1[u] = wr1; nx2[u] = wr2; nx3[u] = wr3; }
+            else { nx1[u] = s1[VU * NS]; nx2[u] = s2[VU * NS]; nx3[u] = s3[VU * NS]; }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < VU; u++) {
+        if (!GUARD || u < cnt) {
+            const uint32_t c = __byte_perm(cb[u], 0, 0x4140);                        // two uint8 costs -> u16x2
+            const uint32_t hi1 = __byte_perm(p1.cur, nx1[u], 0x5432), hi2 = __byte_perm(p2.cur, nx2[u], 0x5432),
+                           hi3 = __byte_perm(p3.cur, nx3[u], 0x5432);                // L[2k+1], L[2k+2]
+            uint32_t t1 = __vimin3_u16x2(p1.lo, hi1, p1.q), t2 = __vimin3_u16x2(p2.lo, hi2, p2.q),
+                     t3 = __vimin3_u16x2(p3.lo, hi3, p3.q);                          // min(L[d-1], L[d+1], minL + P2 - P1)
+            t1 = __viaddmin_u16x2(t1, SW_P1X2, p1.cur);                              // min(. + P1, L[d])
+            t2 = __viaddmin_u16x2(t2, SW_P1X2, p2.cur);
+            t3 = __viaddmin_u16x2(t3, SW_P1X2, p3.cur);
+            t1 = add3(t1, c, p1.ng); t2 = add3(t2, c, p2.ng); t3 = add3(t3, c, p3.ng);   // C + min(...) - minL
+            w1[u * NS] = t1; w2[u * NS] = t2; w3[u * NS] = t3;
+            p1.mr = __vminu2(p1.mr, t1); p2.mr = __vminu2(p2.mr, t2); p3.mr = __vminu2(p3.mr, t3);
+            Sg[u * 32] = add3(t1, t2, t3) + sb[u];
+            p1.lo = hi1; p2.lo = hi2; p3.lo = hi3;
+            p1.cur = nx1[u]; p2.cur = nx2[u]; p3.cur = nx3[u];
+        }
+    }
+}
+
+// NS = physical slots per state row: up to NS-3 ring slots, then the border slot and two halo slots (row parity).
+// FULL: every warp's third of the disparity pairs is a whole number of VU-blocks (no guards in the inner loop).
+template <int NS, bool FULL>
+__global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel(const uint8_t *__restrict__ img_all,
+                                                                                const uint16_t *__restrict__ cost_all,
+                                                                                uint32_t *__restrict__ S_all, VArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / a.csize, nclusters = gridDim.x / a.csize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int PW = NW * 32;                    // words per pixel-path state
-    constexpr int SLOTB = 6 * PW;                  // ring slot: PW u16 costs + PW u32 S words
-    const int W = a.W, H = a.H;
-    const int x0 = rank * a.SC;
-    const int nc = min(a.SC, W - x0);              // columns of this strip (>= 1, checked by the launcher)
+    const int W = a.t.W, H = a.t.H, K2 = a.t.K2, G = a.t.G;
+    constexpr int BIGS = NS - 3, HALO = NS - 2;
+    const int gl = warp / VPARTS, part = warp % VPARTS;
+    const int g_first = rank * a.GC;
+    const int ng = min(a.GC, G - g_first);          // column groups of this strip (>= 1, checked by the launcher)
+    const int n = ng * 32;                          // ring modulus
+    const int x0 = g_first * 32;
     const int dj = a.pass == 0 ? 1 : -1, di = dj;
     const int i1 = a.pass == 0 ? 0 : H - 1;
+    const int KP = (K2 + VPARTS - 1) / VPARTS;
+    const int k0 = part * KP, k1 = min(K2, k0 + KP);
+    const bool active = gl < ng && k0 < k1;
+    const int nact = (K2 + KP - 1) / KP;            // warps of a column group that own disparity pairs
 
-    uint32_t *st = smem;                            // [3][SC][PW]
-    uint32_t *halo1 = st + 3 * a.SC * PW;           // [2][PW]  r1 state of the line entering this strip
-    uint32_t *halo3 = halo1 + 2 * PW;               // [2][PW]  r3 state of the line entering this strip
-    uint4 *p2tab = reinterpret_cast<uint4 *>(halo3 + 2 * PW);   // [2][SC]  (P2 - P1) * 0x10001 for r1, r2, r3
-    uint8_t *ring = reinterpret_cast<uint8_t *>(p2tab + 2 * a.SC) + warp * (VRING * SLOTB);
-    const uint32_t ring_a = smem_u32(ring);
-    const uint32_t bars = smem_u32(reinterpret_cast<uint8_t *>(p2tab + 2 * a.SC) + SWV_WARPS * VRING * SLOTB) + warp * (VRING * 8);
+    uint32_t *st = smem;                            // [3][K2][NS]   un-normalised L of the previous row, per line
+    uint32_t *mn = st + 3 * K2 * NS;                // [3][VPARTS][NS] min_d of each third of that row
+    for (int idx = tid; idx < 3 * K2 * NS; idx += blockDim.x) st[idx] = SW_BIG2;
+    for (int idx = tid; idx < 3 * VPARTS * NS; idx += blockDim.x) mn[idx] = (idx % NS == BIGS) ? 0u : 0x3FFFu;
     // r1 lines move by +dj per row, r3 lines by -dj: where a leaving line's state goes
-    uint32_t *push1 = (rank + dj >= 0 && rank + dj < a.csize) ? cluster.map_shared_rank(halo1, rank + dj) : nullptr;
-    uint32_t *push3 = (rank - dj >= 0 && rank - dj < a.csize) ? cluster.map_shared_rank(halo3, rank - dj) : nullptr;
+    const bool has1 = rank + dj >= 0 && rank + dj < a.csize, has3 = rank - dj >= 0 && rank - dj < a.csize;
+    uint32_t *push1_st = has1 ? cluster.map_shared_rank(st, rank + dj) : nullptr;
+    uint32_t *push3_st = has3 ? cluster.map_shared_rank(st, rank - dj) : nullptr;
+    const int gl_leave1 = dj > 0 ? ng - 1 : 0, lane_leave1 = dj > 0 ? 31 : 0;
+    const int gl_leave3 = dj > 0 ? 0 : ng - 1, lane_leave3 = dj > 0 ? 0 : 31;
+    cluster.sync();
 
-    bool wv[NW];
-#pragma unroll
-    for (int k = 0; k < NW; k++) wv[k] = !PAD || (2 * NW * lane + 2 * k < a.D);
-
+    const int lc = gl * 32 + lane;                  // local column
+    const int x = x0 + lc;
+    const int xr = min(x, W - 1);                   // padding columns read the last image column (results unused)
     const long npx = (long)W * H;
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < VRING; q++) mbar_init(bars + q * 8, 1);
-        mbar_init_fence();
-    }
-    __syncwarp();
-    // this warp's pixel stream: frames f = cid, cid + nclusters, ...; rows in sweep order; columns warp, warp + 16, ...
-    int pf = cid, ps = 0, pjl = warp;               // producer position
-    unsigned pq = 0, cq = 0;                        // pixels produced / consumed
-    auto produce = [&]() {
-        if (pf < a.n) {
-            if (lane == 0) {
-                const long px = (long)pf * npx + (long)(i1 + ps * di) * W + x0 + pjl;
-                const uint32_t slot = pq % VRING;
-                const uint32_t dst = ring_a + slot * SLOTB, bar = bars + slot * 8;
-                mbar_expect_tx(bar, SLOTB);
-                tma_load_1d(dst, cost_all + px * PW, 2 * PW, bar);
-                tma_load_1d(dst + 2 * PW, S_all + px * PW, 4 * PW, bar);
-            }
-            pq++;
-            pjl += SWV_WARPS;
-            if (pjl >= nc) {
-                pjl = warp;
-                if (++ps == H) { ps = 0; pf += nclusters; }
-            }
-        }
-    };
-    if (warp < nc) {
-#pragma unroll
-        for (int q = 0; q < VRING; q++) produce();
-    }
+    const int g = g_first + gl;
 
-    unsigned gstep = 0;                             // rows processed by this cluster so far (halo / P2 double-buffer parity)
+    unsigned gstep = 0;                             // rows processed by this cluster so far (halo slot parity)
+    uint32_t cb[VU], sb[VU];                        // first operand block of the next row (prefetched across the barrier)
+#pragma unroll
+    for (int u = 0; u < VU; u++) { cb[u] = 0; sb[u] = 0; }
     for (int f = cid; f < a.n; f += nclusters) {
         const uint8_t *img = img_all + f * npx;
-        uint32_t *S = S_all + f * npx * PW + lane;
-        int sh = 0;                                 // s mod nc
+        const uint16_t *cost_f = cost_all + f * a.t.frame + lane;
+        uint32_t *S_f = S_all + f * a.t.frame + lane;
+        int sh = 0;                                 // s mod n
+        // intensities for the P2 of row s (prefetched one row ahead): centre, r1, r2, r3 predecessors
+        int ipc = 0, ip1 = 0, ip2 = 0, ip3 = 0;
+        auto load_block = [&](const uint16_t *cp, const uint32_t *sp, int cnt, uint32_t (&c)[VU], uint32_t (&sv)[VU], bool with_s) {
+#pragma unroll
+            for (int u = 0; u < VU; u++) {
+                if (FULL || u < cnt) {
+                    c[u] = cp[u * 32];
+                    sv[u] = with_s ? sp[u * 32] : 0u;
+                }
+            }
+        };
+        if (active && f == cid) load_block(cost_f + (((long)i1 * G + g) * K2 + k0) * 32, nullptr, k1 - k0, cb, sb, false);
         for (int s = 0; s < H; s++, gstep++) {
             const int i = i1 + s * di;
-            if (gstep > 0) cluster.barrier_wait();  // row s-1 (state, halos, P2 table) complete everywhere
+            if (gstep > 0) cluster.barrier_wait();  // row s-1 (state, mins, halos) complete everywhere
             const unsigned par = gstep & 1u;
-            const uint4 *p2row = p2tab + par * a.SC;
-            const uint32_t *h1in = halo1 + (par ^ 1u) * PW, *h3in = halo3 + (par ^ 1u) * PW;
-
-            for (int jl = warp; jl < nc; jl += SWV_WARPS) {
-                const uint32_t slot = cq % VRING;
-                mbar_wait(bars + slot * 8, (cq / VRING) & 1u);
-                cq++;
-                const uint16_t *rc = reinterpret_cast<const uint16_t *>(ring + slot * SLOTB) + lane;
-                const uint32_t *rs = reinterpret_cast<const uint32_t *>(ring + slot * SLOTB + 2 * PW) + lane;
-                uint32_t c[NW], sv[NW];
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    c[k] = __byte_perm((uint32_t)rc[k * 32], 0, 0x4140);
-                    sv[k] = rs[k * 32];
+            if (active) {
+                const long tb0 = (((long)i * G + g) * K2 + k0) * 32;
+                const uint16_t *cp = cost_f + tb0;
+                uint32_t *sp = S_f + tb0;
+                if (s + 1 < H) {
+                    // pull the next row's operands of this warp into L2 while this row is being processed
+                    const long tbn = (((long)(i + di) * G + g) * K2 + k0) * 32 - lane;
+                    if (k0 + lane < k1) prefetch_l2(S_f + tbn + lane * 32);
+                    if (k0 + 2 * lane < k1) prefetch_l2(cost_f + tbn + lane * 64);
                 }
-                __syncwarp();
-                produce();                          // refill the slot that was just read
-                const int j = x0 + jl;
-                // ring slots: a line moving +1 column per row sits in slot (jl - s) mod nc, one moving -1 in (jl + s) mod nc
-                int slotA = jl - sh; if (slotA < 0) slotA += nc;
-                int slotB = jl + sh; if (slotB >= nc) slotB -= nc;
-                const int slot1 = dj > 0 ? slotA : slotB;
-                const int slot3 = dj > 0 ? slotB : slotA;
-                uint32_t *s1 = st + (0 * a.SC + slot1) * PW + lane;
-                uint32_t *s2 = st + (1 * a.SC + jl) * PW + lane;
-                uint32_t *s3 = st + (2 * a.SC + slot3) * PW + lane;
-                uint32_t n1[NW], n2[NW], n3[NW];
+                // ring slots: a line moving +1 column per row sits in slot (lc - s) mod n, one moving -1 in (lc + s) mod n
+                int slotA = lc - sh; if (slotA < 0) slotA += n;
+                int slotB = lc + sh; if (slotB >= n) slotB -= n;
+                const int d1 = dj > 0 ? slotA : slotB, d2 = lc, d3 = dj > 0 ? slotB : slotA;
+                uint32_t *w1 = st + (0 * K2 + k0) * NS + d1, *w2 = st + (1 * K2 + k0) * NS + d2, *w3 = st + (2 * K2 + k0) * NS + d3;
+                VPath p1, p2, p3;
+                p1.mr = p2.mr = p3.mr = SW_BIG2;
                 if (s == 0) {
                     // first row of the pass: L = C on all three paths, nothing is summed (StereoSGM_SSE.hpp:116-218)
+                    for (int kb = k0; kb < k1; kb += VU) {
+                        uint32_t cn[VU], sn[VU];
 #pragma unroll
-                    for (int k = 0; k < NW; k++) n1[k] = n2[k] = n3[k] = c[k];
+                        for (int u = 0; u < VU; u++) { cn[u] = 0; sn[u] = 0; }
+                        if (kb + VU < k1) load_block(cp + VU * 32, nullptr, k1 - kb - VU, cn, sn, false);
+#pragma unroll
+                        for (int u = 0; u < VU; u++) {
+                            if (FULL || kb + u < k1) {
+                                const uint32_t c = __byte_perm(cb[u], 0, 0x4140);
+                                w1[u * NS] = c; w2[u * NS] = c; w3[u * NS] = c;
+                                p1.mr = __vminu2(p1.mr, c);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < VU; u++) cb[u] = cn[u];
+                        cp += VU * 32; w1 += VU * NS; w2 += VU * NS; w3 += VU * NS;
+                    }
+                    p2.mr = p1.mr; p3.mr = p1.mr;
                 } else {
-                    const uint4 pm = p2row[jl];
-                    uint32_t w[NW];
-                    // r2: predecessor (i - di, j)
+                    // predecessors: r1 (i - di, x - dj), r2 (i - di, x), r3 (i - di, x + dj)
+                    const int xp1 = x - dj, lp1 = lc - dj, xp3 = x + dj, lp3 = lc + dj;
+                    const int halo_in = HALO + (int)(par ^ 1u);
+                    // a line entering through the image border reads the border slot: L = 65535 (here: BIG), min = 0
+                    // => min(65535, 65535 + P1, 0 + P2) - 0 = P2   (StereoSGM_SSE.hpp:48-58,:69-72)
+                    const int r1s = (xp1 < 0 || xp1 >= W) ? BIGS : ((lp1 < 0 || lp1 >= n) ? halo_in : d1);
+                    const int r3s = (xp3 < 0 || xp3 >= W) ? BIGS : ((lp3 < 0 || lp3 >= n) ? halo_in : d3);
+                    const uint32_t *s1 = st + (0 * K2 + k0) * NS + r1s, *s2 = w2, *s3 = st + (2 * K2 + k0) * NS + r3s;
+                    // min_d of the predecessors
+                    uint32_t m1 = mn[(0 * VPARTS + 0) * NS + r1s], m2 = mn[(1 * VPARTS + 0) * NS + d2], m3 = mn[(2 * VPARTS + 0) * NS + r3s];
 #pragma unroll
-                    for (int k = 0; k < NW; k++) w[k] = s2[k * 32];
-                    sw_step<NW>(w, c, pm.y, lane, n2);
-                    // r1: predecessor (i - di, j - dj)
-                    const int jp1 = j - dj, jlp1 = jl - dj;
-                    if (jp1 < 0 || jp1 >= W) {
-                        // enters through the image border: min(65535, 65535 + P1, 0 + P2) - 0 = P2  (:48-58,:69-72)
-#pragma unroll
-                        for (int k = 0; k < NW; k++) n1[k] = c[k] + pm.x + SW_P1X2;
-                    } else {
-                        const uint32_t *src = (jlp1 >= 0 && jlp1 < nc) ? s1 : h1in + lane;
-#pragma unroll
-                        for (int k = 0; k < NW; k++) w[k] = src[k * 32];
-                        sw_step<NW>(w, c, pm.x, lane, n1);
+                    for (int pt = 1; pt < VPARTS; pt++) {
+                        m1 = min(m1, mn[(0 * VPARTS + pt) * NS + r1s]);
+                        m2 = min(m2, mn[(1 * VPARTS + pt) * NS + d2]);
+                        m3 = min(m3, mn[(2 * VPARTS + pt) * NS + r3s]);
                     }
-                    // r3: predecessor (i - di, j + dj)
-                    const int jp3 = j + dj, jlp3 = jl + dj;
-                    if (jp3 < 0 || jp3 >= W) {
-#pragma unroll
-                        for (int k = 0; k < NW; k++) n3[k] = c[k] + pm.z + SW_P1X2;
-                    } else {
-                        const uint32_t *src = (jlp3 >= 0 && jlp3 < nc) ? s3 : h3in + lane;
-#pragma unroll
-                        for (int k = 0; k < NW; k++) w[k] = src[k * 32];
-                        sw_step<NW>(w, c, pm.z, lane, n3);
+                    // P2 from the FLAT image stream (prefetched); q = (min + P2 - P1) x2, ng = -(min x2)
+                    p1.q = (m1 + (uint32_t)(sw_adapt_p2(ipc, ip1) - SW_P1)) * 0x10001u;
+                    p2.q = (m2 + (uint32_t)(sw_adapt_p2(ipc, ip2) - SW_P1)) * 0x10001u;
+                    p3.q = (m3 + (uint32_t)(sw_adapt_p2(ipc, ip3) - SW_P1)) * 0x10001u;
+                    p1.ng = 0u - m1 * 0x10001u; p2.ng = 0u - m2 * 0x10001u; p3.ng = 0u - m3 * 0x10001u;
+                    // identity shuffles keep -(minL x2) in a register: otherwise ptxas re-fuses the multiply into every
+                    // add of the inner loop (IADD + IMAD instead of one IADD3 per path and disparity pair)
+                    p1.ng = __shfl_sync(0xFFFFFFFFu, p1.ng, lane); p2.ng = __shfl_sync(0xFFFFFFFFu, p2.ng, lane);
+                    p3.ng = __shfl_sync(0xFFFFFFFFu, p3.ng, lane);
+                    // register window over the disparity pairs; the neighbours just outside this warp's third are read
+                    // before the other warps of the column group may overwrite them
+                    const uint32_t pv1 = k0 > 0 ? s1[-NS] : SW_BIG2, pv2 = k0 > 0 ? s2[-NS] : SW_BIG2, pv3 = k0 > 0 ? s3[-NS] : SW_BIG2;
+                    const int ke = (k1 - k0) * NS;
+                    const uint32_t wr1 = k1 < K2 ? s1[ke] : SW_BIG2, wr2 = k1 < K2 ? s2[ke] : SW_BIG2, wr3 = k1 < K2 ? s3[ke] : SW_BIG2;
+                    p1.cur = s1[0]; p2.cur = s2[0]; p3.cur = s3[0];
+                    p1.lo = __byte_perm(pv1, p1.cur, 0x5432); p2.lo = __byte_perm(pv2, p2.cur, 0x5432);
+                    p3.lo = __byte_perm(pv3, p3.cur, 0x5432);
+                    if (nact > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + gl), "r"(nact * 32) : "memory");
+                    // two operand blocks ping-pong between cb/sb and cn/sn: one is consumed while the other loads
+                    for (int kb = k0; kb < k1; kb += 2 * VU) {
+                        uint32_t cn[VU], sn[VU];
+                        const bool last1 = kb + VU >= k1;
+                        if (!last1) load_block(cp + VU * 32, sp + VU * 32, k1 - kb - VU, cn, sn, true);
+                        v_block<NS, !FULL>(cb, sb, s1, s2, s3, w1, w2, w3, wr1, wr2, wr3, p1, p2, p3, sp, k1 - kb, last1);
+                        cp += VU * 32; sp += VU * 32;
+                        s1 += VU * NS; s2 += VU * NS; s3 += VU * NS; w1 += VU * NS; w2 += VU * NS; w3 += VU * NS;
+                        if (last1) break;
+                        const bool last2 = kb + 2 * VU >= k1;
+                        if (!last2) load_block(cp + VU * 32, sp + VU * 32, k1 - kb - 2 * VU, cb, sb, true);
+                        v_block<NS, !FULL>(cn, sn, s1, s2, s3, w1, w2, w3, wr1, wr2, wr3, p1, p2, p3, sp, k1 - kb - VU, last2);
+                        cp += VU * 32; sp += VU * 32;
+                        s1 += VU * NS; s2 += VU * NS; s3 += VU * NS; w1 += VU * NS; w2 += VU * NS; w3 += VU * NS;
                     }
-                    const int o = (i * W + j) * PW;
-#pragma unroll
-                    for (int k = 0; k < NW; k++)
-                        if (wv[k]) S[o + k * 32] = sv[k] + n1[k] + n2[k] + n3[k];
                 }
-                if (PAD) {
-#pragma unroll
-                    for (int k = 0; k < NW; k++) if (!wv[k]) { n1[k] = SW_BIG2; n2[k] = SW_BIG2; n3[k] = SW_BIG2; }
+                // minima of this third of the row
+                const uint32_t mr1 = min(p1.mr & 0xFFFFu, p1.mr >> 16), mr2 = min(p2.mr & 0xFFFFu, p2.mr >> 16),
+                               mr3 = min(p3.mr & 0xFFFFu, p3.mr >> 16);
+                mn[(0 * VPARTS + part) * NS + d1] = mr1;
+                mn[(1 * VPARTS + part) * NS + d2] = mr2;
+                mn[(2 * VPARTS + part) * NS + d3] = mr3;
+                // push the lines that leave the strip into the neighbour's halo slot of this row's parity
+                const int halo_out = HALO + (int)par;
+                if (has1 && gl == gl_leave1) {
+                    __syncwarp();
+                    const int sl = __shfl_sync(0xFFFFFFFFu, d1, lane_leave1);
+                    const uint32_t mv = __shfl_sync(0xFFFFFFFFu, mr1, lane_leave1);
+                    for (int k = k0 + lane; k < k1; k += 32) push1_st[(0 * K2 + k) * NS + halo_out] = st[(0 * K2 + k) * NS + sl];
+                    if (lane == 0) push1_st[3 * K2 * NS + (0 * VPARTS + part) * NS + halo_out] = mv;
                 }
-                // normalise, keep as the state of this row; push a line that leaves the strip to the neighbour's halo
-                const uint32_t m1 = sw_min<NW>(n1) * 0x10001u;
-                const uint32_t m2 = (s == 0) ? m1 : sw_min<NW>(n2) * 0x10001u;
-                const uint32_t m3 = (s == 0) ? m1 : sw_min<NW>(n3) * 0x10001u;
-                const bool leave1 = (jl + dj < 0 || jl + dj >= nc) && push1 != nullptr;
-                const bool leave3 = (jl - dj < 0 || jl - dj >= nc) && push3 != nullptr;
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const uint32_t v1 = n1[k] - m1, v2 = n2[k] - m2, v3 = n3[k] - m3;
-                    s1[k * 32] = v1;
-                    s2[k * 32] = v2;
-                    s3[k * 32] = v3;
-                    if (leave1) push1[par * PW + k * 32 + lane] = v1;
-                    if (leave3) push3[par * PW + k * 32 + lane] = v3;
+                if (has3 && gl == gl_leave3) {
+                    __syncwarp();
+                    const int sl = __shfl_sync(0xFFFFFFFFu, d3, lane_leave3);
+                    const uint32_t mv = __shfl_sync(0xFFFFFFFFu, mr3, lane_leave3);
+                    for (int k = k0 + lane; k < k1; k += 32) push3_st[(2 * K2 + k) * NS + halo_out] = st[(2 * K2 + k) * NS + sl];
+                    if (lane == 0) push3_st[3 * K2 * NS + (2 * VPARTS + part) * NS + halo_out] = mv;
                 }
-            }
-            // P2 of the next row for this strip: intensities from the FLAT image stream (wrap across row ends); on the
-            // row right after the pass's first row the "previous line" is that same row (StereoSGM_SSE.hpp:221,:238-243)
-            if (s + 1 < H) {
-                const int in = i + di;
-                const int il = (s == 0) ? in : i;
-                uint4 *p2next = p2tab + (par ^ 1u) * a.SC;
-                for (int t = tid; t < nc; t += SWV_WARPS * 32) {
-                    const int j = x0 + t;
-                    const int ip = img[in * W + j];
-                    long q1 = (long)il * W + j - dj, q2 = (long)il * W + j, q3 = (long)il * W + j + dj;
+                // prefetch for the next row: P2 intensities (on the row right after the pass's first row the "previous
+                // line" is that same row, StereoSGM_SSE.hpp:221,:238-243) and the first operand block
+                if (s + 1 < H) {
+                    const int in = i + di;
+                    const int il = (s == 0) ? in : i;
+                    long q1 = (long)il * W + xr - dj, q3 = (long)il * W + xr + dj;
                     q1 = q1 < 0 ? 0 : (q1 >= npx ? npx - 1 : q1);
                     q3 = q3 < 0 ? 0 : (q3 >= npx ? npx - 1 : q3);
-                    uint4 e;
-                    e.x = (uint32_t)(sw_adapt_p2(ip, img[q1]) - SW_P1) * 0x10001u;
-                    e.y = (uint32_t)(sw_adapt_p2(ip, img[q2]) - SW_P1) * 0x10001u;
-                    e.z = (uint32_t)(sw_adapt_p2(ip, img[q3]) - SW_P1) * 0x10001u;
-                    e.w = 0;
-                    p2next[t] = e;
+                    ipc = img[in * W + xr]; ip1 = img[q1]; ip2 = img[il * W + xr]; ip3 = img[q3];
+                    const long tbn = (((long)in * G + g) * K2 + k0) * 32;
+                    load_block(cost_f + tbn, S_f + tbn, k1 - k0, cb, sb, true);
+                } else if (f + nclusters < a.n) {
+                    // first row of this cluster's next frame
+                    const uint16_t *cost_n = cost_all + (long)(f + nclusters) * a.t.frame + lane;
+                    load_block(cost_n + (((long)i1 * G + g) * K2 + k0) * 32, nullptr, k1 - k0, cb, sb, false);
                 }
             }
-            if (++sh == nc) sh = 0;
+            if (++sh == n) sh = 0;
             cluster.barrier_arrive();
         }
     }
     if (gstep > 0) cluster.barrier_wait();          // nobody leaves while a neighbour may still push into its halo
 }
 
-static size_t v_fixed_bytes(int NW) { return (size_t)4 * NW * 32 * 4 + (size_t)SWV_WARPS * VRING * (6 * NW * 32 + 8); }
-static size_t v_smem_bytes(int NW, int SC) { return (size_t)3 * SC * NW * 32 * 4 + (size_t)2 * SC * 16 + v_fixed_bytes(NW); }
+static size_t v_smem_bytes(int NS, int K2) { return ((size_t)3 * K2 * NS + (size_t)3 * VPARTS * NS) * 4; }
 
-// tuning / test hook: upper bound on the strip width (0 = as wide as shared memory allows)
+// tuning / test hook: upper bound on the strip width in columns (0 = as wide as shared memory allows)
 static int g_max_strip = 0;
 void sweep_set_max_strip(int cols) { g_max_strip = cols < 0 ? 0 : cols; }
 
-struct VPlan { int csize, SC, nclusters; size_t smem; };
+struct VPlan { int csize, GC, NS, nclusters; size_t smem; };
 
-template <int NW, bool PAD>
-static int plan_v(int W, int n, VPlan *plan)
+template <int NS, bool FULL>
+static int v_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, const VPlan &p, cudaStream_t st)
 {
-    auto kern = sgm_v_kernel<NW, PAD>;
-    int dev = 0, smem_optin = 0;
-    VPP_CUDA_TRY(cudaGetDevice(&dev));
-    VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if ((size_t)smem_optin <= v_fixed_bytes(NW)) return 1;
-    int sc_max = (int)(((size_t)smem_optin - v_fixed_bytes(NW)) / ((size_t)3 * NW * 32 * 4 + 32));
-    if (g_max_strip > 0 && g_max_strip < sc_max) sc_max = g_max_strip;
-    if (sc_max < 1) return VPPB200_ERR_ARG;
-    int csize = 1;
-    while (csize * sc_max < W && csize < 16) csize *= 2;
-    if (csize * sc_max < W) return 1;               // does not fit a cluster: caller falls back to the per-path kernels
-    const int SC = (W + csize - 1) / csize;
-    if ((csize - 1) * SC >= W) return 1;            // an empty strip
-    const size_t smem = v_smem_bytes(NW, SC);
-    VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (csize > 8) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(csize * n));
-    cfg.blockDim = dim3(SWV_WARPS * 32);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
+    auto kern = sgm_v_kernel<NS, FULL>;
+    VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    if (p.csize > 8) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3((unsigned)(p.csize * p.nclusters));
+    cfg->blockDim = dim3((unsigned)(p.GC * VPARTS * 32));
+    cfg->dynamicSmemBytes = p.smem;
+    cfg->stream = st;
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int max_clusters = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
-    if (e != cudaSuccess || max_clusters < 1) { cudaGetLastError(); return 1; }
-    plan->csize = csize; plan->SC = SC; plan->smem = smem;
-    plan->nclusters = n < max_clusters ? n : max_clusters;
+    attr[0].val.clusterDim.x = (unsigned)p.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg->attrs = attr; cfg->numAttrs = 1;
     return VPPB200_OK;
 }
 
-template <int NW, bool PAD>
-static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, int W, int H, int D, int pass, int n, const VPlan &p,
-                 cudaStream_t st)
+template <int NS>
+static int v_max_clusters(const VPlan &p, int *out)
+{
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int rc = v_config<NS, true>(&cfg, attr, p, nullptr);
+    if (rc) return rc;
+    cfg.gridDim = dim3((unsigned)(p.csize * 64));
+    cudaError_t e = cudaOccupancyMaxActiveClusters(out, sgm_v_kernel<NS, true>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); *out = 0; }
+    return VPPB200_OK;
+}
+
+// 0 = plan made; 1 = this shape does not fit the cluster sweep; < 0 = error
+static int plan_v(const TL &t, int n, VPlan *plan)
+{
+    int dev = 0, smem_optin = 0;
+    VPP_CUDA_TRY(cudaGetDevice(&dev));
+    VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int gc_max = 0;
+    for (int gc = 6; gc >= 1; gc--)
+        if (v_smem_bytes(gc * 32 + 3, t.K2) <= (size_t)smem_optin) { gc_max = gc; break; }
+    if (g_max_strip > 0) gc_max = std::min(gc_max, std::max(1, g_max_strip / 32));
+    if (gc_max < 1) return 1;
+    int csize = 1;
+    while (csize * gc_max < t.G && csize < 16) csize *= 2;
+    if (csize * gc_max < t.G) return 1;
+    VPlan p;
+    p.csize = csize;
+    p.GC = (t.G + csize - 1) / csize;
+    if ((csize - 1) * p.GC >= t.G) return 1;        // an empty strip
+    p.NS = p.GC * 32 + 3;
+    p.smem = v_smem_bytes(p.NS, t.K2);
+    p.nclusters = 1;
+    int mc = 0, rc;
+    switch (p.GC) {
+        case 1: rc = v_max_clusters<35>(p, &mc); break;
+        case 2: rc = v_max_clusters<67>(p, &mc); break;
+        case 3: rc = v_max_clusters<99>(p, &mc); break;
+        case 4: rc = v_max_clusters<131>(p, &mc); break;
+        case 5: rc = v_max_clusters<163>(p, &mc); break;
+        default: rc = v_max_clusters<195>(p, &mc); break;
+    }
+    if (rc) return rc;
+    if (mc < 1) return 1;
+    p.nclusters = n < mc ? n : mc;
+    *plan = p;
+    return VPPB200_OK;
+}
+
+template <int NS>
+static int run_v_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int pass, int n, const VPlan &p,
+                   cudaStream_t st)
 {
     VArgs a;
-    a.W = W; a.H = H; a.D = D; a.n = n; a.pass = pass; a.csize = p.csize; a.SC = p.SC;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(p.csize * p.nclusters));
-    cfg.blockDim = dim3(SWV_WARPS * 32);
-    cfg.dynamicSmemBytes = p.smem;
-    cfg.stream = st;
+    a.t = t; a.n = n; a.pass = pass; a.csize = p.csize; a.GC = p.GC;
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    VPP_CUDA_TRY(cudaLaunchKernelEx(&cfg, sgm_v_kernel<NW, PAD>, img, cost, S, a));
+    // FULL: K2 splits into VPARTS equal thirds of whole VU-blocks
+    const bool full = t.K2 % (VPARTS * VU) == 0;
+    int rc = full ? v_config<NS, true>(&cfg, attr, p, st) : v_config<NS, false>(&cfg, attr, p, st);
+    if (rc) return rc;
+    if (full) VPP_CUDA_TRY(cudaLaunchKernelEx(&cfg, sgm_v_kernel<NS, true>, img, cost, S, a));
+    else VPP_CUDA_TRY(cudaLaunchKernelEx(&cfg, sgm_v_kernel<NS, false>, img, cost, S, a));
     note_launch();
     return VPPB200_OK;
 }
 
-template <int NW, bool PAD>
-static int aggregate_plane_t(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, int W, int H, int D, int n, int h_bwd,
-                             cudaStream_t st)
+static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int pass, int n, const VPlan &p,
+                 cudaStream_t st)
 {
-    VPlan plan;
-    int rc = plan_v<NW, PAD>(W, n, &plan);
-    if (rc) return rc;
-    const uint16_t *cost = reinterpret_cast<const uint16_t *>(cost8);
-    uint32_t *S = reinterpret_cast<uint32_t *>(S16);
-    if ((rc = run_h<NW>(img, cost, S, W, H, D, +1, true, n, st))) return rc;
-    if ((rc = run_v<NW, PAD>(img, cost, S, W, H, D, 0, n, plan, st))) return rc;
-    if ((rc = run_v<NW, PAD>(img, cost, S, W, H, D, 1, n, plan, st))) return rc;
-    if (h_bwd && (rc = run_h<NW>(img, cost, S, W, H, D, -1, false, n, st))) return rc;
-    return VPPB200_OK;
+    switch (p.GC) {
+        case 1: return run_v_t<35>(img, cost, S, t, pass, n, p, st);
+        case 2: return run_v_t<67>(img, cost, S, t, pass, n, p, st);
+        case 3: return run_v_t<99>(img, cost, S, t, pass, n, p, st);
+        case 4: return run_v_t<131>(img, cost, S, t, pass, n, p, st);
+        case 5: return run_v_t<163>(img, cost, S, t, pass, n, p, st);
+        default: return run_v_t<195>(img, cost, S, t, pass, n, p, st);
+    }
 }
 
 // does the cluster sweep cover this shape on the current device?  (strip state must fit one cluster's shared memory)
 static int g_sweep_off = 0;
 void sweep_set_enabled(int on) { g_sweep_off = !on; }
-bool aggregate_plane_supported(int W, int H, int D, int n)
+bool aggregate_tile_supported(int W, int H, int D, int n)
 {
-    if (g_sweep_off || (long)W * H * 128 >= (1L << 31) || H < 3) return false;
-    const int nw = (D + 63) / 64;
-    const bool pad = (D != 64 * nw);
+    if (g_sweep_off || H < 3) return false;
+    const TL t = make_tl(W, H, D);
+    if (t.frame >= (1L << 31)) return false;
     VPlan plan;
-    int rc;
-    switch (nw) {
-        case 1: rc = pad ? plan_v<1, true>(W, n, &plan) : plan_v<1, false>(W, n, &plan); break;
-        case 2: rc = pad ? plan_v<2, true>(W, n, &plan) : plan_v<2, false>(W, n, &plan); break;
-        case 3: rc = pad ? plan_v<3, true>(W, n, &plan) : plan_v<3, false>(W, n, &plan); break;
-        default: rc = pad ? plan_v<4, true>(W, n, &plan) : plan_v<4, false>(W, n, &plan); break;
-    }
-    return rc == VPPB200_OK;
+    return plan_v(t, n, &plan) == VPPB200_OK;
 }
 
 // 0 = done; 1 = this shape does not fit the cluster sweep (caller uses sgm.cu); < 0 = error.
-// h_bwd = 0 leaves out r0 of pass 1 (the caller fuses it into the WTA sweep).
-int launch_aggregate_plane(const uint8_t *img, const uint8_t *cost, uint16_t *S, int W, int H, int D, int n, int h_bwd,
-                           cudaStream_t st)
+int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, int W, int H, int D, int n, cudaStream_t st)
 {
-    if ((long)W * H * 128 >= (1L << 31) || H < 3) return 1;
-    const int nw = (D + 63) / 64;
-    const bool pad = (D != 64 * nw);
-    switch (nw) {
-        case 1: return pad ? aggregate_plane_t<1, true>(img, cost, S, W, H, D, n, h_bwd, st)
-                           : aggregate_plane_t<1, false>(img, cost, S, W, H, D, n, h_bwd, st);
-        case 2: return pad ? aggregate_plane_t<2, true>(img, cost, S, W, H, D, n, h_bwd, st)
-                           : aggregate_plane_t<2, false>(img, cost, S, W, H, D, n, h_bwd, st);
-        case 3: return pad ? aggregate_plane_t<3, true>(img, cost, S, W, H, D, n, h_bwd, st)
-                           : aggregate_plane_t<3, false>(img, cost, S, W, H, D, n, h_bwd, st);
-        default: return pad ? aggregate_plane_t<4, true>(img, cost, S, W, H, D, n, h_bwd, st)
-                            : aggregate_plane_t<4, false>(img, cost, S, W, H, D, n, h_bwd, st);
-    }
+    const TL t = make_tl(W, H, D);
+    VPlan plan;
+    int rc = plan_v(t, n, &plan);
+    if (rc) return rc;
+    const uint16_t *cost = reinterpret_cast<const uint16_t *>(cost8);
+    uint32_t *S = reinterpret_cast<uint32_t *>(S16);
+    if ((rc = run_h(img, cost, S, t, +1, n, st))) return rc;
+    if ((rc = run_v(img, cost, S, t, 0, n, plan, st))) return rc;
+    if ((rc = run_v(img, cost, S, t, 1, n, plan, st))) return rc;
+    if ((rc = run_h(img, cost, S, t, -1, n, st))) return rc;
+    return VPPB200_OK;
 }
+
+// uint8 elements of a layout-T cost volume (S has the same number of uint16 elements)
+size_t tile_volume_elems(int W, int H, int D, int n) { return (size_t)n * (size_t)make_tl(W, H, D).frame * 2; }
 
 }  // namespace vppb200
