@@ -329,23 +329,33 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
     // rsgm.py:263-268  Hamming volume (+ optional guided modulation); rsgm.py:270  8-path aggregation (effective default
     // parameters); rsgm.py:272-273  WTA left (+ equiangular sub-pixel) and right
     const bool tiled = aggregate_tile_supported(d.Wp, d.Hp, D, n);
+    const bool want_volume = taps && taps->dsi_agg;          // only the test tap needs the aggregated volume itself
     const uint16_t *S_final = w.S;
     if (tiled) {
         if ((rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
         if (hints && (rc = launch_guided_tile(w.dsi, hints, validhints, d, n, st))) return rc;
         tm.mark();
-        if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc < 0 ? rc : VPPB200_ERR_ARG;
-        tm.mark();
-        if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
-        S_final = w.S_xyd;
+        if (!want_volume) {
+            // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
+            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, st)))
+                return rc < 0 ? rc : VPPB200_ERR_ARG;
+            tm.mark();
+        } else {
+            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, st)))
+                return rc < 0 ? rc : VPPB200_ERR_ARG;
+            tm.mark();
+            if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
+            S_final = w.S_xyd;
+            if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
+        }
     } else {
         if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
         if (hints && (rc = launch_guided_u8(w.dsi, hints, validhints, d, n, st))) return rc;
         tm.mark();
         if ((rc = launch_aggregate_fast(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc;
         tm.mark();
+        if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
     }
-    if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
     tm.mark();
     if ((rc = launch_median(w.dl, w.dlf, d.Wp, d.Hp, n, st))) return rc;
     if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, st))) return rc;

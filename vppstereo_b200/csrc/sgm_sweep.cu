@@ -226,15 +226,22 @@ static size_t h_stage_bytes(int K2) { return (size_t)K2 * (HCROW + HSROW); }
 
 __device__ __forceinline__ uint32_t &u4c(uint4 &v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-template <int NW, bool STORE, int DIR>
+// MODE 0: S = L (first sweep);  MODE 1: S += L;  MODE 2: S + L is the final aggregated volume and is consumed on the
+// fly by the winner-takes-all step instead of being written (RSGM/StereoBMHelper.cpp:634-750 left, :893-1015 right,
+// :1072-1102 sub-pixel; same arithmetic as wta_rows_kernel in rsgm_ops.cu, which sweeps x = W-1 .. 0 like this pass).
+template <int NW, int MODE, int DIR>
 __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__restrict__ img, const uint16_t *__restrict__ cost,
-                                                            uint32_t *__restrict__ S, TL t, long total_rows)
+                                                            uint32_t *__restrict__ S, TL t, long total_rows,
+                                                            float *__restrict__ disp_l, float *__restrict__ disp_r,
+                                                            const float *__restrict__ lut)
 {
+    constexpr bool STORE = MODE == 0, WTA = MODE == 2;
+    static_assert(!WTA || DIR < 0, "the fused WTA rides the backward sweep");
     extern __shared__ __align__(16) uint8_t hsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * HWARPS + warp;
     if (row >= total_rows) return;
-    const int K2 = t.K2, W = t.W;
+    const int K2 = t.K2, W = t.W, D = t.D;
     const int stage_b = K2 * (HCROW + HSROW);
     uint8_t *base = hsm + (size_t)warp * 2 * stage_b;
     const uint8_t *irow = img + row * W;
@@ -245,6 +252,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     for (int j = 0; j < NW; j++) wv[j] = NW * lane + j < K2;
     const int nchunks = W / 8;                      // W % 16 == 0
     const int xs = DIR > 0 ? 0 : W - 1;
+    const int d0 = 2 * NW * lane;
 
     // gather chunk q (sweep order) into stage q & 1: 16-byte pieces, one per cost row, two per S row
     auto issue = [&](int q) {
@@ -284,12 +292,16 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     uint32_t w[NW];
 #pragma unroll
     for (int j = 0; j < NW; j++) w[j] = 0;
+    uint32_t bucket[2 * NW];                        // WTA right: best (cost << 16 | d) of the in-flight target pixels
+#pragma unroll
+    for (int k = 0; k < 2 * NW; k++) bucket[k] = 0xFFFFFFFFu;
     int step = 0;
     for (int q = 0; q < nchunks; q++) {
         cp_async_wait<1>();
         __syncwarp();
         uint8_t *sb = base + (q & 1) * stage_b;
         uint8_t *ssb = sb + K2 * HCROW;
+        const int xlo = (DIR > 0 ? q : nchunks - 1 - q) * 8;
         // this lane's rows of the chunk: 8 pixels x NW disparity pairs, costs (uint16) and S words
         uint4 cv[NW], s0[NW], s1[NW];
 #pragma unroll
@@ -303,6 +315,9 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                 }
             }
         }
+        float out_l = 0.0f, out_r = 0.0f;            // lane p keeps the results of the chunk's pixel p
+        // per-warp scratch behind the stages: final S of the current and of the previous pixel (sub-pixel lookups)
+        uint32_t *scr = reinterpret_cast<uint32_t *>(hsm + (size_t)HWARPS * 2 * stage_b) + warp * 2 * K2;
 #pragma unroll
         for (int pp = 0; pp < 8; pp++, step++) {
             const int p = DIR > 0 ? pp : 7 - pp;
@@ -322,25 +337,78 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
 #pragma unroll
             for (int j = 0; j < NW; j++) if (!wv[j]) nw[j] = SW_BIG2;
             const uint32_t m2 = sw_min<NW>(nw) * 0x10001u;
+            uint32_t fin[NW];
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 w[j] = nw[j] - m2;
                 uint32_t &acc = p < 4 ? u4c(s0[j], p) : u4c(s1[j], p - 4);
                 acc = STORE ? nw[j] : acc + nw[j];
+                fin[j] = acc;
             }
-        }
+            if (WTA) {
+                const int x = xlo + p;
+                uint32_t key[2 * NW];
 #pragma unroll
-        for (int j = 0; j < NW; j++) {
-            if (wv[j]) {
-                *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW) = s0[j];
-                *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW + 16) = s1[j];
+                for (int j = 0; j < NW; j++) {
+                    const int d = d0 + 2 * j;
+                    key[2 * j] = wv[j] ? ((fin[j] << 16) | (uint32_t)d) : 0xFFFFFFFFu;
+                    key[2 * j + 1] = wv[j] ? ((fin[j] & 0xFFFF0000u) | (uint32_t)(d + 1)) : 0xFFFFFFFFu;
+                }
+                // left: first arg-min over d <= min(D-1, x)
+                const int end = min(D - 1, x);
+                uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < 2 * NW; k++) m = min(m, (d0 + k <= end) ? key[k] : 0xFFFFFFFFu);
+                m = __reduce_min_sync(0xFFFFFFFFu, m);
+                const int best = (int)(m & 0xFFFFu);
+                float o = (float)best;
+                // final S of this pixel -> scratch (two buffers by step parity: the other one still holds pixel x+1)
+                uint32_t *sc = scr + (step & 1) * K2;
+#pragma unroll
+                for (int j = 0; j < NW; j++) if (wv[j]) sc[NW * lane + j] = fin[j];
+                __syncwarp();
+                if (x >= 1 && x <= W - 2) {
+                    if (best > 0) {
+                        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(sc);
+                        const int c0 = s16[best - 1], c1 = (int)(m >> 16);
+                        // best = D-1 reads the next pixel's d = 0 (xyd stream order)
+                        const int c2 = best + 1 < D ? s16[best + 1] : reinterpret_cast<const uint16_t *>(scr + ((step & 1) ^ 1) * K2)[0];
+                        const int lower = min(c1 - c0, c1 - c2);            // <= 0
+                        o = __fadd_rn((float)best, __fmul_rn((float)(c2 - c0), lut[-lower]));
+                    } else {
+                        o = -10.0f;
+                    }
+                }
+                __syncwarp();
+                if (lane == p) out_l = o;
+                // right: every in-flight target absorbs its disparity slot, slot 0 retires to disp_r[x]
+#pragma unroll
+                for (int k = 0; k < 2 * NW; k++) bucket[k] = min(bucket[k], key[k]);
+                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bucket[0], 0);
+                if (lane == p) out_r = (float)(b0 & 0xFFFFu);
+                uint32_t from_up = __shfl_down_sync(0xFFFFFFFFu, bucket[0], 1);
+                if (lane == 31) from_up = 0xFFFFFFFFu;
+#pragma unroll
+                for (int k = 0; k < 2 * NW - 1; k++) bucket[k] = bucket[k + 1];
+                bucket[2 * NW - 1] = from_up;
             }
         }
-        __syncwarp();
-        {
+        if (WTA) {
+            if (lane < 8) {
+                disp_l[row * W + xlo + lane] = out_l;
+                disp_r[row * W + xlo + lane] = out_r;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                if (wv[j]) {
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW) = s0[j];
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW + 16) = s1[j];
+                }
+            }
+            __syncwarp();
             // write the chunk's S rows back: two 16-byte pieces = one 32-byte sector per row
-            const int xc = DIR > 0 ? q : nchunks - 1 - q;
-            const int toff = ((xc >> 2) * K2) * 32 + (xc & 3) * 8;
+            const int toff = ((xlo >> 5) * K2) * 32 + (xlo & 31);
             uint32_t *dst = srow + toff + (lane >> 1) * 32 + (lane & 1) * 4;
             const uint8_t *src = ssb + (lane >> 1) * HSROW + (lane & 1) * 16;
             for (int r0 = 0; r0 < K2; r0 += 16)
@@ -353,28 +421,35 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     cp_async_wait<0>();
 }
 
-template <int NW, bool STORE, int DIR>
-static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int n, cudaStream_t st)
+template <int NW, int MODE, int DIR>
+static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int n, float *dl, float *dr,
+                   const float *lut, cudaStream_t st)
 {
     const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
-    const size_t smem = (size_t)HWARPS * 2 * h_stage_bytes(t.K2);
-    auto kern = sgm_h_kernel<NW, STORE, DIR>;
+    const size_t smem = (size_t)HWARPS * 2 * h_stage_bytes(t.K2) + (MODE == 2 ? (size_t)HWARPS * 2 * t.K2 * 4 : 0);
+    auto kern = sgm_h_kernel<NW, MODE, DIR>;
     if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows);
+    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows, dl, dr, lut);
     VPP_LAUNCH_CHECK("sgm_h_kernel");
     return VPPB200_OK;
 }
 
-// forward sweep stores S = L, backward sweep adds
-static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int dirn, int n, cudaStream_t st)
+// mode 0: forward sweep, S = L;  mode 1: backward sweep, S += L;  mode 2: backward sweep fused with WTA (dl, dr, lut)
+static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int mode, int n, float *dl, float *dr,
+                 const float *lut, cudaStream_t st)
 {
+#define VPP_RUN_H(NW)                                                                                   \
+    return mode == 0 ? run_h_t<NW, 0, 1>(img, cost, S, t, n, nullptr, nullptr, nullptr, st)             \
+         : mode == 1 ? run_h_t<NW, 1, -1>(img, cost, S, t, n, nullptr, nullptr, nullptr, st)            \
+                     : run_h_t<NW, 2, -1>(img, cost, S, t, n, dl, dr, lut, st)
     switch ((t.K2 + 31) / 32) {
-        case 1: return dirn > 0 ? run_h_t<1, true, 1>(img, cost, S, t, n, st) : run_h_t<1, false, -1>(img, cost, S, t, n, st);
-        case 2: return dirn > 0 ? run_h_t<2, true, 1>(img, cost, S, t, n, st) : run_h_t<2, false, -1>(img, cost, S, t, n, st);
-        case 3: return dirn > 0 ? run_h_t<3, true, 1>(img, cost, S, t, n, st) : run_h_t<3, false, -1>(img, cost, S, t, n, st);
-        default: return dirn > 0 ? run_h_t<4, true, 1>(img, cost, S, t, n, st) : run_h_t<4, false, -1>(img, cost, S, t, n, st);
+        case 1: VPP_RUN_H(1);
+        case 2: VPP_RUN_H(2);
+        case 3: VPP_RUN_H(3);
+        default: VPP_RUN_H(4);
     }
+#undef VPP_RUN_H
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -772,7 +847,10 @@ bool aggregate_tile_supported(int W, int H, int D, int n)
 }
 
 // 0 = done; 1 = this shape does not fit the cluster sweep (caller uses sgm.cu); < 0 = error.
-int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, int W, int H, int D, int n, cudaStream_t st)
+// dl != NULL: the last sweep is fused with the winner-takes-all step (left + sub-pixel into dl, right into dr) and the
+// final S is never written; dl == NULL: S holds the aggregated volume in layout T.
+int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, int W, int H, int D, int n, float *dl,
+                          float *dr, const float *lut, cudaStream_t st)
 {
     const TL t = make_tl(W, H, D);
     VPlan plan;
@@ -780,10 +858,10 @@ int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S1
     if (rc) return rc;
     const uint16_t *cost = reinterpret_cast<const uint16_t *>(cost8);
     uint32_t *S = reinterpret_cast<uint32_t *>(S16);
-    if ((rc = run_h(img, cost, S, t, +1, n, st))) return rc;
+    if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_v(img, cost, S, t, 0, n, plan, st))) return rc;
     if ((rc = run_v(img, cost, S, t, 1, n, plan, st))) return rc;
-    if ((rc = run_h(img, cost, S, t, -1, n, st))) return rc;
+    if ((rc = run_h(img, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, st))) return rc;
     return VPPB200_OK;
 }
 
