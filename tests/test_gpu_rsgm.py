@@ -243,3 +243,30 @@ def test_kitti_shape_properties(mods, orc):
     xs = np.arange(gt.shape[1])[None, :]
     sel = (xs > gt + 16) & (got[0] > 0)
     assert np.median(np.abs(got[0] - gt)[sel]) < 4.0    # the synthetic right view is warped with d(u), not d(x)
+
+
+def test_pipeline_streaming_matches_synchronous(mods):
+    """VppRsgmPipeline.submit_host/collect (copies overlapped on their own streams, two batches in flight) returns what the
+    synchronous run_host returns for the same batches and pattern seeds."""
+    import torch
+    from vppstereo_b200.pipeline import VppRsgmPipeline
+    synth = mods[2]
+    frames = [synth.make_pair(40 + f, shape=(60, 140), hints="lidar") for f in range(6)]
+    batches = []
+    for b in range(3):
+        fr = frames[2 * b:2 * b + 2]
+        batches.append(tuple(torch.from_numpy(np.stack([p[k] for p in fr])).pin_memory() for k in ("left", "right", "hints")))
+    sync_pipe = VppRsgmPipeline(60, 140, 3, batch=2, dmax=64, seed=5)
+    want = [sync_pipe.run_host(*b).clone().numpy() for b in batches]
+    pipe = VppRsgmPipeline(60, 140, 3, batch=2, dmax=64, seed=5)
+    got, prev = [], None
+    for b in batches:
+        tk = pipe.submit_host(*b)
+        if prev is not None:
+            got.append(pipe.collect(prev).clone().numpy())
+        prev = tk
+    got.append(pipe.collect(prev).clone().numpy())
+    for k in range(3):
+        assert_same(got[k], want[k], f"streamed batch {k}")
+    with pytest.raises(RuntimeError):
+        pipe.collect(0)

@@ -6,7 +6,8 @@ batch of frames, with the images staying on the device between the two (test.py:
     disp = pipe.run_host(left_pinned, right_pinned, hints_pinned)  # host tensors in, pinned host float32 out
 
 run_host is the end-to-end path: host->device copies of the three inputs and the device->host copy of the disparities
-are part of the call.
+are part of the call.  submit_host / collect is the same path for streams of batches: the copies of batch k+1 and of
+batch k-1 ride their own CUDA streams while batch k computes (two staging sets, events between the streams).
 """
 import ctypes as C
 
@@ -42,6 +43,7 @@ class VppRsgmPipeline:
             self.d_right = torch.empty_like(self.lv)
             self.d_hints = torch.empty((self.N, self.H, self.W), dtype=torch.float32, device=self.device)
             self.h_disp = torch.empty((self.N, self.H, self.W), dtype=torch.float32).pin_memory()
+            self._stream_sets = None                  # created by the first submit_host
 
     def workspace_bytes(self):
         return self.ws_rsgm.numel() + self.ws_vpp.numel()
@@ -80,3 +82,57 @@ class VppRsgmPipeline:
             self.h_disp[:N].copy_(out, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
         return self.h_disp[:N]
+
+    # ---- streaming front-end: overlapped host<->device copies ---------------------------------------------------
+    def _streaming(self):
+        torch = self.torch
+        if self._stream_sets is None:
+            with torch.cuda.device(self.device):
+                sets = []
+                for _ in range(2):
+                    sets.append(dict(left=torch.empty_like(self.lv), right=torch.empty_like(self.lv),
+                                     hints=torch.empty_like(self.d_hints), disp=torch.empty_like(self.disp),
+                                     h_disp=torch.empty((self.N, self.H, self.W), dtype=torch.float32).pin_memory(),
+                                     copied_in=torch.cuda.Event(), computed=torch.cuda.Event(), copied_out=torch.cuda.Event(),
+                                     busy=False))
+                self._stream_sets = dict(sets=sets, h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device), turn=0)
+        return self._stream_sets
+
+    def submit_host(self, left, right, hints):
+        """Queue one batch of host tensors (pinned for real overlap); returns a ticket for collect().  At most two
+        batches are in flight: submitting a third one first requires collecting the oldest."""
+        torch = self.torch
+        ss = self._streaming()
+        slot = ss["turn"] & 1
+        st = ss["sets"][slot]
+        if st["busy"]:
+            raise RuntimeError("submit_host: collect() the batch submitted two calls ago first")
+        N = left.shape[0]
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(ss["h2d"]):
+                # the staging set was last read by the compute of two submits ago, which collect() has waited for
+                st["left"][:N].copy_(left, non_blocking=True)
+                st["right"][:N].copy_(right, non_blocking=True)
+                st["hints"][:N].copy_(hints, non_blocking=True)
+                st["copied_in"].record(ss["h2d"])
+            compute.wait_event(st["copied_in"])
+            self.run_device(st["left"][:N], st["right"][:N], st["hints"][:N], out=st["disp"][:N])
+            st["computed"].record(compute)
+            with torch.cuda.stream(ss["d2h"]):
+                ss["d2h"].wait_event(st["computed"])
+                st["h_disp"][:N].copy_(st["disp"][:N], non_blocking=True)
+                st["copied_out"].record(ss["d2h"])
+        st["busy"], st["n"] = True, N
+        ss["turn"] += 1
+        return slot
+
+    def collect(self, ticket):
+        """Wait for a submitted batch; returns its pinned host float32 [N,H,W] disparities (valid until that staging set is
+        reused by the second submit_host after this call)."""
+        st = self._streaming()["sets"][ticket]
+        if not st["busy"]:
+            raise RuntimeError("collect: nothing in flight for this ticket")
+        st["copied_out"].synchronize()
+        st["busy"] = False
+        return st["h_disp"][:st["n"]]
