@@ -474,6 +474,43 @@ __device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c)
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- halo exchange between the CTAs of a cluster: asynchronous remote stores that complete transaction bytes on an
+// mbarrier of the destination CTA (st.async ... mbarrier::complete_tx), so that neither side needs a fence or a
+// cluster-wide barrier: the consumer waits on its own mbarrier for the expected byte count of a row.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error traps (visible failure) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spin = 0; spin < (1u << 26); spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, int rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v),
+                 "r"(remote_bar)
+                 : "memory");
+}
+
 // per-path registers of the disparity walk
 struct VPath {
     uint32_t cur;      // L[2k], L[2k+1] of the predecessor (un-normalised)
@@ -555,12 +592,25 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
     uint32_t *mn = st + 3 * K2 * NS;                // [3][VPARTS][NS] min_d of each third of that row
     for (int idx = tid; idx < 3 * K2 * NS; idx += blockDim.x) st[idx] = SW_BIG2;
     for (int idx = tid; idx < 3 * VPARTS * NS; idx += blockDim.x) mn[idx] = (idx % NS == BIGS) ? 0u : 0x3FFFu;
-    // r1 lines move by +dj per row, r3 lines by -dj: where a leaving line's state goes
+    // r1 lines move by +dj per row, r3 lines by -dj.  A line that leaves the strip goes to the neighbour's halo slot;
+    // hb[0..1] count the bytes of an entering r1 line (row parity), hb[2..3] those of an entering r3 line.
     const bool has1 = rank + dj >= 0 && rank + dj < a.csize, has3 = rank - dj >= 0 && rank - dj < a.csize;
-    uint32_t *push1_st = has1 ? cluster.map_shared_rank(st, rank + dj) : nullptr;
-    uint32_t *push3_st = has3 ? cluster.map_shared_rank(st, rank - dj) : nullptr;
+    const uint32_t st_a = smem_u32(st), mn_a = smem_u32(mn), hb_a = (smem_u32(mn + 3 * VPARTS * NS) + 7u) & ~7u;
+    const uint32_t push1_st = has1 ? mapa_u32(st_a, rank + dj) : 0u, push1_mn = has1 ? mapa_u32(mn_a, rank + dj) : 0u,
+                   push1_hb = has1 ? mapa_u32(hb_a, rank + dj) : 0u;
+    const uint32_t push3_st = has3 ? mapa_u32(st_a, rank - dj) : 0u, push3_mn = has3 ? mapa_u32(mn_a, rank - dj) : 0u,
+                   push3_hb = has3 ? mapa_u32(hb_a + 16, rank - dj) : 0u;
     const int gl_leave1 = dj > 0 ? ng - 1 : 0, lane_leave1 = dj > 0 ? 31 : 0;
     const int gl_leave3 = dj > 0 ? 0 : ng - 1, lane_leave3 = dj > 0 ? 0 : 31;
+    // an r1 line enters where r3 lines leave (from rank - dj) and vice versa
+    const bool enter1 = has3 && gl == gl_leave3, enter3 = has1 && gl == gl_leave1;
+    const uint32_t halo_bytes = (uint32_t)(K2 + nact) * 4u;         // state words + the thirds' minima of one line
+    if (tid == 0) {
+        for (int q = 0; q < 4; q++) mbar_init(hb_a + q * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (has3) { mbar_expect_tx(hb_a, halo_bytes); mbar_expect_tx(hb_a + 8, halo_bytes); }
+        if (has1) { mbar_expect_tx(hb_a + 16, halo_bytes); mbar_expect_tx(hb_a + 24, halo_bytes); }
+    }
     cluster.sync();
 
     const int lc = gl * 32 + lane;                  // local column
@@ -592,8 +642,21 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
         if (active && f == cid) load_block(cost_f + (((long)i1 * G + g) * K2 + k0) * 32, nullptr, k1 - k0, cb, sb, false);
         for (int s = 0; s < H; s++, gstep++) {
             const int i = i1 + s * di;
-            if (gstep > 0) cluster.barrier_wait();  // row s-1 (state, mins, halos) complete everywhere
+            if (gstep > 0) __syncthreads();         // row s-1 of this strip (state, mins) complete
             const unsigned par = gstep & 1u;
+            if (active && gstep > 0) {
+                // the neighbours' lines of row s-1 must have landed in the halo slots (waited for on every row, also when
+                // the row does not read them, so that the barrier phases stay in step); one thread re-arms the phase
+                const uint32_t pp = par ^ 1u, phase = ((gstep - 1) >> 1) & 1u;
+                if (enter1) {
+                    mbar_wait(hb_a + pp * 8, phase);
+                    if (part == 0 && lane == 0) mbar_expect_tx(hb_a + pp * 8, halo_bytes);
+                }
+                if (enter3) {
+                    mbar_wait(hb_a + 16 + pp * 8, phase);
+                    if (part == 0 && lane == 0) mbar_expect_tx(hb_a + 16 + pp * 8, halo_bytes);
+                }
+            }
             if (active) {
                 const long tb0 = (((long)i * G + g) * K2 + k0) * 32;
                 const uint16_t *cp = cost_f + tb0;
@@ -694,15 +757,17 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
                     __syncwarp();
                     const int sl = __shfl_sync(0xFFFFFFFFu, d1, lane_leave1);
                     const uint32_t mv = __shfl_sync(0xFFFFFFFFu, mr1, lane_leave1);
-                    for (int k = k0 + lane; k < k1; k += 32) push1_st[(0 * K2 + k) * NS + halo_out] = st[(0 * K2 + k) * NS + sl];
-                    if (lane == 0) push1_st[3 * K2 * NS + (0 * VPARTS + part) * NS + halo_out] = mv;
+                    for (int k = k0 + lane; k < k1; k += 32)
+                        st_async_u32(push1_st + ((0 * K2 + k) * NS + halo_out) * 4, st[(0 * K2 + k) * NS + sl], push1_hb + par * 8);
+                    if (lane == 0) st_async_u32(push1_mn + ((0 * VPARTS + part) * NS + halo_out) * 4, mv, push1_hb + par * 8);
                 }
                 if (has3 && gl == gl_leave3) {
                     __syncwarp();
                     const int sl = __shfl_sync(0xFFFFFFFFu, d3, lane_leave3);
                     const uint32_t mv = __shfl_sync(0xFFFFFFFFu, mr3, lane_leave3);
-                    for (int k = k0 + lane; k < k1; k += 32) push3_st[(2 * K2 + k) * NS + halo_out] = st[(2 * K2 + k) * NS + sl];
-                    if (lane == 0) push3_st[3 * K2 * NS + (2 * VPARTS + part) * NS + halo_out] = mv;
+                    for (int k = k0 + lane; k < k1; k += 32)
+                        st_async_u32(push3_st + ((2 * K2 + k) * NS + halo_out) * 4, st[(2 * K2 + k) * NS + sl], push3_hb + par * 8);
+                    if (lane == 0) st_async_u32(push3_mn + ((2 * VPARTS + part) * NS + halo_out) * 4, mv, push3_hb + par * 8);
                 }
                 // prefetch for the next row: P2 intensities (on the row right after the pass's first row the "previous
                 // line" is that same row, StereoSGM_SSE.hpp:221,:238-243) and the first operand block
@@ -722,13 +787,18 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
                 }
             }
             if (++sh == n) sh = 0;
-            cluster.barrier_arrive();
         }
     }
-    if (gstep > 0) cluster.barrier_wait();          // nobody leaves while a neighbour may still push into its halo
+    // drain: the last row's inbound lines must have landed before this CTA's shared memory goes away
+    if (active && gstep > 0) {
+        const uint32_t pp = (gstep - 1) & 1u, phase = ((gstep - 1) >> 1) & 1u;
+        if (enter1) mbar_wait(hb_a + pp * 8, phase);
+        if (enter3) mbar_wait(hb_a + 16 + pp * 8, phase);
+    }
+    cluster.sync();
 }
 
-static size_t v_smem_bytes(int NS, int K2) { return ((size_t)3 * K2 * NS + (size_t)3 * VPARTS * NS) * 4; }
+static size_t v_smem_bytes(int NS, int K2) { return ((size_t)3 * K2 * NS + (size_t)3 * VPARTS * NS) * 4 + 8 + 4 * 8; }
 
 // tuning / test hook: upper bound on the strip width in columns (0 = as wide as shared memory allows)
 static int g_max_strip = 0;
