@@ -8,8 +8,10 @@ One step = one pass of the hot path (VPP random-pattern projection, then compute
 (configs[1]: 1242x375, LiDAR-like 5 % hints, D=192, batch 64 per GPU).  Prints ONE JSON line (rank 0).
   value      whole-job pairs/s with the inputs resident in HBM
   e2e        the same through the host-buffer API (pinned H2D of inputs + D2H of disparities inside the timed region)
-  roofline   SGM aggregation (dominant stage): algorithmic bytes (4*W*H*D + W*H per frame) / its device
-             time measured live with CUDA events on the launching stream, against MEASURED_PEAKS.json hbm_gbs
+  roofline   the dominant kernel, sgm_v_kernel (one vertical+diagonal sweep = 3 of the 8 SGM paths, 2 launches per step):
+             its compulsory bytes per launch (cost volume read + S read-modify-write = 5*W*H*D per frame) /
+             its average launch duration measured live with CUDA events on the launching stream, against
+             MEASURED_PEAKS.json hbm_gbs; the whole aggregation against SURVEY.md 8d's 4*W*H*D + W*H is reported beside it
   cpu_baseline  the reference's own CPU code (oracle/_ref) on the host cores, bounded sample, rank 0 at N=1
 --impl reference: times that CPU path instead, same metric/config, all host cores.
 """
@@ -28,8 +30,11 @@ METRIC = "VPP pairs/s & rSGM fps @1242x375, 5% hints, D=192; % of HBM peak"
 H, W, C, D = 375, 1242, 3, 192
 HP, WP = 384, 1248
 ALG_BYTES_AGG = 4 * WP * HP * D + WP * HP            # aggregate, per frame (368.5 MB)
+ALG_BYTES_VSWEEP = 5 * WP * HP * D + WP * HP         # one v-sweep launch, per frame: uint8 costs in, uint16 S in and out (460 MB)
+NCU_TRAFFIC_VSWEEP = 29.369e9                        # dram read+write per launch, profiles/r01_sweep_summary.md (ncu, batch 64)
 ALG_BYTES_VPP = 4 * H * W * C + 4 * H * W + H * W    # + C * in-image patch pixels of the hints (added at run time)
-STAGES = ["pad_gray", "census", "cost_volume", "sgm_aggregate", "wta_subpixel", "median_interp", "tail"]
+STAGES = ["pad_gray", "census", "cost_volume", "sgm_h_fwd", "sgm_v_down", "sgm_v_up", "sgm_h_bwd_wta", "wta_unfused", "median_interp",
+          "tail"]
 
 
 def measured_peak():
@@ -266,7 +271,7 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     launches = _lib.launch_count() - launches0
     import ctypes
-    st_ms = (ctypes.c_float * 7)(); calls = ctypes.c_int(0)
+    st_ms = (ctypes.c_float * len(STAGES))(); calls = ctypes.c_int(0)
     L.vppb200_stage_times(st_ms, ctypes.byref(calls))
     L.vppb200_stage_timing(0)
     stage_ms = {s: st_ms[i] / max(calls.value, 1) for i, s in enumerate(STAGES)}
@@ -330,8 +335,10 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         frames_total = world * B * args.steps
-        agg_s = stage_ms["sgm_aggregate"] * 1e-3
-        achieved = ALG_BYTES_AGG * B / agg_s / 1e9
+        v_s = 0.5 * (stage_ms["sgm_v_down"] + stage_ms["sgm_v_up"]) * 1e-3          # average launch of the dominant kernel
+        achieved = ALG_BYTES_VSWEEP * B / v_s / 1e9
+        agg_s = sum(stage_ms[k] for k in ("sgm_h_fwd", "sgm_v_down", "sgm_v_up", "sgm_h_bwd_wta")) * 1e-3
+        agg_achieved = ALG_BYTES_AGG * B / agg_s / 1e9
         vpp_bytes = (ALG_BYTES_VPP + C * 9 * n_hints) * B
         line = {
             "metric": METRIC, "value": frames_total / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -342,9 +349,13 @@ def main():
                        "collective": "all_gather of disparities per step" if world > 1 else "none",
                        "stage_ms_per_step": {k: round(v, 3) for k, v in stage_ms.items()}, "vpp_ms_per_step": round(vpp_ms, 3),
                        "rsgm_fps": B / (rsgm_ms * 1e-3), "vpp_pairs_per_s": B / (vpp_ms * 1e-3), "check_mean_disp": check_val},
-            "roofline": {"bound": "hbm", "kernel": "sgm_path_fast_kernel (8 launches = one aggregate_SSE)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch_group": ALG_BYTES_AGG * B,
+            "roofline": {"bound": "hbm", "kernel": "sgm_v_kernel (v-sweep: paths r1+r2+r3 of one pass, 2 launches per step)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_VSWEEP if B == 64 else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_VSWEEP * B, "launch_ms": v_s * 1e3,
+                         "aggregate_8_paths": {"what": "h_fwd + v_down + v_up + h_bwd(+WTA) vs SURVEY 8d aggregate bytes (4WHD+WH)",
+                                               "achieved": agg_achieved, "frac": agg_achieved / peak, "ms": agg_s * 1e3,
+                                               "algorithmic_bytes": ALG_BYTES_AGG * B},
                          "vpp": {"achieved": vpp_bytes / (vpp_ms * 1e-3) / 1e9, "frac": vpp_bytes / (vpp_ms * 1e-3) / 1e9 / peak,
                                  "algorithmic_bytes": vpp_bytes}},
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "pairs/s",

@@ -56,10 +56,23 @@ int vppb200_glibc_srand(uint32_t *state34, uint32_t seed);
 int vppb200_glibc_rand_fill(uint32_t *state34, uint8_t *out_host, int64_t n);
 
 /* Per-stage device timing of vppb200_compute_rsgm (CUDA events recorded on the call's stream at the stage boundaries).
- * Stages: 0 pad+gray, 1 census, 2 cost volume, 3 SGM aggregation, 4 WTA L/R + sub-pixel, 5 median + interpolation, 6 tail.
+ * The 8-path aggregation runs as four sweeps (csrc/sgm_sweep.cu): horizontal forward, vertical+diagonal down,
+ * vertical+diagonal up, horizontal backward; the last one also produces the WTA / sub-pixel disparities, so the WTA slot
+ * only fills on the paths that still materialise the aggregated volume (test tap, shapes the cluster sweep cannot hold,
+ * where the whole per-path aggregation is booked on the SGM_H_BWD slot).
  * vppb200_stage_timing(1) enables and resets; vppb200_stage_times synchronises the pending events, writes the
- * accumulated milliseconds per stage to ms_out[7] and the number of timed calls to *calls_out. */
-#define VPPB200_N_STAGES 7
+ * accumulated milliseconds per stage to ms_out[VPPB200_N_STAGES] and the number of timed calls to *calls_out. */
+#define VPPB200_STAGE_PAD_GRAY 0
+#define VPPB200_STAGE_CENSUS 1
+#define VPPB200_STAGE_COST 2
+#define VPPB200_STAGE_SGM_H_FWD 3
+#define VPPB200_STAGE_SGM_V_DOWN 4
+#define VPPB200_STAGE_SGM_V_UP 5
+#define VPPB200_STAGE_SGM_H_BWD 6
+#define VPPB200_STAGE_WTA 7
+#define VPPB200_STAGE_MEDIAN_INTERP 8
+#define VPPB200_STAGE_TAIL 9
+#define VPPB200_N_STAGES 10
 int vppb200_stage_timing(int enable);
 int vppb200_stage_times(float *ms_out, int *calls_out);
 
@@ -71,6 +84,7 @@ int vppb200_stage_times(float *ms_out, int *calls_out);
  *   VPPB200_TUNE_SGM_SWEEP:     0 = always use the per-path kernels, 1 = default */
 #define VPPB200_TUNE_SGM_MAX_STRIP 0
 #define VPPB200_TUNE_SGM_SWEEP 1
+#define VPPB200_TUNE_SGM_CLUSTERS 2   /* clusters launched by the v-sweep (0 = occupancy estimate); experiments only */
 int vppb200_set_tuning(int key, int value);
 
 /* ---- pyrSGM operators ----------------------------------------------------------------------------------- */

@@ -50,7 +50,7 @@ def lib():
     return _lib
 
 
-TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP = 0, 1
+TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS = 0, 1, 2
 
 
 def set_tuning(key, value):

@@ -76,13 +76,20 @@ struct StageMarks {
         for (auto &e : ev) cudaEventCreate(&e);
         cudaEventRecord(ev[next++], st);
     }
-    void mark() { if (on && next <= VPPB200_N_STAGES) cudaEventRecord(ev[next++], st); }
+    // stage `stage` ends here; stages that were skipped since the last mark get (almost) zero time
+    void done(int stage)
+    {
+        if (!on) return;
+        while (next <= stage + 1 && next <= VPPB200_N_STAGES) cudaEventRecord(ev[next++], st);
+    }
     void end()
     {
         if (!on) return;
+        done(VPPB200_N_STAGES - 1);
         std::lock_guard<std::mutex> lock(g_timer_mutex);
         for (auto &e : ev) g_timer.pending.push_back(e);
     }
+    static void hook(void *ctx, int stage) { static_cast<StageMarks *>(ctx)->done(stage); }
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -211,6 +218,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
     switch (key) {
         case VPPB200_TUNE_SGM_MAX_STRIP: sweep_set_max_strip(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_SWEEP: sweep_set_enabled(value); return VPPB200_OK;
+        case VPPB200_TUNE_SGM_CLUSTERS: sweep_set_clusters(value); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }
 }
@@ -322,10 +330,10 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
     if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, n, st))) return rc;
     if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, st))) return rc;
     if ((rc = launch_pad_flatbytes(left, w.guide, d, n, st))) return rc;
-    tm.mark();
+    tm.done(VPPB200_STAGE_PAD_GRAY);
     if ((rc = launch_census(w.gray_l, w.census_l, d.Wp, d.Hp, n, st))) return rc;
     if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, st))) return rc;
-    tm.mark();
+    tm.done(VPPB200_STAGE_CENSUS);
     // rsgm.py:263-268  Hamming volume (+ optional guided modulation); rsgm.py:270  8-path aggregation (effective default
     // parameters); rsgm.py:272-273  WTA left (+ equiangular sub-pixel) and right
     const bool tiled = aggregate_tile_supported(d.Wp, d.Hp, D, n);
@@ -334,16 +342,15 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
     if (tiled) {
         if ((rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
         if (hints && (rc = launch_guided_tile(w.dsi, hints, validhints, d, n, st))) return rc;
-        tm.mark();
+        tm.done(VPPB200_STAGE_COST);
+        const StageHook hook = {StageMarks::hook, &tm};
         if (!want_volume) {
             // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
-            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, st)))
+            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, &hook, st)))
                 return rc < 0 ? rc : VPPB200_ERR_ARG;
-            tm.mark();
         } else {
-            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, st)))
+            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, &hook, st)))
                 return rc < 0 ? rc : VPPB200_ERR_ARG;
-            tm.mark();
             if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
             S_final = w.S_xyd;
             if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
@@ -351,20 +358,20 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
     } else {
         if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
         if (hints && (rc = launch_guided_u8(w.dsi, hints, validhints, d, n, st))) return rc;
-        tm.mark();
+        tm.done(VPPB200_STAGE_COST);
         if ((rc = launch_aggregate_fast(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc;
-        tm.mark();
+        tm.done(VPPB200_STAGE_SGM_H_BWD);                    // the per-path fallback is booked on the last sweep's slot
         if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
     }
-    tm.mark();
+    tm.done(VPPB200_STAGE_WTA);
     if ((rc = launch_median(w.dl, w.dlf, d.Wp, d.Hp, n, st))) return rc;
     if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, st))) return rc;
     if ((rc = launch_interp_clip(w.dlf, d.Wp, d.Hp, n, st))) return rc;
     if ((rc = launch_interp_clip(w.drf, d.Wp, d.Hp, n, st))) return rc;
-    tm.mark();
+    tm.done(VPPB200_STAGE_MEDIAN_INTERP);
     // rsgm.py:275-292  crop, LR check, speckle filter, sub-pixel restore, background fill
     if ((rc = launch_tail(w.dlf, w.drf, disp_out, d, flags & 1, w.tail, n, st))) return rc;
-    tm.mark();
+    tm.done(VPPB200_STAGE_TAIL);
     tm.end();
     if (taps) {
         const size_t np = (size_t)n * d.Hp * d.Wp;

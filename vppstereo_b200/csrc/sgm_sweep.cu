@@ -804,6 +804,9 @@ static size_t v_smem_bytes(int NS, int K2) { return ((size_t)3 * K2 * NS + (size
 static int g_max_strip = 0;
 void sweep_set_max_strip(int cols) { g_max_strip = cols < 0 ? 0 : cols; }
 
+static int g_force_clusters = 0;    // experiment hook: launch this many clusters instead of the occupancy estimate
+void sweep_set_clusters(int c) { g_force_clusters = c < 0 ? 0 : c; }
+
 struct VPlan { int csize, GC, NS, nclusters; size_t smem; };
 
 template <int NS, bool FULL>
@@ -868,6 +871,7 @@ static int plan_v(const TL &t, int n, VPlan *plan)
     }
     if (rc) return rc;
     if (mc < 1) return 1;
+    if (g_force_clusters > 0) mc = g_force_clusters;
     p.nclusters = n < mc ? n : mc;
     *plan = p;
     return VPPB200_OK;
@@ -920,7 +924,7 @@ bool aggregate_tile_supported(int W, int H, int D, int n)
 // dl != NULL: the last sweep is fused with the winner-takes-all step (left + sub-pixel into dl, right into dr) and the
 // final S is never written; dl == NULL: S holds the aggregated volume in layout T.
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, int W, int H, int D, int n, float *dl,
-                          float *dr, const float *lut, cudaStream_t st)
+                          float *dr, const float *lut, const StageHook *hook, cudaStream_t st)
 {
     const TL t = make_tl(W, H, D);
     VPlan plan;
@@ -928,10 +932,15 @@ int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S1
     if (rc) return rc;
     const uint16_t *cost = reinterpret_cast<const uint16_t *>(cost8);
     uint32_t *S = reinterpret_cast<uint32_t *>(S16);
+    auto done = [&](int stage) { if (hook) hook->fn(hook->ctx, stage); };
     if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, st))) return rc;
+    done(VPPB200_STAGE_SGM_H_FWD);
     if ((rc = run_v(img, cost, S, t, 0, n, plan, st))) return rc;
+    done(VPPB200_STAGE_SGM_V_DOWN);
     if ((rc = run_v(img, cost, S, t, 1, n, plan, st))) return rc;
+    done(VPPB200_STAGE_SGM_V_UP);
     if ((rc = run_h(img, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, st))) return rc;
+    done(VPPB200_STAGE_SGM_H_BWD);
     return VPPB200_OK;
 }
 
