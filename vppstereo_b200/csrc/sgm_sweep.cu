@@ -516,7 +516,7 @@ struct VPath {
     uint32_t cur;      // L[2k], L[2k+1] of the predecessor (un-normalised)
     uint32_t lo;       // L[2k-1], L[2k]
     uint32_t q;        // (minL + P2 - P1) x2
-    uint32_t ng;       // -(minL x2)
+    uint32_t ng;       // minL of the predecessor (subtracted as minL * -(0x10001))
     uint32_t mr;       // running min of the new values
 };
 
@@ -530,7 +530,9 @@ __device__ __forceinline__ void v_block(const uint32_t (&cb)[VU], const uint32_t
                                         uint32_t wr1, uint32_t wr2, uint32_t wr3, VPath &p1, VPath &p2, VPath &p3,
                                         uint32_t *Sg, int cnt, bool last)
 {
+    static_assert(VU % 2 == 0, "running minima are folded two pairs at a time");
     uint32_t nx1[VU], nx2[VU], nx3[VU];
+    uint32_t tp1 = 0, tp2 = 0, tp3 = 0;
 #pragma unroll
     for (int u = 0; u < VU; u++) {
         if (u + 1 < VU) {
@@ -552,10 +554,18 @@ __device__ __forceinline__ void v_block(const uint32_t (&cb)[VU], const uint32_t
             t1 = __viaddmin_u16x2(t1, SW_P1X2, p1.cur);                              // min(. + P1, L[d])
             t2 = __viaddmin_u16x2(t2, SW_P1X2, p2.cur);
             t3 = __viaddmin_u16x2(t3, SW_P1X2, p3.cur);
-            t1 = add3(t1, c, p1.ng); t2 = add3(t2, c, p2.ng); t3 = add3(t3, c, p3.ng);   // C + min(...) - minL
+            // C + min(...) - minL.  The ALU pipe (VIMNMX*, PRMT, IADD3: one warp instruction per 2 cycles and SMSP) is the
+            // busiest unit of this loop, so the adds are written as multiply-adds for the otherwise idle FMA pipe
+            // (IMAD.IADD / IMAD): ng = minL, the subtraction is minL * -(0x10001).
+            t1 = (t1 + c) + p1.ng * 0xFFFEFFFFu; t2 = (t2 + c) + p2.ng * 0xFFFEFFFFu; t3 = (t3 + c) + p3.ng * 0xFFFEFFFFu;
             w1[u * NS] = t1; w2[u * NS] = t2; w3[u * NS] = t3;
-            p1.mr = __vminu2(p1.mr, t1); p2.mr = __vminu2(p2.mr, t2); p3.mr = __vminu2(p3.mr, t3);
-            Sg[u * 32] = add3(t1, t2, t3) + sb[u];
+            if (u & 1) {
+                p1.mr = __vimin3_u16x2(p1.mr, tp1, t1); p2.mr = __vimin3_u16x2(p2.mr, tp2, t2); p3.mr = __vimin3_u16x2(p3.mr, tp3, t3);
+            } else if (GUARD && u + 1 >= cnt) {
+                p1.mr = __vminu2(p1.mr, t1); p2.mr = __vminu2(p2.mr, t2); p3.mr = __vminu2(p3.mr, t3);
+            }
+            tp1 = t1; tp2 = t2; tp3 = t3;
+            Sg[u * 32] = ((t1 + t2) + t3) + sb[u];
             p1.lo = hi1; p2.lo = hi2; p3.lo = hi3;
             p1.cur = nx1[u]; p2.cur = nx2[u]; p3.cur = nx3[u];
         }
@@ -715,11 +725,7 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
                     p1.q = (m1 + (uint32_t)(sw_adapt_p2(ipc, ip1) - SW_P1)) * 0x10001u;
                     p2.q = (m2 + (uint32_t)(sw_adapt_p2(ipc, ip2) - SW_P1)) * 0x10001u;
                     p3.q = (m3 + (uint32_t)(sw_adapt_p2(ipc, ip3) - SW_P1)) * 0x10001u;
-                    p1.ng = 0u - m1 * 0x10001u; p2.ng = 0u - m2 * 0x10001u; p3.ng = 0u - m3 * 0x10001u;
-                    // identity shuffles keep -(minL x2) in a register: otherwise ptxas re-fuses the multiply into every
-                    // add of the inner loop (IADD + IMAD instead of one IADD3 per path and disparity pair)
-                    p1.ng = __shfl_sync(0xFFFFFFFFu, p1.ng, lane); p2.ng = __shfl_sync(0xFFFFFFFFu, p2.ng, lane);
-                    p3.ng = __shfl_sync(0xFFFFFFFFu, p3.ng, lane);
+                    p1.ng = m1; p2.ng = m2; p3.ng = m3;
                     // register window over the disparity pairs; the neighbours just outside this warp's third are read
                     // before the other warps of the column group may overwrite them
                     const uint32_t pv1 = k0 > 0 ? s1[-NS] : SW_BIG2, pv2 = k0 > 0 ? s2[-NS] : SW_BIG2, pv3 = k0 > 0 ? s3[-NS] : SW_BIG2;
