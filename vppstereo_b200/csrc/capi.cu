@@ -99,6 +99,7 @@ struct RsgmWs {
     uint32_t *census_l, *census_r;
     uint8_t *dsi;
     uint16_t *S, *S_xyd;
+    void *halo;
     float *dl, *dlf, *dr, *drf;
     TailBufs tail;
 };
@@ -116,6 +117,7 @@ static size_t rsgm_ws_layout(const RsgmDims &d, int n, void *base, RsgmWs *ws)
     w.dsi = (uint8_t *)take(tv > np * d.D ? tv : np * d.D);
     w.S = (uint16_t *)take((tv > np * d.D ? tv : np * d.D) * 2);
     w.S_xyd = (uint16_t *)take(np * d.D * 2);                 // the reference's xyd order (WTA input, test tap)
+    w.halo = (void *)take(sweep_halo_bytes(d.D));
     w.dl = (float *)take(np * 4); w.dlf = (float *)take(np * 4); w.dr = (float *)take(np * 4); w.drf = (float *)take(np * 4);
     w.tail.u8 = (uint8_t *)take(nc); w.tail.label = (int *)take(nc * 4); w.tail.count = (int *)take(nc * 4);
     if (ws) *ws = w;
@@ -346,10 +348,10 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
         const StageHook hook = {StageMarks::hook, &tm};
         if (!want_volume) {
             // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
-            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, &hook, st)))
+            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, &hook, st)))
                 return rc < 0 ? rc : VPPB200_ERR_ARG;
         } else {
-            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, &hook, st)))
+            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, &hook, st)))
                 return rc < 0 ? rc : VPPB200_ERR_ARG;
             if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
             S_final = w.S_xyd;

@@ -474,42 +474,31 @@ __device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c)
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// ---- halo exchange between the CTAs of a cluster: asynchronous remote stores that complete transaction bytes on an
-// mbarrier of the destination CTA (st.async ... mbarrier::complete_tx), so that neither side needs a fence or a
-// cluster-wide barrier: the consumer waits on its own mbarrier for the expected byte count of a row.
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+// ---- halo exchange between the CTAs of a team (the CTAs that share one frame): self-validating words in global
+// memory.  State words are < 2^28 (two uint16 values <= 305), so the top four bits carry a tag that changes with the
+// row; the consumer polls a word until its tag is the expected one.  No fence, no barrier between CTAs: every word is
+// its own flag (relaxed gpu-scope stores and loads go through L2).
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t *p, uint32_t v)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 // bounded wait: a protocol error traps (visible failure) instead of hanging the device
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ uint32_t halo_wait(const uint32_t *p, uint32_t tag)
 {
-    for (uint32_t spin = 0; spin < (1u << 26); spin++) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-        if (ok) return;
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        const uint32_t v = ld_relaxed_gpu(p);
+        if ((v >> 28) == tag) return v & 0x0FFFFFFFu;
     }
     __trap();
+    return 0;
 }
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, int rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar)
-{
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v),
-                 "r"(remote_bar)
-                 : "memory");
-}
+static constexpr uint32_t HALO_INVALID = 0xF0000000u;
 
 // per-path registers of the disparity walk
 struct VPath {
@@ -577,11 +566,10 @@ __device__ __forceinline__ void v_block(const uint32_t (&cb)[VU], const uint32_t
 template <int NS, bool FULL>
 __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel(const uint8_t *__restrict__ img_all,
                                                                                 const uint16_t *__restrict__ cost_all,
-                                                                                uint32_t *__restrict__ S_all, VArgs a)
+                                                                                uint32_t *__restrict__ S_all, uint32_t *halo, VArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
+    const int rank = (int)(blockIdx.x % a.csize);   // position of this CTA's strip in its team
     const int cid = blockIdx.x / a.csize, nclusters = gridDim.x / a.csize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.t.W, H = a.t.H, K2 = a.t.K2, G = a.t.G;
@@ -599,29 +587,23 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
     const int nact = (K2 + KP - 1) / KP;            // warps of a column group that own disparity pairs
 
     uint32_t *st = smem;                            // [3][K2][NS]   un-normalised L of the previous row, per line
-    uint32_t *mn = st + 3 * K2 * NS;                // [3][VPARTS][NS] min_d of each third of that row
+    uint32_t *mn = st + 3 * K2 * NS;                // [3][VPARTS][NS] min_d of each share of that row
     for (int idx = tid; idx < 3 * K2 * NS; idx += blockDim.x) st[idx] = SW_BIG2;
     for (int idx = tid; idx < 3 * VPARTS * NS; idx += blockDim.x) mn[idx] = (idx % NS == BIGS) ? 0u : 0x3FFFu;
-    // r1 lines move by +dj per row, r3 lines by -dj.  A line that leaves the strip goes to the neighbour's halo slot;
-    // hb[0..1] count the bytes of an entering r1 line (row parity), hb[2..3] those of an entering r3 line.
+    // r1 lines move by +dj per row, r3 lines by -dj.  A line that leaves the strip goes to the neighbour CTA's inbound
+    // buffer in global memory: [CTA][r1 | r3][row parity][K2 state words + VPARTS minima], tagged per row.
+    const int HL = K2 + VPARTS;
     const bool has1 = rank + dj >= 0 && rank + dj < a.csize, has3 = rank - dj >= 0 && rank - dj < a.csize;
-    const uint32_t st_a = smem_u32(st), mn_a = smem_u32(mn), hb_a = (smem_u32(mn + 3 * VPARTS * NS) + 7u) & ~7u;
-    const uint32_t push1_st = has1 ? mapa_u32(st_a, rank + dj) : 0u, push1_mn = has1 ? mapa_u32(mn_a, rank + dj) : 0u,
-                   push1_hb = has1 ? mapa_u32(hb_a, rank + dj) : 0u;
-    const uint32_t push3_st = has3 ? mapa_u32(st_a, rank - dj) : 0u, push3_mn = has3 ? mapa_u32(mn_a, rank - dj) : 0u,
-                   push3_hb = has3 ? mapa_u32(hb_a + 16, rank - dj) : 0u;
+    uint32_t *in1 = halo + ((size_t)blockIdx.x * 2 + 0) * 2 * HL, *in3 = halo + ((size_t)blockIdx.x * 2 + 1) * 2 * HL;
+    uint32_t *push1 = halo + ((size_t)(blockIdx.x + dj) * 2 + 0) * 2 * HL;       // neighbour's inbound r1 (valid if has1)
+    uint32_t *push3 = halo + ((size_t)(blockIdx.x - dj) * 2 + 1) * 2 * HL;       // neighbour's inbound r3 (valid if has3)
     const int gl_leave1 = dj > 0 ? ng - 1 : 0, lane_leave1 = dj > 0 ? 31 : 0;
     const int gl_leave3 = dj > 0 ? 0 : ng - 1, lane_leave3 = dj > 0 ? 0 : 31;
     // an r1 line enters where r3 lines leave (from rank - dj) and vice versa
     const bool enter1 = has3 && gl == gl_leave3, enter3 = has1 && gl == gl_leave1;
-    const uint32_t halo_bytes = (uint32_t)(K2 + nact) * 4u;         // state words + the thirds' minima of one line
-    if (tid == 0) {
-        for (int q = 0; q < 4; q++) mbar_init(hb_a + q * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (has3) { mbar_expect_tx(hb_a, halo_bytes); mbar_expect_tx(hb_a + 8, halo_bytes); }
-        if (has1) { mbar_expect_tx(hb_a + 16, halo_bytes); mbar_expect_tx(hb_a + 24, halo_bytes); }
-    }
-    cluster.sync();
+    for (int idx = tid; idx < 2 * HL; idx += blockDim.x) { st_relaxed_gpu(in1 + idx, HALO_INVALID); st_relaxed_gpu(in3 + idx, HALO_INVALID); }
+    __threadfence();
+    cg::this_grid().sync();                         // every inbound buffer is invalidated before anybody pushes
 
     const int lc = gl * 32 + lane;                  // local column
     const int x = x0 + lc;
@@ -654,18 +636,23 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
             const int i = i1 + s * di;
             if (gstep > 0) __syncthreads();         // row s-1 of this strip (state, mins) complete
             const unsigned par = gstep & 1u;
+            uint32_t hm1 = 0x3FFFu, hm3 = 0x3FFFu;  // min_d of the lines that enter from the neighbours
             if (active && gstep > 0) {
-                // the neighbours' lines of row s-1 must have landed in the halo slots (waited for on every row, also when
-                // the row does not read them, so that the barrier phases stay in step); one thread re-arms the phase
-                const uint32_t pp = par ^ 1u, phase = ((gstep - 1) >> 1) & 1u;
+                // copy the neighbours' lines of row s-1 into the halo slot of that row's parity (every row, also when the
+                // row does not read them).  Each warp also takes the pairs just outside its share (register window).
+                const unsigned pp = par ^ 1u, tag = ((gstep - 1) >> 1) & 7u;
+                const int ka = max(k0 - 1, 0), kz = min(k1 + 1, K2);
                 if (enter1) {
-                    mbar_wait(hb_a + pp * 8, phase);
-                    if (part == 0 && lane == 0) mbar_expect_tx(hb_a + pp * 8, halo_bytes);
+                    const uint32_t *src = in1 + pp * HL;
+                    for (int k = ka + lane; k < kz; k += 32) st[(0 * K2 + k) * NS + HALO + (int)pp] = halo_wait(src + k, tag);
+                    for (int pt = 0; pt < nact; pt++) hm1 = min(hm1, halo_wait(src + K2 + pt, tag));
                 }
                 if (enter3) {
-                    mbar_wait(hb_a + 16 + pp * 8, phase);
-                    if (part == 0 && lane == 0) mbar_expect_tx(hb_a + 16 + pp * 8, halo_bytes);
+                    const uint32_t *src = in3 + pp * HL;
+                    for (int k = ka + lane; k < kz; k += 32) st[(2 * K2 + k) * NS + HALO + (int)pp] = halo_wait(src + k, tag);
+                    for (int pt = 0; pt < nact; pt++) hm3 = min(hm3, halo_wait(src + K2 + pt, tag));
                 }
+                __syncwarp();
             }
             if (active) {
                 const long tb0 = (((long)i * G + g) * K2 + k0) * 32;
@@ -721,6 +708,8 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
                         m2 = min(m2, mn[(1 * VPARTS + pt) * NS + d2]);
                         m3 = min(m3, mn[(2 * VPARTS + pt) * NS + r3s]);
                     }
+                    if (r1s == halo_in) m1 = hm1;
+                    if (r3s == halo_in) m3 = hm3;
                     // P2 from the FLAT image stream (prefetched); q = (min + P2 - P1) x2, ng = -(min x2)
                     p1.q = (m1 + (uint32_t)(sw_adapt_p2(ipc, ip1) - SW_P1)) * 0x10001u;
                     p2.q = (m2 + (uint32_t)(sw_adapt_p2(ipc, ip2) - SW_P1)) * 0x10001u;
@@ -757,23 +746,23 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
                 mn[(0 * VPARTS + part) * NS + d1] = mr1;
                 mn[(1 * VPARTS + part) * NS + d2] = mr2;
                 mn[(2 * VPARTS + part) * NS + d3] = mr3;
-                // push the lines that leave the strip into the neighbour's halo slot of this row's parity
-                const int halo_out = HALO + (int)par;
+                // push the lines that leave the strip to the neighbour's inbound buffer of this row's parity, tagged
+                const uint32_t otag = ((gstep >> 1) & 7u) << 28;
                 if (has1 && gl == gl_leave1) {
                     __syncwarp();
                     const int sl = __shfl_sync(0xFFFFFFFFu, d1, lane_leave1);
                     const uint32_t mv = __shfl_sync(0xFFFFFFFFu, mr1, lane_leave1);
-                    for (int k = k0 + lane; k < k1; k += 32)
-                        st_async_u32(push1_st + ((0 * K2 + k) * NS + halo_out) * 4, st[(0 * K2 + k) * NS + sl], push1_hb + par * 8);
-                    if (lane == 0) st_async_u32(push1_mn + ((0 * VPARTS + part) * NS + halo_out) * 4, mv, push1_hb + par * 8);
+                    uint32_t *dst = push1 + par * HL;
+                    for (int k = k0 + lane; k < k1; k += 32) st_relaxed_gpu(dst + k, st[(0 * K2 + k) * NS + sl] | otag);
+                    if (lane == 0) st_relaxed_gpu(dst + K2 + part, mv | otag);
                 }
                 if (has3 && gl == gl_leave3) {
                     __syncwarp();
                     const int sl = __shfl_sync(0xFFFFFFFFu, d3, lane_leave3);
                     const uint32_t mv = __shfl_sync(0xFFFFFFFFu, mr3, lane_leave3);
-                    for (int k = k0 + lane; k < k1; k += 32)
-                        st_async_u32(push3_st + ((2 * K2 + k) * NS + halo_out) * 4, st[(2 * K2 + k) * NS + sl], push3_hb + par * 8);
-                    if (lane == 0) st_async_u32(push3_mn + ((2 * VPARTS + part) * NS + halo_out) * 4, mv, push3_hb + par * 8);
+                    uint32_t *dst = push3 + par * HL;
+                    for (int k = k0 + lane; k < k1; k += 32) st_relaxed_gpu(dst + k, st[(2 * K2 + k) * NS + sl] | otag);
+                    if (lane == 0) st_relaxed_gpu(dst + K2 + part, mv | otag);
                 }
                 // prefetch for the next row: P2 intensities (on the row right after the pass's first row the "previous
                 // line" is that same row, StereoSGM_SSE.hpp:221,:238-243) and the first operand block
@@ -795,124 +784,128 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
             if (++sh == n) sh = 0;
         }
     }
-    // drain: the last row's inbound lines must have landed before this CTA's shared memory goes away
-    if (active && gstep > 0) {
-        const uint32_t pp = (gstep - 1) & 1u, phase = ((gstep - 1) >> 1) & 1u;
-        if (enter1) mbar_wait(hb_a + pp * 8, phase);
-        if (enter3) mbar_wait(hb_a + 16 + pp * 8, phase);
-    }
-    cluster.sync();
 }
 
-static size_t v_smem_bytes(int NS, int K2) { return ((size_t)3 * K2 * NS + (size_t)3 * VPARTS * NS) * 4 + 8 + 4 * 8; }
+static size_t v_smem_bytes(int NS, int K2) { return ((size_t)3 * K2 * NS + (size_t)3 * VPARTS * NS) * 4; }
 
-// tuning / test hook: upper bound on the strip width in columns (0 = as wide as shared memory allows)
+// tuning / test hook: upper bound on the strip width in columns (0 = chosen by the planner)
 static int g_max_strip = 0;
 void sweep_set_max_strip(int cols) { g_max_strip = cols < 0 ? 0 : cols; }
+static int g_force_teams = 0;       // experiment hook: frames in flight instead of the occupancy estimate
+void sweep_set_clusters(int c) { g_force_teams = c < 0 ? 0 : c; }
 
-static int g_force_clusters = 0;    // experiment hook: launch this many clusters instead of the occupancy estimate
-void sweep_set_clusters(int c) { g_force_clusters = c < 0 ? 0 : c; }
-
-struct VPlan { int csize, GC, NS, nclusters; size_t smem; };
-
-template <int NS, bool FULL>
-static int v_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, const VPlan &p, cudaStream_t st)
-{
-    auto kern = sgm_v_kernel<NS, FULL>;
-    VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    if (p.csize > 8) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    *cfg = cudaLaunchConfig_t{};
-    cfg->gridDim = dim3((unsigned)(p.csize * p.nclusters));
-    cfg->blockDim = dim3((unsigned)(p.GC * VPARTS * 32));
-    cfg->dynamicSmemBytes = p.smem;
-    cfg->stream = st;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg->attrs = attr; cfg->numAttrs = 1;
-    return VPPB200_OK;
-}
+// a team = the csize CTAs (one per SM) that hold one frame; nteams frames are in flight
+struct VPlan { int csize, GC, NS, nteams; size_t smem; };
 
 template <int NS>
-static int v_max_clusters(const VPlan &p, int *out)
+static int v_resident_ctas(size_t smem, int threads, int *out)
 {
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
-    int rc = v_config<NS, true>(&cfg, attr, p, nullptr);
-    if (rc) return rc;
-    cfg.gridDim = dim3((unsigned)(p.csize * 64));
-    cudaError_t e = cudaOccupancyMaxActiveClusters(out, sgm_v_kernel<NS, true>, &cfg);
-    if (e != cudaSuccess) { cudaGetLastError(); *out = 0; }
+    int dev = 0, sms = 0, per_sm = 0;
+    VPP_CUDA_TRY(cudaGetDevice(&dev));
+    VPP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VPP_CUDA_TRY(cudaFuncSetAttribute(sgm_v_kernel<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VPP_CUDA_TRY(cudaFuncSetAttribute(sgm_v_kernel<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VPP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgm_v_kernel<NS, true>, threads, smem));
+    *out = per_sm >= 1 ? sms : 0;                   // one CTA per SM: a second one would only share the SM's issue slots
     return VPPB200_OK;
 }
+static int v_resident(int GC, size_t smem, int *out)
+{
+    const int threads = GC * VPARTS * 32;
+    switch (GC) {
+        case 1: return v_resident_ctas<35>(smem, threads, out);
+        case 2: return v_resident_ctas<67>(smem, threads, out);
+        case 3: return v_resident_ctas<99>(smem, threads, out);
+        case 4: return v_resident_ctas<131>(smem, threads, out);
+        case 5: return v_resident_ctas<163>(smem, threads, out);
+        default: return v_resident_ctas<195>(smem, threads, out);
+    }
+}
 
-// 0 = plan made; 1 = this shape does not fit the cluster sweep; < 0 = error
+// Strip width: all CTAs of a team must be resident at once (they wait for each other's halo lines), so a team takes
+// csize SMs and floor(#SM / csize) frames are in flight.  The planner minimises rounds x groups-per-CTA, i.e. the
+// makespan of the launch in units of one 32-column group sweep.
+// 0 = plan made; 1 = this shape does not fit the sweep; < 0 = error
 static int plan_v(const TL &t, int n, VPlan *plan)
 {
-    int dev = 0, smem_optin = 0;
+    // one-entry cache: the pipeline asks twice per call with the same shape
+    static thread_local struct { int W, H, D, n, dev, strip, teams; VPlan p; bool ok; } memo = {0, 0, 0, 0, -1, 0, 0, {}, false};
+    int dev = 0, smem_optin = 0, coop = 0;
     VPP_CUDA_TRY(cudaGetDevice(&dev));
+    if (memo.ok && memo.W == t.W && memo.H == t.H && memo.D == t.D && memo.n == n && memo.dev == dev && memo.strip == g_max_strip &&
+        memo.teams == g_force_teams) {
+        *plan = memo.p;
+        return VPPB200_OK;
+    }
     VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    VPP_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return 1;
     int gc_max = 0;
     for (int gc = 6; gc >= 1; gc--)
         if (v_smem_bytes(gc * 32 + 3, t.K2) <= (size_t)smem_optin) { gc_max = gc; break; }
     if (g_max_strip > 0) gc_max = std::min(gc_max, std::max(1, g_max_strip / 32));
     if (gc_max < 1) return 1;
-    int csize = 1;
-    while (csize * gc_max < t.G && csize < 16) csize *= 2;
-    if (csize * gc_max < t.G) return 1;
-    VPlan p;
-    p.csize = csize;
-    p.GC = (t.G + csize - 1) / csize;
-    if ((csize - 1) * p.GC >= t.G) return 1;        // an empty strip
-    p.NS = p.GC * 32 + 3;
-    p.smem = v_smem_bytes(p.NS, t.K2);
-    p.nclusters = 1;
-    int mc = 0, rc;
-    switch (p.GC) {
-        case 1: rc = v_max_clusters<35>(p, &mc); break;
-        case 2: rc = v_max_clusters<67>(p, &mc); break;
-        case 3: rc = v_max_clusters<99>(p, &mc); break;
-        case 4: rc = v_max_clusters<131>(p, &mc); break;
-        case 5: rc = v_max_clusters<163>(p, &mc); break;
-        default: rc = v_max_clusters<195>(p, &mc); break;
+    long best_cost = -1;
+    VPlan best{};
+    for (int gc = gc_max; gc >= 1; gc--) {
+        VPlan p;
+        p.GC = gc;
+        p.csize = (t.G + gc - 1) / gc;
+        p.NS = gc * 32 + 3;
+        p.smem = v_smem_bytes(p.NS, t.K2);
+        int resident = 0;
+        int rc = v_resident(gc, p.smem, &resident);
+        if (rc) return rc;
+        int teams = resident / p.csize;
+        if (teams < 1) continue;
+        if (g_force_teams > 0) teams = std::min(teams, g_force_teams);
+        p.nteams = std::min(teams, n);
+        const long rounds = (n + p.nteams - 1) / p.nteams;
+        // time of one round ~ max(1.6, 0.41 * gc) ms at K (measured on B200, tools/exp_clusters.py): below 4 groups the
+        // SM is latency bound (too few warps), above it the round time grows with the strip width
+        const long cost = rounds * std::max(160, 41 * gc);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = p; }
+        if (g_max_strip > 0) break;                 // forced strip width: take it as is
     }
-    if (rc) return rc;
-    if (mc < 1) return 1;
-    if (g_force_clusters > 0) mc = g_force_clusters;
-    p.nclusters = n < mc ? n : mc;
-    *plan = p;
+    if (best_cost < 0) return 1;
+    *plan = best;
+    memo = {t.W, t.H, t.D, n, dev, g_max_strip, g_force_teams, best, true};
     return VPPB200_OK;
 }
 
 template <int NS>
-static int run_v_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int pass, int n, const VPlan &p,
-                   cudaStream_t st)
+static int run_v_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, uint32_t *halo, const TL &t, int pass, int n,
+                   const VPlan &p, cudaStream_t st)
 {
     VArgs a;
     a.t = t; a.n = n; a.pass = pass; a.csize = p.csize; a.GC = p.GC;
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[1];
-    // FULL: K2 splits into VPARTS equal thirds of whole VU-blocks
+    // FULL: K2 splits into VPARTS equal shares of whole VU-blocks
     const bool full = t.K2 % (VPARTS * VU) == 0;
-    int rc = full ? v_config<NS, true>(&cfg, attr, p, st) : v_config<NS, false>(&cfg, attr, p, st);
-    if (rc) return rc;
-    if (full) VPP_CUDA_TRY(cudaLaunchKernelEx(&cfg, sgm_v_kernel<NS, true>, img, cost, S, a));
-    else VPP_CUDA_TRY(cudaLaunchKernelEx(&cfg, sgm_v_kernel<NS, false>, img, cost, S, a));
+    void *args[] = {(void *)&img, (void *)&cost, (void *)&S, (void *)&halo, (void *)&a};
+    const void *kern = full ? (const void *)sgm_v_kernel<NS, true> : (const void *)sgm_v_kernel<NS, false>;
+    VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    // cooperative launch: all CTAs resident (they poll each other's halo words), one grid sync at the start
+    VPP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(p.csize * p.nteams)), dim3((unsigned)(p.GC * VPARTS * 32)), args,
+                                             p.smem, st));
     note_launch();
     return VPPB200_OK;
 }
 
-static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int pass, int n, const VPlan &p,
-                 cudaStream_t st)
+static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, uint32_t *halo, const TL &t, int pass, int n,
+                 const VPlan &p, cudaStream_t st)
 {
     switch (p.GC) {
-        case 1: return run_v_t<35>(img, cost, S, t, pass, n, p, st);
-        case 2: return run_v_t<67>(img, cost, S, t, pass, n, p, st);
-        case 3: return run_v_t<99>(img, cost, S, t, pass, n, p, st);
-        case 4: return run_v_t<131>(img, cost, S, t, pass, n, p, st);
-        case 5: return run_v_t<163>(img, cost, S, t, pass, n, p, st);
-        default: return run_v_t<195>(img, cost, S, t, pass, n, p, st);
+        case 1: return run_v_t<35>(img, cost, S, halo, t, pass, n, p, st);
+        case 2: return run_v_t<67>(img, cost, S, halo, t, pass, n, p, st);
+        case 3: return run_v_t<99>(img, cost, S, halo, t, pass, n, p, st);
+        case 4: return run_v_t<131>(img, cost, S, halo, t, pass, n, p, st);
+        case 5: return run_v_t<163>(img, cost, S, halo, t, pass, n, p, st);
+        default: return run_v_t<195>(img, cost, S, halo, t, pass, n, p, st);
     }
 }
+
+// bytes of the inbound halo buffers of the largest possible grid (one CTA per SM, generously 1024 SMs)
+size_t sweep_halo_bytes(int D) { return (size_t)1024 * 2 * 2 * (D / 2 + VPARTS) * 4; }
 
 // does the cluster sweep cover this shape on the current device?  (strip state must fit one cluster's shared memory)
 static int g_sweep_off = 0;
@@ -929,8 +922,8 @@ bool aggregate_tile_supported(int W, int H, int D, int n)
 // 0 = done; 1 = this shape does not fit the cluster sweep (caller uses sgm.cu); < 0 = error.
 // dl != NULL: the last sweep is fused with the winner-takes-all step (left + sub-pixel into dl, right into dr) and the
 // final S is never written; dl == NULL: S holds the aggregated volume in layout T.
-int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, int W, int H, int D, int n, float *dl,
-                          float *dr, const float *lut, const StageHook *hook, cudaStream_t st)
+int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, void *halo_ws, int W, int H, int D, int n,
+                          float *dl, float *dr, const float *lut, const StageHook *hook, cudaStream_t st)
 {
     const TL t = make_tl(W, H, D);
     VPlan plan;
@@ -941,9 +934,10 @@ int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S1
     auto done = [&](int stage) { if (hook) hook->fn(hook->ctx, stage); };
     if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, st))) return rc;
     done(VPPB200_STAGE_SGM_H_FWD);
-    if ((rc = run_v(img, cost, S, t, 0, n, plan, st))) return rc;
+    uint32_t *halo = static_cast<uint32_t *>(halo_ws);
+    if ((rc = run_v(img, cost, S, halo, t, 0, n, plan, st))) return rc;
     done(VPPB200_STAGE_SGM_V_DOWN);
-    if ((rc = run_v(img, cost, S, t, 1, n, plan, st))) return rc;
+    if ((rc = run_v(img, cost, S, halo, t, 1, n, plan, st))) return rc;
     done(VPPB200_STAGE_SGM_V_UP);
     if ((rc = run_h(img, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, st))) return rc;
     done(VPPB200_STAGE_SGM_H_BWD);
