@@ -77,14 +77,14 @@ int vppb200_stage_timing(int enable);
 int vppb200_stage_times(float *ms_out, int *calls_out);
 
 /* Tuning / test hooks (process-wide, not part of the reference's interface).  compute_rsgm aggregates with the
- * cluster sweep of csrc/sgm_sweep.cu when the frame's strip state fits one cluster's shared memory and with the
- * per-path kernels of csrc/sgm.cu otherwise; results are identical.
- *   VPPB200_TUNE_SGM_MAX_STRIP: upper bound on columns per CTA strip (0 = as wide as shared memory allows); small
- *                               values force multi-CTA clusters on small frames (parity tests of the halo exchange)
+ * four sweeps of csrc/sgm_sweep.cu when a team of resident CTAs can hold the frame's path state in shared memory and
+ * with the per-path kernels of csrc/sgm.cu otherwise; results are identical.
+ *   VPPB200_TUNE_SGM_MAX_STRIP: upper bound on columns per CTA strip (0 = chosen by the planner); small values force
+ *                               many-CTA teams on small frames (parity tests of the halo exchange)
  *   VPPB200_TUNE_SGM_SWEEP:     0 = always use the per-path kernels, 1 = default */
 #define VPPB200_TUNE_SGM_MAX_STRIP 0
 #define VPPB200_TUNE_SGM_SWEEP 1
-#define VPPB200_TUNE_SGM_CLUSTERS 2   /* clusters launched by the v-sweep (0 = occupancy estimate); experiments only */
+#define VPPB200_TUNE_SGM_CLUSTERS 2   /* upper bound on frames in flight in the v-sweep (0 = all SMs); experiments only */
 int vppb200_set_tuning(int key, int value);
 
 /* ---- pyrSGM operators ----------------------------------------------------------------------------------- */

@@ -92,6 +92,34 @@ struct StageMarks {
     static void hook(void *ctx, int stage) { static_cast<StageMarks *>(ctx)->done(stage); }
 };
 
+// ---- a side stream per device: the left and the right image branches of compute_rsgm (pad/gray/census before the
+// cost volume, median/interpolation after WTA) are independent and individually too small to fill the GPU, so the right
+// branch is forked onto the side stream and joined back with events (works under stream capture as well).
+static std::mutex g_side_mutex;
+static cudaStream_t g_side[64] = {nullptr};
+static cudaStream_t side_stream()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    if (!g_side[dev] && cudaStreamCreateWithFlags(&g_side[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        g_side[dev] = nullptr;
+    }
+    return g_side[dev];
+}
+// make `to` wait for everything queued on `from` so far
+static int stream_chain(cudaStream_t from, cudaStream_t to)
+{
+    cudaEvent_t e;
+    VPP_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t r = cudaEventRecord(e, from);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent(to, e, 0);
+    cudaEventDestroy(e);                                  // released once the event has completed
+    if (r != cudaSuccess) return cuda_fail("stream_chain", r);
+    return VPPB200_OK;
+}
+
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct RsgmWs {
@@ -329,12 +357,16 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
     StageMarks tm;
     tm.begin(st);
     // rsgm.py:258-262  pad (BORDER_REFLECT) + RGB2GRAY; the P2 guide is the raw byte stream of the padded `left`
+    cudaStream_t side = side_stream();
+    if (!side) side = st;                                    // no side stream: everything in order on the caller's stream
+    if (side != st && (rc = stream_chain(st, side))) return rc;
+    if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, side))) return rc;
+    if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, side))) return rc;
     if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, n, st))) return rc;
-    if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, st))) return rc;
     if ((rc = launch_pad_flatbytes(left, w.guide, d, n, st))) return rc;
     tm.done(VPPB200_STAGE_PAD_GRAY);
     if ((rc = launch_census(w.gray_l, w.census_l, d.Wp, d.Hp, n, st))) return rc;
-    if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, st))) return rc;
+    if (side != st && (rc = stream_chain(side, st))) return rc;
     tm.done(VPPB200_STAGE_CENSUS);
     // rsgm.py:263-268  Hamming volume (+ optional guided modulation); rsgm.py:270  8-path aggregation (effective default
     // parameters); rsgm.py:272-273  WTA left (+ equiangular sub-pixel) and right
@@ -366,10 +398,12 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
         if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
     }
     tm.done(VPPB200_STAGE_WTA);
+    if (side != st && (rc = stream_chain(st, side))) return rc;
+    if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, side))) return rc;
+    if ((rc = launch_interp_clip(w.drf, d.Wp, d.Hp, n, side))) return rc;
     if ((rc = launch_median(w.dl, w.dlf, d.Wp, d.Hp, n, st))) return rc;
-    if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, st))) return rc;
     if ((rc = launch_interp_clip(w.dlf, d.Wp, d.Hp, n, st))) return rc;
-    if ((rc = launch_interp_clip(w.drf, d.Wp, d.Hp, n, st))) return rc;
+    if (side != st && (rc = stream_chain(side, st))) return rc;
     tm.done(VPPB200_STAGE_MEDIAN_INTERP);
     // rsgm.py:275-292  crop, LR check, speckle filter, sub-pixel restore, background fill
     if ((rc = launch_tail(w.dlf, w.drf, disp_out, d, flags & 1, w.tail, n, st))) return rc;

@@ -9,14 +9,15 @@
 //   v-sweep up   : r1+r2+r3 of pass 1 together, S += L1+L2+L3                                      (one RMW)
 //   h-sweep bwd  : r0 of pass 1, S += L
 //
-// v-sweep (the heavy one: 6 of the 8 paths).  A thread-block CLUSTER owns one frame; CTA c owns a strip of 32-column
-// groups and keeps the three paths' previous-row values L_r(x, d) of its strip in shared memory (~188 KB at D = 192 /
-// 160 columns).  LANE = COLUMN: a warp owns 32 adjacent columns x one third of the disparity range and walks the
-// disparities sequentially, so L[d-1], L[d], L[d+1] are a register window, min_d is a running minimum, P2 is per lane --
-// no shuffles, no warp reductions, ~30 instructions per (32 pixels x 2 disparities x 3 paths).
-// Diagonal state is stored per LINE (ring slot = (column -/+ row) mod strip) so a line's state never moves; only the
-// line that leaves the strip is pushed into the neighbour CTA's halo slot through distributed shared memory, one
-// cluster barrier per row.  Lines that enter through the image border read a constant "border slot".
+// v-sweep (the heavy one: 6 of the 8 paths).  A TEAM of CTAs (one per SM, all resident: cooperative launch) owns one frame;
+// CTA c owns a strip of 32-column groups and keeps the three paths' previous-row values L_r(x, d) of its strip in shared
+// memory (~188 KB at D = 192 / 160 columns); floor(#SM / team) frames are in flight (18 at K).  LANE = COLUMN: a warp owns
+// 32 adjacent columns x one third of the disparity range and walks the disparities sequentially, so L[d-1], L[d], L[d+1]
+// are a register window, min_d is a running minimum, P2 is per lane -- no shuffles, no warp reductions, ~28 instructions
+// per (32 pixels x 2 disparities x 3 paths).  Diagonal state is stored per LINE (ring slot = (column -/+ row) mod strip) so
+// a line's state never moves; only the line that leaves the strip is handed to the neighbour CTA, through self-validating
+// words in global memory (4 tag bits per word, polled: no fence, no barrier between CTAs); one __syncthreads per row.
+// Lines that enter through the image border read a constant "border slot".
 //
 // Arithmetic: the "fast" domain of sgm.cu -- uint8 costs, the effective default parameters (P1=7, P2min=17,
 // Alpha=0.25, Gamma=50 => P2 in [17,50]), so no uint16 saturation is reachable (L <= 255+50, S <= 8*305); packed
@@ -453,13 +454,13 @@ static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// v-sweep: paths r1, r2, r3 of one pass, cluster per frame, lane = column, state in (distributed) shared memory
+// v-sweep: paths r1, r2, r3 of one pass, a team of CTAs per frame, lane = column, path state in shared memory
 // ------------------------------------------------------------------------------------------------------------
 struct VArgs {
     TL t;
     int n;
     int pass;          // 0: top-down (di = dj = +1), 1: bottom-up (di = dj = -1)
-    int csize;         // CTAs per cluster
+    int csize;         // CTAs per team (one frame)
     int GC;            // 32-column groups per CTA, ceil(G / csize)
 };
 
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int rank = (int)(blockIdx.x % a.csize);   // position of this CTA's strip in its team
-    const int cid = blockIdx.x / a.csize, nclusters = gridDim.x / a.csize;
+    const int cid = blockIdx.x / a.csize, nteams = gridDim.x / a.csize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = a.t.W, H = a.t.H, K2 = a.t.K2, G = a.t.G;
     constexpr int BIGS = NS - 3, HALO = NS - 2;
@@ -611,11 +612,11 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
     const long npx = (long)W * H;
     const int g = g_first + gl;
 
-    unsigned gstep = 0;                             // rows processed by this cluster so far (halo slot parity)
+    unsigned gstep = 0;                             // rows processed by this team so far (halo slot parity)
     uint32_t cb[VU], sb[VU];                        // first operand block of the next row (prefetched across the barrier)
 #pragma unroll
     for (int u = 0; u < VU; u++) { cb[u] = 0; sb[u] = 0; }
-    for (int f = cid; f < a.n; f += nclusters) {
+    for (int f = cid; f < a.n; f += nteams) {
         const uint8_t *img = img_all + f * npx;
         const uint16_t *cost_f = cost_all + f * a.t.frame + lane;
         uint32_t *S_f = S_all + f * a.t.frame + lane;
@@ -775,9 +776,9 @@ __global__ void __launch_bounds__(((NS - 3) / 32) * VPARTS * 32, 1) sgm_v_kernel
                     ipc = img[in * W + xr]; ip1 = img[q1]; ip2 = img[il * W + xr]; ip3 = img[q3];
                     const long tbn = (((long)in * G + g) * K2 + k0) * 32;
                     load_block(cost_f + tbn, S_f + tbn, k1 - k0, cb, sb, true);
-                } else if (f + nclusters < a.n) {
-                    // first row of this cluster's next frame
-                    const uint16_t *cost_n = cost_all + (long)(f + nclusters) * a.t.frame + lane;
+                } else if (f + nteams < a.n) {
+                    // first row of this team's next frame
+                    const uint16_t *cost_n = cost_all + (long)(f + nteams) * a.t.frame + lane;
                     load_block(cost_n + (((long)i1 * G + g) * K2 + k0) * 32, nullptr, k1 - k0, cb, sb, false);
                 }
             }
@@ -907,7 +908,7 @@ static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, uint32_t
 // bytes of the inbound halo buffers of the largest possible grid (one CTA per SM, generously 1024 SMs)
 size_t sweep_halo_bytes(int D) { return (size_t)1024 * 2 * 2 * (D / 2 + VPARTS) * 4; }
 
-// does the cluster sweep cover this shape on the current device?  (strip state must fit one cluster's shared memory)
+// does the sweep cover this shape on the current device?  (a team of resident CTAs must hold a frame's path state)
 static int g_sweep_off = 0;
 void sweep_set_enabled(int on) { g_sweep_off = !on; }
 bool aggregate_tile_supported(int W, int H, int D, int n)
@@ -919,7 +920,7 @@ bool aggregate_tile_supported(int W, int H, int D, int n)
     return plan_v(t, n, &plan) == VPPB200_OK;
 }
 
-// 0 = done; 1 = this shape does not fit the cluster sweep (caller uses sgm.cu); < 0 = error.
+// 0 = done; 1 = this shape does not fit the sweep (caller uses sgm.cu); < 0 = error.
 // dl != NULL: the last sweep is fused with the winner-takes-all step (left + sub-pixel into dl, right into dr) and the
 // final S is never written; dl == NULL: S holds the aggregated volume in layout T.
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, void *halo_ws, int W, int H, int D, int n,

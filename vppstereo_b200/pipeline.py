@@ -37,6 +37,11 @@ class VppRsgmPipeline:
             self.occ = torch.zeros((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
             self.lv = torch.empty((self.N, self.H, self.W, self.C), dtype=torch.uint8, device=self.device)
             self.rv = torch.empty_like(self.lv)
+            # two projected-image sets + VPP stream: see run_device
+            self.lv2, self.rv2 = [self.lv, torch.empty_like(self.lv)], [self.rv, torch.empty_like(self.lv)]
+            self.vpp_stream = torch.cuda.Stream(self.device)
+            self.vpp_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self.rsgm_done = [None, None]
             self.disp = torch.empty((self.N, self.H, self.W), dtype=torch.float32, device=self.device)
             # staging for run_host
             self.d_left = torch.empty_like(self.lv)
@@ -48,26 +53,46 @@ class VppRsgmPipeline:
     def workspace_bytes(self):
         return self.ws_rsgm.numel() + self.ws_vpp.numel()
 
-    def run_device(self, left, right, hints, out=None):
-        """VPP (in copies) + compute_rsgm; all operands CUDA tensors [N,H,W,C] uint8 / [N,H,W] float32."""
+    def run_device(self, left, right, hints, out=None, inputs_ready=None):
+        """VPP (in copies) + compute_rsgm; all operands CUDA tensors [N,H,W,C] uint8 / [N,H,W] float32.
+
+        VPP runs on the pipeline's own stream into one of two projected-image sets, compute_rsgm on the caller's current
+        stream: the projection of call k+1 overlaps the matcher of call k (VPP is latency bound and fits beside the SGM
+        sweeps).  `inputs_ready`: None = the inputs were produced on the current stream (VPP waits for everything queued
+        on it so far: no overlap); True = the inputs are complete; a torch.cuda.Event = wait for that event."""
         torch, L = self.torch, self.lib
         N = left.shape[0]
         assert N <= self.N and left.shape[1:] == (self.H, self.W, self.C)
         out = self.disp[:N] if out is None else out
-        st = _lib.stream_ptr(self.device)
-        lv, rv = self.lv[:N], self.rv[:N]
-        lv.copy_(left); rv.copy_(right)              # vpp() returns copies (vpp_standalone.py:397)
+        main = torch.cuda.current_stream(self.device)
+        side = self.vpp_stream
+        b = self.step & 1
+        lv, rv = self.lv2[b][:N], self.rv2[b][:N]
         self.step += 1
         seed = (self.seed * 0x9E3779B97F4A7C15 + self.step) & (2**64 - 1)
-        rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), self.W, self.H, self.C, 0, self.wsize,
-                                    self.direction, C.c_double(self.blending), C.c_double(self.c_occ), _lib.ptr(self.occ),
-                                    0, int(self.interpolate), 1, None, None, C.c_uint64(seed), None, _lib.ptr(self.ws_vpp),
-                                    C.c_size_t(self.ws_vpp.numel()), N, st)
-        _lib.check(rc, "vpp_scan_rnd")
+        if inputs_ready is None:
+            side.wait_stream(main)
+        elif inputs_ready is not True:
+            side.wait_event(inputs_ready)
+        if self.rsgm_done[b] is not None:
+            side.wait_event(self.rsgm_done[b])           # this set was last read by the matcher two calls ago
+        with torch.cuda.stream(side):
+            lv.copy_(left); rv.copy_(right)              # vpp() returns copies (vpp_standalone.py:397)
+            rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), self.W, self.H, self.C, 0, self.wsize,
+                                        self.direction, C.c_double(self.blending), C.c_double(self.c_occ), _lib.ptr(self.occ),
+                                        0, int(self.interpolate), 1, None, None, C.c_uint64(seed), None, _lib.ptr(self.ws_vpp),
+                                        C.c_size_t(self.ws_vpp.numel()), N, C.c_void_p(side.cuda_stream))
+            _lib.check(rc, "vpp_scan_rnd")
+            self.vpp_done[b].record(side)
+        main.wait_event(self.vpp_done[b])
         rc = L.vppb200_compute_rsgm(_lib.ptr(left), _lib.ptr(lv), _lib.ptr(rv), None, None, _lib.ptr(out), self.H, self.W,
                                     self.C, self.D, 1 if self.subpixel else 0, None, _lib.ptr(self.ws_rsgm),
-                                    C.c_size_t(self.ws_rsgm.numel()), N, st)
+                                    C.c_size_t(self.ws_rsgm.numel()), N, C.c_void_p(main.cuda_stream))
         _lib.check(rc, "compute_rsgm")
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.rsgm_done[b] = ev
+        self.lv, self.rv = self.lv2[b], self.rv2[b]     # the projected pair of the latest call
         return out
 
     def run_host(self, left, right, hints):
@@ -117,7 +142,7 @@ class VppRsgmPipeline:
                 st["hints"][:N].copy_(hints, non_blocking=True)
                 st["copied_in"].record(ss["h2d"])
             compute.wait_event(st["copied_in"])
-            self.run_device(st["left"][:N], st["right"][:N], st["hints"][:N], out=st["disp"][:N])
+            self.run_device(st["left"][:N], st["right"][:N], st["hints"][:N], out=st["disp"][:N], inputs_ready=st["copied_in"])
             st["computed"].record(compute)
             with torch.cuda.stream(ss["d2h"]):
                 ss["d2h"].wait_event(st["computed"])
