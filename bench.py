@@ -276,7 +276,7 @@ def main():
     import ctypes
     L.vppb200_stage_timing(1)
     for k in range(max(3, min(args.steps, 5))):
-        pipe.run_device(left, right, hints)
+        pipe.run_device_serial(left, right, hints)
     sync_all()
     st_ms = (ctypes.c_float * len(STAGES))(); calls = ctypes.c_int(0)
     L.vppb200_stage_times(st_ms, ctypes.byref(calls))
@@ -353,7 +353,7 @@ def main():
             "config": {"workload": "configs[1]: KITTI-shape 1242x375x3 pairs, LiDAR-like 5% hints, VPP rnd 3x3 blending 0.4 + rSGM D=192, batch 64 per GPU",
                        "batch_per_gpu": B, "frames_per_step": world * B, "l2": "inputs per step (298 MB) and cost volumes (17.7 GB) exceed the 126 MB L2",
                        "collective": "all_gather of disparities per step" if world > 1 else "none",
-                       "overlap": "VPP of step k+1 runs on its own stream beside the matcher of step k; right-image branches on a side stream",
+                       "overlap": "three-phase software pipeline across steps on three streams: front(k+1) = VPP + pad/gray/census/cost volume, main(k) = SGM sweeps + WTA, tail(k-1) = median..fills; two buffer sets; right-image branches on side streams",
                        "stage_ms_per_step_serial": {k: round(v, 3) for k, v in stage_ms.items()}, "vpp_ms_per_step": round(vpp_ms, 3),
                        "rsgm_fps": B / (rsgm_ms * 1e-3), "vpp_pairs_per_s": B / (vpp_ms * 1e-3), "check_mean_disp": check_val},
             "roofline": {"bound": "hbm", "kernel": "sgm_v_kernel (v-sweep: paths r1+r2+r3 of one pass, 2 launches per step)",

@@ -127,6 +127,25 @@ int vppb200_compute_rsgm(const uint8_t *left, const uint8_t *left_vpp, const uin
                          int H, int W, int C, int D, int flags, const float *rcp_lut,
                          void *workspace, size_t workspace_bytes, int n, void *stream);
 
+/* The same pipeline in three phases, for callers that overlap neighbouring batches on different streams (the reference
+ * has no such interface: it is this library's pipelining of rsgm.py:250-294 across calls).
+ *   FRONT: pad + gray + census + Hamming volume (rsgm.py:254-268)   reads the images, writes buffer set `set`
+ *   MAIN : 8-path aggregation + WTA left/right (rsgm.py:270-273)    reads / writes buffer set `set`
+ *   TAIL : median, interpolation, crop, LR check, speckles, fills (rsgm.py:272-292)  reads set `set`, writes disp_out
+ * `phases` = any OR of the three, run in that order on `stream`; the workspace must hold `sets` (1..4) buffer sets
+ * (vppb200_rsgm_workspace_bytes_sets).  Ordering between calls on different streams is the caller's job (events);
+ * phases == 7 with sets == 1 is vppb200_compute_rsgm.  Image pointers may be NULL when FRONT is not requested, disp_out
+ * when TAIL is not; hints/validhints are read by FRONT only. */
+#define VPPB200_PHASE_FRONT 1
+#define VPPB200_PHASE_MAIN 2
+#define VPPB200_PHASE_TAIL 4
+size_t vppb200_rsgm_workspace_bytes_sets(int H, int W, int C, int D, int n, int sets);
+int vppb200_compute_rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp,
+                                const float *hints, const float *validhints, float *disp_out,
+                                int H, int W, int C, int D, int flags, const float *rcp_lut,
+                                void *workspace, size_t workspace_bytes, int n, void *stream,
+                                int phases, int sets, int set);
+
 /* Stage taps of the same pipeline for tests (any pointer may be NULL): padded census L/R u32 [n][Hp][Wp], aggregated
  * volume u16 [n][Hp][Wp][D], left/right disparities after median+interpolation+clip f32 [n][Hp][Wp].  Set before the
  * call, valid after the stream is synchronised. */

@@ -270,3 +270,43 @@ def test_pipeline_streaming_matches_synchronous(mods):
         assert_same(got[k], want[k], f"streamed batch {k}")
     with pytest.raises(RuntimeError):
         pipe.collect(0)
+
+
+def test_pipeline_phases_overlapped_match_serial_and_oracle(mods, orc):
+    """run_device queues front / main / tail of consecutive calls on three streams with two buffer sets; every call must
+    return what the in-order run_device_serial returns, and (pattern passed through the device generator, so VPP is checked
+    separately) compute_rsgm of the projected pair must equal the oracle's."""
+    import torch
+    from vppstereo_b200.pipeline import VppRsgmPipeline
+    synth = mods[2]
+    frames = [synth.make_pair(70 + f, shape=(72, 160), hints="lidar") for f in range(10)]
+    batches = []
+    for b in range(5):
+        fr = frames[2 * b:2 * b + 2]
+        batches.append(tuple(torch.from_numpy(np.stack([p[k] for p in fr])).cuda() for k in ("left", "right", "hints")))
+    serial = VppRsgmPipeline(72, 160, 3, batch=2, dmax=64, seed=9)
+    want, proj = [], []
+    for b in batches:
+        want.append(serial.run_device_serial(*b).clone())
+        proj.append((serial.lv.clone(), serial.rv.clone()))
+    pipe = VppRsgmPipeline(72, 160, 3, batch=2, dmax=64, seed=9)
+    outs = [torch.empty((2, 72, 160), dtype=torch.float32, device="cuda") for _ in batches]
+    for b, o in zip(batches, outs):                    # back to back: phases of neighbouring calls overlap
+        pipe.run_device(*b, out=o, inputs_ready=True)
+    torch.cuda.synchronize()
+    for k in range(5):
+        assert_same(outs[k].cpu().numpy(), want[k].cpu().numpy(), f"overlapped call {k}")
+    # default output buffer + in-order semantics on the caller's stream
+    got = [pipe.run_device(*b).clone() for b in batches[:3]]
+    torch.cuda.synchronize()
+    pipe2 = VppRsgmPipeline(72, 160, 3, batch=2, dmax=64, seed=9)
+    for k in range(5):
+        pipe2.run_device_serial(*batches[k])
+    for k in range(3):
+        w = pipe2.run_device_serial(*batches[k]).clone()
+        assert_same(got[k].cpu().numpy(), w.cpu().numpy(), f"in-order call {k}")
+    # the matcher half against the oracle on the projected pair of the last serial call
+    lv, rv = proj[-1]
+    for i in range(2):
+        ref = orc.compute_rsgm(batches[-1][0][i].cpu().numpy(), lv[i].cpu().numpy(), rv[i].cpu().numpy(), dmax=64)
+        assert_same(want[-1][i].cpu().numpy(), ref, f"serial call vs oracle, frame {i}")

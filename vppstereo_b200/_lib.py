@@ -22,6 +22,7 @@ SYMBOLS = [
     "vppb200_census5x5", "vppb200_cost_census5x5_xyd", "vppb200_aggregate", "vppb200_match_wta",
     "vppb200_match_wta_right", "vppb200_subpixel_refine", "vppb200_median3x3",
     "vppb200_rsgm_workspace_bytes", "vppb200_compute_rsgm", "vppb200_compute_rsgm_tapped",
+    "vppb200_rsgm_workspace_bytes_sets", "vppb200_compute_rsgm_phases",
     "vppb200_vpp_workspace_bytes", "vppb200_vpp_scan_rnd", "vppb200_vpp_scan_max_dist", "vppb200_gt_reshape",
     "vppb200_u8hwc_to_f32chw", "vppb200_set_tuning",
 ]
@@ -46,6 +47,7 @@ def lib():
         l.vppb200_launch_count.restype = C.c_uint64
         l.vppb200_rsgm_workspace_bytes.restype = C.c_size_t
         l.vppb200_vpp_workspace_bytes.restype = C.c_size_t
+        l.vppb200_rsgm_workspace_bytes_sets.restype = C.c_size_t
         _lib = l
     return _lib
 

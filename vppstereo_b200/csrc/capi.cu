@@ -96,17 +96,19 @@ struct StageMarks {
 // cost volume, median/interpolation after WTA) are independent and individually too small to fill the GPU, so the right
 // branch is forked onto the side stream and joined back with events (works under stream capture as well).
 static std::mutex g_side_mutex;
-static cudaStream_t g_side[64] = {nullptr};
-static cudaStream_t side_stream()
+static cudaStream_t g_side[2][64] = {{nullptr}, {nullptr}};
+// which: 0 = front phase (pad/gray/census of the right image), 1 = tail phase (median/interpolation of the right map);
+// two streams so that the front of batch k+1 and the tail of batch k do not serialise when they run concurrently
+static cudaStream_t side_stream(int which)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lock(g_side_mutex);
-    if (!g_side[dev] && cudaStreamCreateWithFlags(&g_side[dev], cudaStreamNonBlocking) != cudaSuccess) {
+    if (!g_side[which][dev] && cudaStreamCreateWithFlags(&g_side[which][dev], cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
-        g_side[dev] = nullptr;
+        g_side[which][dev] = nullptr;
     }
-    return g_side[dev];
+    return g_side[which][dev];
 }
 // make `to` wait for everything queued on `from` so far
 static int stream_chain(cudaStream_t from, cudaStream_t to)
@@ -132,21 +134,30 @@ struct RsgmWs {
     TailBufs tail;
 };
 
-static size_t rsgm_ws_layout(const RsgmDims &d, int n, void *base, RsgmWs *ws)
+// `sets` buffer sets of everything that crosses a phase boundary (front -> main: guide, cost volume; main -> tail: raw
+// left/right disparities), so that the phases of neighbouring batches can run concurrently on different streams; `set`
+// selects the one this call uses.  Everything else is private to one phase and exists once.
+static size_t rsgm_ws_layout(const RsgmDims &d, int n, int sets, int set, void *base, RsgmWs *ws)
 {
     size_t off = 0;
     char *b = (char *)base;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? b + o : (char *)nullptr; };
     const size_t np = (size_t)n * d.Hp * d.Wp, nc = (size_t)n * d.H * d.W;
     RsgmWs w;
-    w.gray_l = (uint8_t *)take(np); w.gray_r = (uint8_t *)take(np); w.guide = (uint8_t *)take(np);
+    w.gray_l = (uint8_t *)take(np); w.gray_r = (uint8_t *)take(np);
     w.census_l = (uint32_t *)take(np * 4); w.census_r = (uint32_t *)take(np * 4);
     const size_t tv = tile_volume_elems(d.Wp, d.Hp, d.D, n);  // layout T pads the width to 32-column groups
-    w.dsi = (uint8_t *)take(tv > np * d.D ? tv : np * d.D);
-    w.S = (uint16_t *)take((tv > np * d.D ? tv : np * d.D) * 2);
+    const size_t vol = tv > np * d.D ? tv : np * d.D;
+    w.guide = nullptr; w.dsi = nullptr; w.dl = nullptr; w.dr = nullptr;
+    for (int k = 0; k < sets; k++) {
+        uint8_t *guide = (uint8_t *)take(np), *dsi = (uint8_t *)take(vol);
+        float *dl = (float *)take(np * 4), *dr = (float *)take(np * 4);
+        if (k == set) { w.guide = guide; w.dsi = dsi; w.dl = dl; w.dr = dr; }
+    }
+    w.S = (uint16_t *)take(vol * 2);
     w.S_xyd = (uint16_t *)take(np * d.D * 2);                 // the reference's xyd order (WTA input, test tap)
     w.halo = (void *)take(sweep_halo_bytes(d.D));
-    w.dl = (float *)take(np * 4); w.dlf = (float *)take(np * 4); w.dr = (float *)take(np * 4); w.drf = (float *)take(np * 4);
+    w.dlf = (float *)take(np * 4); w.drf = (float *)take(np * 4);
     w.tail.u8 = (uint8_t *)take(nc); w.tail.label = (int *)take(nc * 4); w.tail.count = (int *)take(nc * 4);
     if (ws) *ws = w;
     return off;
@@ -333,81 +344,107 @@ extern "C" int vppb200_median3x3(const float *src, float *dst, int W, int H, int
 extern "C" size_t vppb200_rsgm_workspace_bytes(int H, int W, int C, int D, int n)
 {
     if (H <= 0 || W <= 0 || n <= 0 || D <= 0 || D % 8 || D > 256 || (C != 1 && C != 3)) return 0;
-    return rsgm_ws_layout(make_dims(H, W, C, D), n, nullptr, nullptr);
+    return rsgm_ws_layout(make_dims(H, W, C, D), n, 1, 0, nullptr, nullptr);
 }
 
-extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp,
-                                           const float *hints, const float *validhints, float *disp_out, int H, int W, int C,
-                                           int D, int flags, const float *rcp_lut, void *workspace, size_t workspace_bytes,
-                                           int n, void *stream, const vppb200_rsgm_taps *taps)
+extern "C" size_t vppb200_rsgm_workspace_bytes_sets(int H, int W, int C, int D, int n, int sets)
+{
+    if (H <= 0 || W <= 0 || n <= 0 || D <= 0 || D % 8 || D > 256 || (C != 1 && C != 3) || sets < 1 || sets > 4) return 0;
+    return rsgm_ws_layout(make_dims(H, W, C, D), n, sets, 0, nullptr, nullptr);
+}
+
+// The pipeline in three phases (bit mask `phases`): FRONT = pad/gray/census/cost volume (reads the images, writes the guide
+// and the cost volume of buffer set `set`), MAIN = 8-path aggregation + WTA (reads them, writes the raw disparities of the
+// set), TAIL = median/interpolation/LR check/speckles/fills (reads those, writes disp_out).  One call may run any subset
+// on `stream`; a caller that runs the phases of neighbouring batches on different streams orders them with events
+// (vppstereo_b200/pipeline.py).  workspace must have been sized for `sets` sets.
+static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp, const float *hints,
+                       const float *validhints, float *disp_out, int H, int W, int C, int D, int flags, const float *rcp_lut,
+                       void *workspace, size_t workspace_bytes, int n, void *stream, const vppb200_rsgm_taps *taps, int phases,
+                       int sets, int set)
 {
     if (H <= 0 || W <= 0 || n <= 0 || (C != 1 && C != 3)) return VPPB200_ERR_ARG;
     if (D <= 0 || D % 8 != 0 || D > 256) return VPPB200_ERR_DISP;      // models/rsgm/rsgm.py:31-35
-    if (!left || !left_vpp || !right_vpp || !disp_out) return VPPB200_ERR_ARG;
+    if (phases <= 0 || phases > 7 || sets < 1 || sets > 4 || set < 0 || set >= sets) return VPPB200_ERR_ARG;
+    const bool front = phases & VPPB200_PHASE_FRONT, mainp = phases & VPPB200_PHASE_MAIN, tail = phases & VPPB200_PHASE_TAIL;
+    if (front && (!left || !left_vpp || !right_vpp)) return VPPB200_ERR_ARG;
+    if (tail && !disp_out) return VPPB200_ERR_ARG;
     if ((hints == nullptr) != (validhints == nullptr)) return VPPB200_ERR_ARG;
+    if (taps && phases != 7) return VPPB200_ERR_ARG;
     const RsgmDims d = make_dims(H, W, C, D);
     if (d.Hp < 8) return VPPB200_ERR_ARG;
-    if (!workspace || workspace_bytes < rsgm_ws_layout(d, n, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    if (!workspace || workspace_bytes < rsgm_ws_layout(d, n, sets, 0, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     if (!rcp_lut) rcp_lut = device_rcp_lut(st);
     if (!rcp_lut) return cuda_fail("device_rcp_lut", cudaGetLastError());
     RsgmWs w;
-    rsgm_ws_layout(d, n, workspace, &w);
+    rsgm_ws_layout(d, n, sets, set, workspace, &w);
     int rc;
     StageMarks tm;
-    tm.begin(st);
-    // rsgm.py:258-262  pad (BORDER_REFLECT) + RGB2GRAY; the P2 guide is the raw byte stream of the padded `left`
-    cudaStream_t side = side_stream();
-    if (!side) side = st;                                    // no side stream: everything in order on the caller's stream
-    if (side != st && (rc = stream_chain(st, side))) return rc;
-    if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, side))) return rc;
-    if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, side))) return rc;
-    if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, n, st))) return rc;
-    if ((rc = launch_pad_flatbytes(left, w.guide, d, n, st))) return rc;
-    tm.done(VPPB200_STAGE_PAD_GRAY);
-    if ((rc = launch_census(w.gray_l, w.census_l, d.Wp, d.Hp, n, st))) return rc;
-    if (side != st && (rc = stream_chain(side, st))) return rc;
-    tm.done(VPPB200_STAGE_CENSUS);
-    // rsgm.py:263-268  Hamming volume (+ optional guided modulation); rsgm.py:270  8-path aggregation (effective default
-    // parameters); rsgm.py:272-273  WTA left (+ equiangular sub-pixel) and right
+    if (phases == 7) tm.begin(st);                           // per-stage timing covers whole-pipeline calls only
     const bool tiled = aggregate_tile_supported(d.Wp, d.Hp, D, n);
     const bool want_volume = taps && taps->dsi_agg;          // only the test tap needs the aggregated volume itself
     const uint16_t *S_final = w.S;
-    if (tiled) {
-        if ((rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
-        if (hints && (rc = launch_guided_tile(w.dsi, hints, validhints, d, n, st))) return rc;
-        tm.done(VPPB200_STAGE_COST);
-        const StageHook hook = {StageMarks::hook, &tm};
-        if (!want_volume) {
-            // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
-            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, &hook, st)))
-                return rc < 0 ? rc : VPPB200_ERR_ARG;
+    if (front) {
+        // rsgm.py:258-262  pad (BORDER_REFLECT) + RGB2GRAY; the P2 guide is the raw byte stream of the padded `left`
+        cudaStream_t side = side_stream(0);
+        if (!side) side = st;                                // no side stream: everything in order on the caller's stream
+        if (side != st && (rc = stream_chain(st, side))) return rc;
+        if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, side))) return rc;
+        if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, side))) return rc;
+        if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, n, st))) return rc;
+        if ((rc = launch_pad_flatbytes(left, w.guide, d, n, st))) return rc;
+        tm.done(VPPB200_STAGE_PAD_GRAY);
+        if ((rc = launch_census(w.gray_l, w.census_l, d.Wp, d.Hp, n, st))) return rc;
+        if (side != st && (rc = stream_chain(side, st))) return rc;
+        tm.done(VPPB200_STAGE_CENSUS);
+        // rsgm.py:263-268  Hamming volume (+ optional guided modulation)
+        if (tiled) {
+            if ((rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
+            if (hints && (rc = launch_guided_tile(w.dsi, hints, validhints, d, n, st))) return rc;
         } else {
-            if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, &hook, st)))
-                return rc < 0 ? rc : VPPB200_ERR_ARG;
-            if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
-            S_final = w.S_xyd;
+            if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
+            if (hints && (rc = launch_guided_u8(w.dsi, hints, validhints, d, n, st))) return rc;
+        }
+        tm.done(VPPB200_STAGE_COST);
+    }
+    if (mainp) {
+        // rsgm.py:270  8-path aggregation (effective default parameters); rsgm.py:272-273  WTA left (+ equiangular
+        // sub-pixel) and right
+        if (tiled) {
+            const StageHook hook = {StageMarks::hook, &tm};
+            if (!want_volume) {
+                // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, &hook, st)))
+                    return rc < 0 ? rc : VPPB200_ERR_ARG;
+            } else {
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, &hook, st)))
+                    return rc < 0 ? rc : VPPB200_ERR_ARG;
+                if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
+                S_final = w.S_xyd;
+                if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
+            }
+        } else {
+            if ((rc = launch_aggregate_fast(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc;
+            tm.done(VPPB200_STAGE_SGM_H_BWD);                // the per-path fallback is booked on the last sweep's slot
             if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
         }
-    } else {
-        if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
-        if (hints && (rc = launch_guided_u8(w.dsi, hints, validhints, d, n, st))) return rc;
-        tm.done(VPPB200_STAGE_COST);
-        if ((rc = launch_aggregate_fast(w.guide, w.dsi, w.S, d.Wp, d.Hp, D, n, st))) return rc;
-        tm.done(VPPB200_STAGE_SGM_H_BWD);                    // the per-path fallback is booked on the last sweep's slot
-        if ((rc = launch_wta_both_subpix(S_final, w.dl, w.dr, d.Wp, d.Hp, D, rcp_lut, 0, n, st))) return rc;
+        tm.done(VPPB200_STAGE_WTA);
     }
-    tm.done(VPPB200_STAGE_WTA);
-    if (side != st && (rc = stream_chain(st, side))) return rc;
-    if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, side))) return rc;
-    if ((rc = launch_interp_clip(w.drf, d.Wp, d.Hp, n, side))) return rc;
-    if ((rc = launch_median(w.dl, w.dlf, d.Wp, d.Hp, n, st))) return rc;
-    if ((rc = launch_interp_clip(w.dlf, d.Wp, d.Hp, n, st))) return rc;
-    if (side != st && (rc = stream_chain(side, st))) return rc;
-    tm.done(VPPB200_STAGE_MEDIAN_INTERP);
-    // rsgm.py:275-292  crop, LR check, speckle filter, sub-pixel restore, background fill
-    if ((rc = launch_tail(w.dlf, w.drf, disp_out, d, flags & 1, w.tail, n, st))) return rc;
-    tm.done(VPPB200_STAGE_TAIL);
+    if (tail) {
+        cudaStream_t side = side_stream(1);
+        if (!side) side = st;
+        if (side != st && (rc = stream_chain(st, side))) return rc;
+        if ((rc = launch_median(w.dr, w.drf, d.Wp, d.Hp, n, side))) return rc;
+        if ((rc = launch_interp_clip(w.drf, d.Wp, d.Hp, n, side))) return rc;
+        if ((rc = launch_median(w.dl, w.dlf, d.Wp, d.Hp, n, st))) return rc;
+        if ((rc = launch_interp_clip(w.dlf, d.Wp, d.Hp, n, st))) return rc;
+        if (side != st && (rc = stream_chain(side, st))) return rc;
+        tm.done(VPPB200_STAGE_MEDIAN_INTERP);
+        // rsgm.py:275-292  crop, LR check, speckle filter, sub-pixel restore, background fill
+        if ((rc = launch_tail(w.dlf, w.drf, disp_out, d, flags & 1, w.tail, n, st))) return rc;
+        tm.done(VPPB200_STAGE_TAIL);
+    }
     tm.end();
     if (taps) {
         const size_t np = (size_t)n * d.Hp * d.Wp;
@@ -420,12 +457,30 @@ extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *l
     return VPPB200_OK;
 }
 
+extern "C" int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp,
+                                           const float *hints, const float *validhints, float *disp_out, int H, int W, int C,
+                                           int D, int flags, const float *rcp_lut, void *workspace, size_t workspace_bytes,
+                                           int n, void *stream, const vppb200_rsgm_taps *taps)
+{
+    return rsgm_phases(left, left_vpp, right_vpp, hints, validhints, disp_out, H, W, C, D, flags, rcp_lut, workspace,
+                       workspace_bytes, n, stream, taps, 7, 1, 0);
+}
+
 extern "C" int vppb200_compute_rsgm(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp, const float *hints,
                                     const float *validhints, float *disp_out, int H, int W, int C, int D, int flags,
                                     const float *rcp_lut, void *workspace, size_t workspace_bytes, int n, void *stream)
 {
-    return vppb200_compute_rsgm_tapped(left, left_vpp, right_vpp, hints, validhints, disp_out, H, W, C, D, flags, rcp_lut,
-                                       workspace, workspace_bytes, n, stream, nullptr);
+    return rsgm_phases(left, left_vpp, right_vpp, hints, validhints, disp_out, H, W, C, D, flags, rcp_lut, workspace,
+                       workspace_bytes, n, stream, nullptr, 7, 1, 0);
+}
+
+extern "C" int vppb200_compute_rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp,
+                                           const float *hints, const float *validhints, float *disp_out, int H, int W, int C,
+                                           int D, int flags, const float *rcp_lut, void *workspace, size_t workspace_bytes,
+                                           int n, void *stream, int phases, int sets, int set)
+{
+    return rsgm_phases(left, left_vpp, right_vpp, hints, validhints, disp_out, H, W, C, D, flags, rcp_lut, workspace,
+                       workspace_bytes, n, stream, nullptr, phases, sets, set);
 }
 
 // ---- hand-off to the networks (test.py:179-197) -----------------------------------------------------------

@@ -5,6 +5,11 @@ batch of frames, with the images staying on the device between the two (test.py:
     disp = pipe.run_device(left_u8, right_u8, hints_f32)        # CUDA tensors in, CUDA float32 [N,H,W] out
     disp = pipe.run_host(left_pinned, right_pinned, hints_pinned)  # host tensors in, pinned host float32 out
 
+Three phases of neighbouring batches run concurrently on three internal streams (software pipeline across calls):
+  front(k+1) = VPP + pad/gray/census/cost volume   |   main(k) = 8-path SGM sweeps + WTA   |   tail(k-1) = median ... fills
+with two buffer sets for everything that crosses a phase boundary; the SGM sweeps alone keep the critical stream busy
+and the small, latency-bound front and tail kernels fill the idle issue slots beside them.
+
 run_host is the end-to-end path: host->device copies of the three inputs and the device->host copy of the disparities
 are part of the call.  submit_host / collect is the same path for streams of batches: the copies of batch k+1 and of
 batch k-1 ride their own CUDA streams while batch k computes (two staging sets, events between the streams).
@@ -30,8 +35,8 @@ class VppRsgmPipeline:
         L = _lib.lib()
         self.lib = L
         with torch.cuda.device(self.device):
-            self.ws_rsgm = torch.empty(L.vppb200_rsgm_workspace_bytes(self.H, self.W, self.C, self.D, self.N), dtype=torch.uint8,
-                                       device=self.device)
+            self.ws_rsgm = torch.empty(L.vppb200_rsgm_workspace_bytes_sets(self.H, self.W, self.C, self.D, self.N, 2),
+                                       dtype=torch.uint8, device=self.device)
             self.ws_vpp = torch.empty(L.vppb200_vpp_workspace_bytes(self.H, self.W, self.C, self.N), dtype=torch.uint8,
                                       device=self.device)
             self.occ = torch.zeros((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
@@ -39,9 +44,12 @@ class VppRsgmPipeline:
             self.rv = torch.empty_like(self.lv)
             # two projected-image sets + VPP stream: see run_device
             self.lv2, self.rv2 = [self.lv, torch.empty_like(self.lv)], [self.rv, torch.empty_like(self.lv)]
-            self.vpp_stream = torch.cuda.Stream(self.device)
-            self.vpp_done = [torch.cuda.Event(), torch.cuda.Event()]
-            self.rsgm_done = [None, None]
+            self.vpp_stream = torch.cuda.Stream(self.device)      # front phase: VPP + pad/gray/census/cost volume
+            self.main_stream = torch.cuda.Stream(self.device)     # SGM sweeps + WTA
+            self.tail_stream = torch.cuda.Stream(self.device)     # median ... background fill
+            self.front_done = [torch.cuda.Event(), torch.cuda.Event()]
+            self.main_done = [None, None]
+            self.tail_done = [None, None]
             self.disp = torch.empty((self.N, self.H, self.W), dtype=torch.float32, device=self.device)
             # staging for run_host
             self.d_left = torch.empty_like(self.lv)
@@ -53,46 +61,91 @@ class VppRsgmPipeline:
     def workspace_bytes(self):
         return self.ws_rsgm.numel() + self.ws_vpp.numel()
 
+    def _phase(self, phases, b, left, lv, rv, out, N, stream):
+        L = self.lib
+        rc = L.vppb200_compute_rsgm_phases(_lib.ptr(left), _lib.ptr(lv), _lib.ptr(rv), None, None, _lib.ptr(out), self.H, self.W,
+                                           self.C, self.D, 1 if self.subpixel else 0, None, _lib.ptr(self.ws_rsgm),
+                                           C.c_size_t(self.ws_rsgm.numel()), N, C.c_void_p(stream.cuda_stream), phases, 2, b)
+        _lib.check(rc, "compute_rsgm_phases")
+
     def run_device(self, left, right, hints, out=None, inputs_ready=None):
         """VPP (in copies) + compute_rsgm; all operands CUDA tensors [N,H,W,C] uint8 / [N,H,W] float32.
 
-        VPP runs on the pipeline's own stream into one of two projected-image sets, compute_rsgm on the caller's current
-        stream: the projection of call k+1 overlaps the matcher of call k (VPP is latency bound and fits beside the SGM
-        sweeps).  `inputs_ready`: None = the inputs were produced on the current stream (VPP waits for everything queued
-        on it so far: no overlap); True = the inputs are complete; a torch.cuda.Event = wait for that event."""
+        The work is queued on the pipeline's three streams (front / main / tail, see the module docstring) and the caller's
+        current stream is made to wait for the result, so `out` is valid in current-stream order like the output of any
+        kernel launch, while the phases of the NEXT call can already run beside this one's.
+        `inputs_ready`: None = the inputs were produced on the current stream (the front phase waits for everything queued
+        on it so far, which includes the previous result: no overlap between calls); True = the inputs are complete; a
+        torch.cuda.Event = wait for that event.  The inputs must stay untouched until the front phase has read them
+        (`self.front_done[k & 1]` of call k)."""
         torch, L = self.torch, self.lib
         N = left.shape[0]
         assert N <= self.N and left.shape[1:] == (self.H, self.W, self.C)
         out = self.disp[:N] if out is None else out
-        main = torch.cuda.current_stream(self.device)
-        side = self.vpp_stream
+        caller = torch.cuda.current_stream(self.device)
+        front, main, tail = self.vpp_stream, self.main_stream, self.tail_stream
         b = self.step & 1
         lv, rv = self.lv2[b][:N], self.rv2[b][:N]
         self.step += 1
         seed = (self.seed * 0x9E3779B97F4A7C15 + self.step) & (2**64 - 1)
+        # ---- front: VPP into projected-image set b, then the matcher's front phase into buffer set b
         if inputs_ready is None:
-            side.wait_stream(main)
+            front.wait_stream(caller)
         elif inputs_ready is not True:
-            side.wait_event(inputs_ready)
-        if self.rsgm_done[b] is not None:
-            side.wait_event(self.rsgm_done[b])           # this set was last read by the matcher two calls ago
-        with torch.cuda.stream(side):
+            front.wait_event(inputs_ready)
+        if self.main_done[b] is not None:
+            front.wait_event(self.main_done[b])          # set b (guide, cost volume) was last read by the sweeps two calls ago
+        with torch.cuda.stream(front):
             lv.copy_(left); rv.copy_(right)              # vpp() returns copies (vpp_standalone.py:397)
             rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), self.W, self.H, self.C, 0, self.wsize,
                                         self.direction, C.c_double(self.blending), C.c_double(self.c_occ), _lib.ptr(self.occ),
                                         0, int(self.interpolate), 1, None, None, C.c_uint64(seed), None, _lib.ptr(self.ws_vpp),
-                                        C.c_size_t(self.ws_vpp.numel()), N, C.c_void_p(side.cuda_stream))
+                                        C.c_size_t(self.ws_vpp.numel()), N, C.c_void_p(front.cuda_stream))
             _lib.check(rc, "vpp_scan_rnd")
-            self.vpp_done[b].record(side)
-        main.wait_event(self.vpp_done[b])
-        rc = L.vppb200_compute_rsgm(_lib.ptr(left), _lib.ptr(lv), _lib.ptr(rv), None, None, _lib.ptr(out), self.H, self.W,
-                                    self.C, self.D, 1 if self.subpixel else 0, None, _lib.ptr(self.ws_rsgm),
-                                    C.c_size_t(self.ws_rsgm.numel()), N, C.c_void_p(main.cuda_stream))
-        _lib.check(rc, "compute_rsgm")
-        ev = torch.cuda.Event()
-        ev.record(main)
-        self.rsgm_done[b] = ev
+            self._phase(1, b, left, lv, rv, out, N, front)
+            self.front_done[b].record(front)
+        # ---- main: the four SGM sweeps + WTA (the critical stream)
+        main.wait_event(self.front_done[b])
+        if self.tail_done[b] is not None:
+            main.wait_event(self.tail_done[b])           # raw disparities of set b were last read by the tail two calls ago
+        with torch.cuda.stream(main):
+            self._phase(2, b, left, lv, rv, out, N, main)
+            ev = torch.cuda.Event(); ev.record(main)
+            self.main_done[b] = ev
+        # ---- tail: everything after WTA; `out` may still be read by work the caller queued before this call
+        tail.wait_stream(caller)
+        tail.wait_event(self.main_done[b])
+        with torch.cuda.stream(tail):
+            self._phase(4, b, left, lv, rv, out, N, tail)
+            ev = torch.cuda.Event(); ev.record(tail)
+            self.tail_done[b] = ev
+        caller.wait_event(ev)
         self.lv, self.rv = self.lv2[b], self.rv2[b]     # the projected pair of the latest call
+        return out
+
+    def run_device_serial(self, left, right, hints, out=None):
+        """The same computation, everything in order on the current stream (no overlap between calls, no internal streams
+        except the right-image branches): what bench.py times stage by stage."""
+        torch, L = self.torch, self.lib
+        N = left.shape[0]
+        out = self.disp[:N] if out is None else out
+        st = torch.cuda.current_stream(self.device)
+        for s in (self.vpp_stream, self.main_stream, self.tail_stream):
+            st.wait_stream(s)
+        b = self.step & 1
+        lv, rv = self.lv2[b][:N], self.rv2[b][:N]
+        self.step += 1
+        seed = (self.seed * 0x9E3779B97F4A7C15 + self.step) & (2**64 - 1)
+        lv.copy_(left); rv.copy_(right)
+        rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), self.W, self.H, self.C, 0, self.wsize,
+                                    self.direction, C.c_double(self.blending), C.c_double(self.c_occ), _lib.ptr(self.occ),
+                                    0, int(self.interpolate), 1, None, None, C.c_uint64(seed), None, _lib.ptr(self.ws_vpp),
+                                    C.c_size_t(self.ws_vpp.numel()), N, C.c_void_p(st.cuda_stream))
+        _lib.check(rc, "vpp_scan_rnd")
+        self._phase(7, b, left, lv, rv, out, N, st)
+        for s in (self.vpp_stream, self.main_stream, self.tail_stream):
+            s.wait_stream(st)
+        self.lv, self.rv = self.lv2[b], self.rv2[b]
         return out
 
     def run_host(self, left, right, hints):
