@@ -402,8 +402,13 @@ int launch_median(const float *src, float *dst, int W, int H, int n, cudaStream_
 
 // ------------------------------------------------------------------------------------------------------------
 // _linear_interpolate(dmap, 15, 3) + np.clip(., 0, None)   (models/rsgm/rsgm.py:66-113,:148-151)
-// The scan is sequential and in place (filled pixels become anchors for later gaps): one warp owns one row, stages
-// it in shared memory, lane 0 runs the scan, the warp writes the clipped row back coalesced.
+// The reference scans a row left to right, in place: at a pixel <= 0 it looks for the nearest valid pixel within 7 on
+// either side and, if both exist and differ by < 3, rewrites the whole span between them with the line through them.
+// Closed form of that scan (exact): the span between two valid anchors is a maximal run of L invalid pixels; it is
+// filled iff L <= 13 and |nl - nr| < 3, by the FIRST pixel of the run that sees both anchors, the one at position
+// p = max(1, L - 6) (1-based): m = (nr - nl) / (L + 1), q = nl + m * p, value(j) = (float)(m * (j - p) + q) in float64.
+// The rewritten anchors round back to themselves in float32, runs never chain (their anchors are original pixels), so
+// every pixel is independent: one warp stages a row in shared memory, all lanes resolve their pixels, coalesced write.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) interp_clip_kernel(float *__restrict__ disp, int W, long total_rows)
 {
@@ -415,26 +420,28 @@ __global__ void __launch_bounds__(128) interp_clip_kernel(float *__restrict__ di
     float *g = disp + row * W;
     for (int x = lane; x < W; x += 32) r[x] = g[x];
     __syncwarp();
-    if (lane == 0) {
-        const int n = 7;
-        for (int x = 0; x < W; x++) {
-            if (r[x] <= 0) {
-                double nl = 0, nr = 0;
-                int nlx = 0, nrx = 0;
-                for (int xw = -1; xw >= -n; xw--)
-                    if (x + xw >= 0 && r[x + xw] > 0) { nl = r[x + xw]; nlx = xw; break; }
-                for (int xw = 1; xw <= n; xw++)
-                    if (x + xw < W && r[x + xw] > 0) { nr = r[x + xw]; nrx = xw; break; }
-                if (nl > 0 && nr > 0 && fabs(nl - nr) < 3.0) {
-                    const double m = __ddiv_rn(nr - nl, (double)(nrx - nlx));
-                    const double q = __dsub_rn(nl, __dmul_rn(m, (double)nlx));
-                    for (int xw = nlx; xw <= nrx; xw++) r[x + xw] = (float)__dadd_rn(__dmul_rn(m, (double)xw), q);
+    for (int x = lane; x < W; x += 32) {
+        float v = r[x];
+        if (v <= 0) {
+            int jl = 0, jr = 0;
+            for (int k = 1; k <= 13 && x - k >= 0; k++)
+                if (r[x - k] > 0) { jl = k; break; }
+            if (jl)
+                for (int k = 1; k <= 14 - jl && x + k < W; k++)
+                    if (r[x + k] > 0) { jr = k; break; }
+            if (jl && jr) {
+                const int L = jl + jr - 1;                       // run length (<= 13), this pixel is number jl in it
+                const double nl = r[x - jl], nr = r[x + jr];
+                if (fabs(nl - nr) < 3.0) {
+                    const int p = max(1, L - 6);
+                    const double m = __ddiv_rn(nr - nl, (double)(L + 1));
+                    const double q = __dsub_rn(nl, __dmul_rn(m, (double)(-p)));
+                    v = (float)__dadd_rn(__dmul_rn(m, (double)(jl - p)), q);
                 }
             }
         }
+        g[x] = fmaxf(v, 0.0f);
     }
-    __syncwarp();
-    for (int x = lane; x < W; x += 32) g[x] = fmaxf(r[x], 0.0f);
 }
 int launch_interp_clip(float *disp, int W, int H, int n, cudaStream_t st)
 {
@@ -586,40 +593,49 @@ __global__ void speckle_apply_kernel(const uint8_t *__restrict__ u8, const int *
     out[t] = v;
 }
 
-// _interpolate_background rows (rsgm.py:188-213): warp per row staged in smem, lane 0 scans
+// _interpolate_background rows (rsgm.py:188-213).  Closed form of the sequential scan (exact): an invalid run with valid
+// pixels on both sides takes the minimum of the two, a run that touches the left (right) border takes the first (last)
+// valid value of the row, a row without valid pixels stays as it is; fills only ever read ORIGINAL valid pixels.  One
+// warp per row staged in shared memory: nearest valid index to the left by a ballot scan over 32-pixel chunks, then the
+// same from the right while writing the result.
 __global__ void __launch_bounds__(128) bg_rows_kernel(float *__restrict__ img, int W, long total_rows)
 {
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (row >= total_rows) return;
-    float *r = smem + (size_t)warp * W;
+    float *r = smem + (size_t)warp * 2 * W;
+    int *pv = reinterpret_cast<int *>(r + W);        // index of the nearest valid pixel to the left (-1: none)
     float *g = img + row * W;
     for (int x = lane; x < W; x += 32) r[x] = g[x];
     __syncwarp();
-    if (lane == 0) {
-        int count = 0;
-        for (int u = 0; u < W; u++) {
-            if (r[u] > 0) {
-                if (count >= 1) {
-                    const int u1 = u - count, u2 = u - 1;
-                    if (u1 > 0 && u2 < W - 1) {
-                        const float dd = fminf(r[u1 - 1], r[u2 + 1]);
-                        for (int c = u1; c <= u2; c++) r[c] = dd;
-                    }
-                }
-                count = 0;
-            } else {
-                count++;
-            }
-        }
-        for (int u = 0; u < W; u++)
-            if (r[u] > 0) { for (int u2 = 0; u2 < u; u2++) r[u2] = r[u]; break; }
-        for (int u = W - 1; u >= 0; u--)
-            if (r[u] > 0) { for (int u2 = u + 1; u2 < W; u2++) r[u2] = r[u]; break; }
+    int carry = -1;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const bool valid = x < W && r[x] > 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
+        const unsigned lower = m & ((1u << lane) - 1u);
+        if (x < W) pv[x] = lower ? x0 + 31 - __clz(lower) : carry;
+        if (m) carry = x0 + 31 - __clz(m);
     }
     __syncwarp();
-    for (int x = lane; x < W; x += 32) g[x] = r[x];
+    carry = W;                                       // nearest valid pixel to the right (W: none)
+    for (int x0 = ((W - 1) / 32) * 32; x0 >= 0; x0 -= 32) {
+        const int x = x0 + lane;
+        const bool valid = x < W && r[x] > 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
+        if (x < W && !valid) {
+            const unsigned upper = lane == 31 ? 0u : (m >> (lane + 1)) << (lane + 1);
+            const int nv = upper ? x0 + __ffs(upper) - 1 : carry;
+            const int lv = pv[x];
+            float out = r[x];
+            if (lv >= 0 && nv < W) out = fminf(r[lv], r[nv]);
+            else if (lv >= 0) out = r[lv];
+            else if (nv < W) out = r[nv];
+            g[x] = out;
+        }
+        if (m) carry = x0 + __ffs(m) - 1;
+    }
 }
 // _interpolate_background columns (rsgm.py:215-227): thread per column (coalesced across the warp)
 __global__ void bg_cols_kernel(float *__restrict__ img, int W, int H, long total_cols)
@@ -654,7 +670,7 @@ int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d,
     VPP_LAUNCH_CHECK("speckle_apply_kernel");
     const long rows = (long)n * d.H;
     const int wpb = 4;
-    const size_t sm = (size_t)wpb * d.W * sizeof(float);
+    const size_t sm = (size_t)wpb * 2 * d.W * sizeof(float);
     if (sm > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(bg_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     bg_rows_kernel<<<cdiv(rows, wpb), wpb * 32, sm, st>>>(out, d.W, rows);
     VPP_LAUNCH_CHECK("bg_rows_kernel");

@@ -62,37 +62,78 @@ __device__ __forceinline__ int sw_adapt_p2(int ip, int ipr)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// cost volume in layout T: popc(L ^ R[x-d]) for d <= x on rows 2..H-3, 12 elsewhere (RSGM/StereoBMHelper.cpp:29-140).
-// One warp per tile, lane = column; padding columns (x >= W) hold 0.
+// cost volume in layout T: popc(L ^ R[x-d]) for d <= x on rows 2..H-3, 12 elsewhere (RSGM/StereoBMHelper.cpp:29-140);
+// padding columns (x >= W) hold 0.
+// One warp per tile (32 columns x K2 disparity pairs).  A thread owns 8 adjacent columns x one eighth of the pairs:
+// the 8 left codes stay in registers, the right codes are a 9-word register window that slides by two codes per pair
+// (2 loads per 16 costs), and a pair of disparities for 8 columns leaves as ONE 16-byte store (a 64-byte tile row is
+// written by 4 lanes).  POPC (16 lanes/clk/SM) is the floor of this kernel, not the 92 MB it writes per frame.
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return a | (b << 8) | (c << 16) | (d << 24);
+}
+
+template <bool CHECK>
+__device__ __forceinline__ void cost_pairs(const uint32_t (&L)[8], const uint32_t *__restrict__ rp, int x, int W, int k0, int k1,
+                                           uint4 *__restrict__ out)
+{
+    // w[j] = R[x - 2k - 1 + j]: hi cost (d = 2k+1) of column x+j uses w[j], lo cost (d = 2k) uses w[j+1]
+    auto rload = [&](int i) -> uint32_t { return (!CHECK || (i >= 0 && i < W)) ? rp[i] : 0u; };
+    uint32_t w[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) w[j] = rload(x - 2 * k0 - 1 + j);
+#pragma unroll 4
+    for (int k = k0; k < k1; k++) {
+        uint32_t c[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t lo = (uint32_t)__popc(L[j] ^ w[j + 1]), hi = (uint32_t)__popc(L[j] ^ w[j]);
+            if (CHECK) {
+                if (2 * k > x + j) lo = 12u;
+                if (2 * k + 1 > x + j) hi = 12u;
+            }
+            c[2 * j] = lo; c[2 * j + 1] = hi;
+        }
+        out[k * 4] = make_uint4(pack4(c[0], c[1], c[2], c[3]), pack4(c[4], c[5], c[6], c[7]), pack4(c[8], c[9], c[10], c[11]),
+                                pack4(c[12], c[13], c[14], c[15]));
+#pragma unroll
+        for (int j = 8; j >= 2; j--) w[j] = w[j - 2];
+        w[1] = rload(x - 2 * k - 2);
+        w[0] = rload(x - 2 * k - 3);
+    }
+}
+
 __global__ void __launch_bounds__(256) cost_tile_kernel(const uint32_t *__restrict__ cl, const uint32_t *__restrict__ cr,
                                                         uint16_t *__restrict__ cost, TL t, long total_tiles)
 {
     const long tile = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (tile >= total_tiles) return;
     const int lane = threadIdx.x & 31;
+    const int xq = lane & 3, kq = lane >> 2;
     const int g = (int)(tile % t.G);
     const long row = tile / t.G;                   // row over all frames
     const int y = (int)(row % t.H);
-    const int x = g * 32 + lane;
-    uint16_t *out = cost + tile * t.K2 * 32 + lane;
+    const int x = g * 32 + 8 * xq;
+    const int KB = (t.K2 + 7) / 8;
+    const int k0 = kq * KB, k1 = min(t.K2, k0 + KB);
+    uint4 *out = reinterpret_cast<uint4 *>(cost + tile * t.K2 * 32) + xq;      // pair k of my 8 columns: out[k * 4]
     if (x >= t.W) {
-        for (int k = 0; k < t.K2; k++) out[k * 32] = 0;
+        for (int k = k0; k < k1; k++) out[k * 4] = make_uint4(0, 0, 0, 0);
         return;
     }
     if (y < 2 || y >= t.H - 2) {
-        for (int k = 0; k < t.K2; k++) out[k * 32] = 0x0C0Cu;
+        for (int k = k0; k < k1; k++) out[k * 4] = make_uint4(0x0C0C0C0Cu, 0x0C0C0C0Cu, 0x0C0C0C0Cu, 0x0C0C0C0Cu);
         return;
     }
-    const uint32_t l = cl[row * t.W + x];
-    const uint32_t *rp = cr + row * t.W + x;
-#pragma unroll 4
-    for (int k = 0; k < t.K2; k++) {
-        const int dlo = 2 * k;
-        const uint32_t vlo = dlo > x ? 12u : (uint32_t)__popc(l ^ rp[-dlo]);
-        const uint32_t vhi = dlo + 1 > x ? 12u : (uint32_t)__popc(l ^ rp[-dlo - 1]);
-        out[k * 32] = (uint16_t)(vlo | (vhi << 8));
+    uint32_t L[8];
+    {
+        const uint4 a = *reinterpret_cast<const uint4 *>(cl + row * t.W + x), b = *reinterpret_cast<const uint4 *>(cl + row * t.W + x + 4);
+        L[0] = a.x; L[1] = a.y; L[2] = a.z; L[3] = a.w; L[4] = b.x; L[5] = b.y; L[6] = b.z; L[7] = b.w;
     }
+    const uint32_t *rp = cr + row * t.W;
+    if (g * 32 >= t.D + 2) cost_pairs<false>(L, rp, x, t.W, k0, k1, out);       // every d <= x and every read inside the row
+    else cost_pairs<true>(L, rp, x, t.W, k0, k1, out);
 }
 
 int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st)
