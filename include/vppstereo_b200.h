@@ -84,6 +84,7 @@ int vppb200_stage_times(float *ms_out, int *calls_out);
  *   VPPB200_TUNE_SGM_SWEEP:     0 = always use the per-path kernels, 1 = default */
 #define VPPB200_TUNE_SGM_MAX_STRIP 0
 #define VPPB200_TUNE_SGM_SWEEP 1
+#define VPPB200_TUNE_VPP_ROWS 3       /* 0 = VPP rnd by the ordered per-row replay only, 1 = per-pixel replay where possible (default) */
 #define VPPB200_TUNE_SGM_CLUSTERS 2   /* upper bound on frames in flight in the v-sweep (0 = all SMs); experiments only */
 int vppb200_set_tuning(int key, int value);
 

@@ -66,6 +66,7 @@ int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, 
 void sweep_set_max_strip(int cols);
 void sweep_set_enabled(int on);
 void sweep_set_clusters(int c);
+void vpp_set_rows_kernel(int on);
 int launch_wta_both_subpix(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int plane, int n,
                            cudaStream_t st);
 int launch_wta_left(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st);

@@ -113,14 +113,22 @@ __global__ void __launch_bounds__(256) census5x5_kernel(const uint8_t *__restric
     const bool any_body = (c0 + 3 >= lo) && (c0 <= hi);
     const bool tail_row = (row == H - 3) && (col >= W - 16);
     if (any_body || tail_row) {
+        // flat neighbours c0 + (dy-2)*W + (dx-2), dx = 0..7 (may wrap across row ends; outside the frame: 0), fetched as the
+        // three aligned words that cover them (c0, W and n are multiples of 4: a word is entirely inside or outside)
         uint8_t win[5][8];
 #pragma unroll
-        for (int dy = 0; dy < 5; dy++)
+        for (int dy = 0; dy < 5; dy++) {
+            const long a0 = c0 + (long)(dy - 2) * W - 4;
+            uint32_t wd[3];
 #pragma unroll
-            for (int dx = 0; dx < 8; dx++) {
-                long a = c0 + (long)(dy - 2) * W + (dx - 2);     // flat neighbour, may wrap across row ends
-                win[dy][dx] = (a >= 0 && a < n) ? img[a] : 0;
+            for (int i = 0; i < 3; i++) {
+                const long a = a0 + 4 * i;
+                wd[i] = (a >= 0 && a < n) ? *reinterpret_cast<const uint32_t *>(img + a) : 0u;
             }
+            win[dy][0] = (uint8_t)(wd[0] >> 16); win[dy][1] = (uint8_t)(wd[0] >> 24);
+            win[dy][2] = (uint8_t)wd[1]; win[dy][3] = (uint8_t)(wd[1] >> 8); win[dy][4] = (uint8_t)(wd[1] >> 16);
+            win[dy][5] = (uint8_t)(wd[1] >> 24); win[dy][6] = (uint8_t)wd[2]; win[dy][7] = (uint8_t)(wd[2] >> 8);
+        }
         uint32_t r[4];
 #pragma unroll
         for (int o = 0; o < 4; o++) {

@@ -31,6 +31,8 @@ struct VppWs {
     long long *draws;    // [n][H]   pattern draws per row and channel  (sum of in-image patch pixels)
     long long *hbase;    // [n][H]   exclusive prefix of cnt
     long long *dbase;    // [n][H]   exclusive prefix of draws
+    uint32_t *hpre;      // [n][H][W] per hint (parallel to hx): in-image patch pixels of the earlier hints of its row
+    uint8_t *rowflag;    // [n][H]   1 = this image row is left to the ordered-replay kernel (see vpp_rnd_rows_kernel)
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -45,7 +47,9 @@ static size_t vpp_ws_layout(int H, int W, int n, void *base, VppWs *ws)
     long long *draws = (long long *)take((size_t)n * H * 8);
     long long *hbase = (long long *)take((size_t)n * H * 8);
     long long *dbase = (long long *)take((size_t)n * H * 8);
-    if (ws) { ws->hx = hx; ws->cnt = cnt; ws->draws = draws; ws->hbase = hbase; ws->dbase = dbase; }
+    uint32_t *hpre = (uint32_t *)take((size_t)n * H * W * 4);
+    uint8_t *rowflag = (uint8_t *)take((size_t)n * H);
+    if (ws) { ws->hx = hx; ws->cnt = cnt; ws->draws = draws; ws->hbase = hbase; ws->dbase = dbase; ws->hpre = hpre; ws->rowflag = rowflag; }
     return off;
 }
 
@@ -67,28 +71,45 @@ __global__ void __launch_bounds__(128) vpp_compact_rows_kernel(const float *__re
         const int x = direction != 0 ? s : W - 1 - s;
         const bool hit = s < W && grow[x] > 0.0f;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) out[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)x;
-        int nx = hit ? (min(x + n_patch, W - 1) - max(x - n_patch, 0) + 1) : 0;
+        const int nx1 = hit ? (min(x + n_patch, W - 1) - max(x - n_patch, 0) + 1) : 0;
+        int incl = nx1;                                  // inclusive warp scan of the patch widths
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nx += __shfl_xor_sync(0xFFFFFFFFu, nx, o);
-        draws += (long long)nx * ny;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (hit) {
+            const int slot = count + __popc(m & ((1u << lane) - 1u));
+            out[slot] = (uint16_t)x;
+            ws.hpre[row * W + slot] = (uint32_t)(draws + (long long)(incl - nx1) * ny);
+        }
+        draws += (long long)__shfl_sync(0xFFFFFFFFu, incl, 31) * ny;
         count += __popc(m);
     }
     if (lane == 0) { ws.cnt[row] = count; ws.draws[row] = draws; }
 }
 
-// exclusive prefix over the rows of each frame (one thread per frame; H is a few thousand at most)
-__global__ void vpp_scan_rows_kernel(VppWs ws, int H, int n, int32_t *n_hints_out)
+// exclusive prefix over the rows of each frame: one warp per frame, 32 rows per step
+__global__ void __launch_bounds__(128) vpp_scan_rows_kernel(VppWs ws, int H, int n, int32_t *n_hints_out)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (f >= n) return;
+    const int lane = threadIdx.x & 31;
     long long hb = 0, db = 0;
-    for (int y = 0; y < H; y++) {
+    for (int y0 = 0; y0 < H; y0 += 32) {
+        const int y = y0 + lane;
         const long r = (long)f * H + y;
-        ws.hbase[r] = hb; ws.dbase[r] = db;
-        hb += ws.cnt[r]; db += ws.draws[r];
+        const long long c = y < H ? ws.cnt[r] : 0, d = y < H ? ws.draws[r] : 0;
+        long long ci = c, di = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long tc = __shfl_up_sync(0xFFFFFFFFu, ci, o), td = __shfl_up_sync(0xFFFFFFFFu, di, o);
+            if (lane >= o) { ci += tc; di += td; }
+        }
+        if (y < H) { ws.hbase[r] = hb + ci - c; ws.dbase[r] = db + di - d; }
+        hb += __shfl_sync(0xFFFFFFFFu, ci, 31); db += __shfl_sync(0xFFFFFFFFu, di, 31);
     }
-    if (n_hints_out) n_hints_out[f] = (int32_t)hb;
+    if (n_hints_out && lane == 0) n_hints_out[f] = (int32_t)hb;
 }
 
 // ---- the blend of one patch pixel (vpp_core_opt.pyx:104-124 / :315-335; vpp_standalone.py:342-363 / :206-226) -----
@@ -198,7 +219,7 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
                                                              const float *__restrict__ g, const uint8_t *__restrict__ g_occ,
                                                              const uint8_t *__restrict__ pattern,
                                                              const int64_t *__restrict__ pattern_offsets, uint64_t rng_seed,
-                                                             VppWs ws, VppArgs a, long total)
+                                                             VppWs ws, VppArgs a, long total, int only_flagged)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
@@ -206,6 +227,7 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
     const int yy = (int)((t / a.C) % a.H);
     const long f = t / ((long)a.C * a.H);
     const int W = a.W, H = a.H, n = a.n;
+    if (only_flagged && !ws.rowflag[f * H + yy]) return;        // this row was done by vpp_rnd_rows_kernel
     Splat s{a, l + ((f * H + yy) * W) * a.C + j, r + ((f * H + yy) * W) * a.C + j};
     const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
     const long long pat_len = pattern ? pattern_offsets[f + 1] - pattern_offsets[f] : 0;
@@ -239,6 +261,227 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
             draw_prefix += inb;
         }
     }
+}
+
+// ---- rnd: per-pixel replay, one CTA per (frame, image row yy) -------------------------------------------------
+// Finer than the per-row replay above and still exact: when no hint of the rows yy-n..yy+n is occluded-and-kept, every
+// blend reads only the pixel it writes, so the final value of a pixel is the fold, in scan order,
+// of the blends that target it.  The CTA (1) stages the hints of its 2n+1 source rows, (2) turns every (hint, xw) into
+// up to three write records -- left pixel x+xw, right pixels x-d0+xw and x-d1+xw -- and bins them by target pixel in
+// shared memory (count, exclusive scan, fill), (3) lets one thread per target pixel sort its few records by scan order
+// and replay them for all channels.  Thousands of independent pixels per row instead of one thread per row.
+// Rows it cannot take (an occluded hint that is not discarded: its left blend reads the right image; more hints or
+// records than the shared-memory bins hold; patches wider than 15) are flagged and left to vpp_rnd_replay_kernel.
+struct RowsCfg { int cap_rec, cap_hint; };
+static constexpr int VR_NT = 256;
+
+__device__ __forceinline__ uint8_t blend_plain(const VppArgs &a, double pv, uint8_t old)
+{
+    // tr8(colour + old * (1 - c)) with colour = pv * c in the reference's typing (splat_pixel: non-occluded left / right, rnd)
+    double rc, om;
+    if (a.arith == 0) { rc = (double)__fmul_rn((float)pv, a.c32); om = __dsub_rn(1.0, (double)a.c32); }
+    else { rc = __dmul_rn(pv, a.c64); om = __dsub_rn(1.0, a.c64); }
+    return tr8(__dadd_rn(rc, __dmul_rn((double)old, om)));
+}
+__device__ __forceinline__ uint8_t blend_r0(const VppArgs &a, double pv, uint8_t r0, float b32, double b64)
+{
+    double rc, om, rb;
+    const double b = a.arith == 0 ? (double)b32 : b64;
+    const double omb = __dsub_rn(1.0, b);
+    if (a.arith == 0) { rc = (double)__fmul_rn((float)pv, a.c32); om = __dsub_rn(1.0, (double)a.c32); rb = (double)__fmul_rn((float)r0, b32); }
+    else { rc = __dmul_rn(pv, a.c64); om = __dsub_rn(1.0, a.c64); rb = __dmul_rn((double)r0, b64); }
+    return tr8(__dadd_rn(__dmul_rn(__dadd_rn(rc, __dmul_rn((double)r0, om)), omb), rb));
+}
+__device__ __forceinline__ uint8_t blend_r1(const VppArgs &a, double pv, uint8_t r1, float b32, double b64)
+{
+    double rc, om;
+    const double b = a.arith == 0 ? (double)b32 : b64;
+    const double omb = __dsub_rn(1.0, b);
+    if (a.arith == 0) { rc = (double)__fmul_rn((float)pv, a.c32); om = __dsub_rn(1.0, (double)a.c32); }
+    else { rc = __dmul_rn(pv, a.c64); om = __dsub_rn(1.0, a.c64); }
+    return tr8(__dadd_rn(__dmul_rn(__dadd_rn(rc, __dmul_rn((double)r1, om)), b), __dmul_rn((double)r1, omb)));
+}
+
+// the write records of one (hint, xw): calls emit(target, type) with target in [0, W) = left pixel, [W, 2W) = right pixel;
+// type 0 / 1 = interpolated right blend at x0 / x1, 2 = plain blend
+template <typename F>
+__device__ __forceinline__ void vr_records(const VppArgs &a, int x, float gv, bool occ, int xw, F emit)
+{
+    const int W = a.W;
+    const HintGeom hg = hint_geom(a, gv, x);
+    const int x0 = hg.xd0 + xw, x1 = hg.xd1 + xw;
+    if (0 <= x0 && x0 <= W - 1) {
+        if (occ) return;                                   // occluded and discarded (kept ones never get here)
+        emit(x + xw, 2);
+        if (a.interpolate) {
+            emit(W + x0, 0);
+            if (0 <= x1 && x1 <= W - 1) emit(W + x1, 1);
+        } else {
+            const int xr = hg.xd + xw;
+            emit(W + (xr < 0 ? xr + W : xr), 2);
+        }
+    } else {
+        emit(x + xw, 2);                                   // left-side occlusion (pyx:123-124)
+    }
+}
+
+__global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict__ l, uint8_t *__restrict__ r,
+                                                             const float *__restrict__ g, const uint8_t *__restrict__ g_occ,
+                                                             const uint8_t *__restrict__ pattern,
+                                                             const int64_t *__restrict__ pattern_offsets, uint64_t rng_seed,
+                                                             VppWs ws, VppArgs a, RowsCfg cfg)
+{
+    extern __shared__ __align__(16) uint8_t vsm[];
+    const int W = a.W, H = a.H, n = a.n, C = a.C;
+    const int tid = threadIdx.x;
+    const long fr = blockIdx.x;                           // f * H + yy
+    const int yy = (int)(fr % H);
+    const long f = fr / H;
+    const int ylo_row = max(0, yy - n), yhi_row = min(H - 1, yy + n);
+    const int nrows = yhi_row - ylo_row + 1;
+    __shared__ int rowstart[17];
+    __shared__ long long rowdb[16], rowhb[16];
+    __shared__ int s_flag0, s_flag, s_flag2, s_total;      // one flag per decision point: no thread re-reads a flag others still set
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < nrows && i < 16; i++) {
+            const long row = f * H + ylo_row + i;
+            rowstart[i] = acc; acc += ws.cnt[row];
+            rowdb[i] = ws.dbase[row]; rowhb[i] = ws.hbase[row];
+        }
+        for (int i = min(nrows, 16); i < 17; i++) rowstart[i] = acc;
+        s_flag0 = (n > 7 || C > 4 || acc > cfg.cap_hint) ? 1 : 0;
+        s_flag = 0; s_flag2 = 0;
+        s_total = acc;
+    }
+    __syncthreads();
+    const int nh = s_total;
+    if (nh == 0 || s_flag0) {
+        if (tid == 0) ws.rowflag[fr] = (uint8_t)(nh != 0);
+        return;
+    }
+    // shared memory: offs[2W+1], cur[2W], keys[cap_rec], hint table (gv, row-relative prefix, x, flags)
+    uint32_t *offs = reinterpret_cast<uint32_t *>(vsm);
+    uint32_t *cur = offs + (2 * W + 1);
+    uint32_t *keys = cur + 2 * W;
+    float *hgv = reinterpret_cast<float *>(keys + cfg.cap_rec);
+    uint32_t *hpr = reinterpret_cast<uint32_t *>(hgv + cfg.cap_hint);
+    uint16_t *hxx = reinterpret_cast<uint16_t *>(hpr + cfg.cap_hint);
+    uint8_t *hfl = reinterpret_cast<uint8_t *>(hxx + cfg.cap_hint);        // bit 0: occluded, bits 1..4: source row index
+    for (int i = tid; i < 2 * W + 1; i += VR_NT) offs[i] = 0;
+    for (int h = tid; h < nh; h += VR_NT) {
+        int yr = 0;
+        while (yr + 1 < nrows && rowstart[yr + 1] <= h) yr++;
+        const long row = f * H + ylo_row + yr;
+        const int k = h - rowstart[yr];
+        const int x = ws.hx[row * W + k];
+        const bool occ = g_occ[row * W + x] != 0;
+        hxx[h] = (uint16_t)x; hgv[h] = g[row * W + x]; hpr[h] = ws.hpre[row * W + k];
+        hfl[h] = (uint8_t)((occ ? 1 : 0) | (yr << 1));
+        if (occ && !a.discard) s_flag = 1;               // its left blend reads the right image: ordered replay
+    }
+    __syncthreads();
+    if (s_flag) {
+        if (tid == 0) ws.rowflag[fr] = 1;
+        return;
+    }
+    // (2a) count the records per target
+    for (int h = tid; h < nh; h += VR_NT) {
+        const int x = hxx[h];
+        const bool occ = hfl[h] & 1;
+        for (int xw = max(-n, -x); xw <= min(n, W - 1 - x); xw++)
+            vr_records(a, x, hgv[h], occ, xw, [&](int target, int) { atomicAdd(&offs[target], 1u); });
+    }
+    __syncthreads();
+    // (2b) exclusive scan over the 2W targets: contiguous chunk per thread, block scan of the chunk sums
+    {
+        __shared__ uint32_t part[VR_NT];
+        const int per = (2 * W + VR_NT - 1) / VR_NT;
+        const int b0 = min(tid * per, 2 * W), b1 = min(b0 + per, 2 * W);
+        uint32_t sum = 0;
+        for (int i = b0; i < b1; i++) sum += offs[i];
+        part[tid] = sum;
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t run = 0;
+            for (int c0 = 0; c0 < VR_NT; c0 += 32) {
+                const uint32_t v = part[c0 + tid];
+                uint32_t incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                part[c0 + tid] = run + incl - v;
+                run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            if (tid == 0) { s_total = (int)run; if (run > (uint32_t)cfg.cap_rec) s_flag2 = 1; }
+        }
+        __syncthreads();
+        uint32_t acc = part[tid];
+        for (int i = b0; i < b1; i++) { const uint32_t c = offs[i]; offs[i] = acc; cur[i] = acc; acc += c; }
+        if (tid == VR_NT - 1) offs[2 * W] = (uint32_t)s_total;
+    }
+    __syncthreads();
+    if (s_flag2) {
+        if (tid == 0) ws.rowflag[fr] = 1;
+        return;
+    }
+    if (tid == 0) ws.rowflag[fr] = 0;
+    // (2c) fill: key = scan order of the record = (hint, xw, type)
+    for (int h = tid; h < nh; h += VR_NT) {
+        const int x = hxx[h];
+        const bool occ = hfl[h] & 1;
+        for (int xw = max(-n, -x); xw <= min(n, W - 1 - x); xw++)
+            vr_records(a, x, hgv[h], occ, xw, [&](int target, int type) {
+                keys[atomicAdd(&cur[target], 1u)] = ((uint32_t)h << 6) | ((uint32_t)(xw + n) << 2) | (uint32_t)type;
+            });
+    }
+    __syncthreads();
+    // (3) replay per target pixel
+    const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
+    const long long pat_len = pattern ? pattern_offsets[f + 1] - pattern_offsets[f] : 0;
+    const uint64_t frame_key = rng_seed ^ ((uint64_t)f * 0x9E3779B97F4A7C15ull);
+    for (int t = tid; t < 2 * W; t += VR_NT) {
+        const int k0 = (int)offs[t], k1 = (int)offs[t + 1];
+        if (k0 == k1) continue;
+        for (int i = k0 + 1; i < k1; i++) {                // insertion sort: the lists are a handful of records
+            const uint32_t key = keys[i];
+            int q = i - 1;
+            while (q >= k0 && keys[q] > key) { keys[q + 1] = keys[q]; q--; }
+            keys[q + 1] = key;
+        }
+        uint8_t *px = (t < W ? l + (fr * W + t) * C : r + (fr * W + (t - W)) * C);
+        uint8_t v[4];
+        for (int j = 0; j < C; j++) v[j] = px[j];
+        for (int i = k0; i < k1; i++) {
+            const uint32_t key = keys[i];
+            const int h = (int)(key >> 6), xw = (int)((key >> 2) & 15u) - n, type = (int)(key & 3u);
+            const int x = hxx[h], yr = hfl[h] >> 1;
+            const float gv = hgv[h];
+            const int y = ylo_row + yr;
+            const int ylo = max(y - n, 0), ny = min(y + n, H - 1) - ylo + 1;
+            const int xlo = max(x - n, 0), nx = min(x + n, W - 1) - xlo + 1;
+            const long long inb = (long long)nx * ny;
+            const int d0 = (int)floorf(gv);
+            const float b32 = __fsub_rn(gv, (float)d0);
+            const double b64 = __dsub_rn((double)gv, (double)d0);
+            long long idx = a.uniform ? (long long)C * (rowhb[yr] + (h - rowstart[yr]))
+                                      : (long long)C * (rowdb[yr] + hpr[h]) + (long long)(yy - ylo) * nx + (x + xw - xlo);
+            for (int j = 0; j < C; j++) {
+                const long long ij = a.uniform ? idx + j : idx + (long long)j * inb;
+                const uint8_t rv = pat ? ((ij >= 0 && ij < pat_len) ? pat[ij] : 0) : counter_pattern(frame_key, (uint64_t)ij);
+                const double pv = (double)rv;
+                v[j] = type == 2 ? blend_plain(a, pv, v[j]) : (type == 0 ? blend_r0(a, pv, v[j], b32, b64) : blend_r1(a, pv, v[j], b32, b64));
+            }
+        }
+        for (int j = 0; j < C; j++) px[j] = v[j];
+    }
+}
+
+static size_t vr_smem_bytes(int W, const RowsCfg &c)
+{
+    return (size_t)(4 * W + 1) * 4 + (size_t)c.cap_rec * 4 + (size_t)c.cap_hint * (4 + 4 + 2 + 1) + 16;
 }
 
 // ---- maxDistance: one warp per (frame, channel), sequential over hints ------------------------------------------
@@ -381,10 +624,13 @@ static int prepare_hints(const float *g, int W, int H, int n_patch, int directio
     const long rows = (long)n * H;
     vpp_compact_rows_kernel<<<cdiv(rows * 32, 128), 128, 0, st>>>(g, ws, W, H, n_patch, direction, rows);
     VPP_LAUNCH_CHECK("vpp_compact_rows_kernel");
-    vpp_scan_rows_kernel<<<cdiv(n, 64), 64, 0, st>>>(ws, H, n, n_hints_out);
+    vpp_scan_rows_kernel<<<cdiv((long)n * 32, 128), 128, 0, st>>>(ws, H, n, n_hints_out);
     VPP_LAUNCH_CHECK("vpp_scan_rows_kernel");
     return VPPB200_OK;
 }
+
+static int g_vpp_rows_on = 1;       // test hook: 0 = ordered per-row replay only
+void vpp_set_rows_kernel(int on) { g_vpp_rows_on = on != 0; }
 
 static VppArgs make_args(int W, int H, int C, int uniform, int wsize, int wax, int way, int direction, double c, double c_occ,
                          int discard, int interpolate, int arith)
@@ -422,8 +668,21 @@ extern "C" int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int 
     VppArgs a = make_args(W, H, C, uniform_color, wsize, 1, 1, direction, c, c_occ, discard_occluded, interpolate, arith);
     int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st);
     if (rc) return rc;
+    // per-pixel replay for every row it can take; the rows it flags go to the ordered per-row replay
+    const RowsCfg cfg{8192, 2048};
+    const size_t smem = vr_smem_bytes(W, cfg);
+    int dev = 0, smem_optin = 0;
+    VPP_CUDA_TRY(cudaGetDevice(&dev));
+    VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const bool rows_kernel = g_vpp_rows_on && smem <= (size_t)smem_optin && (long)n * H < (1L << 31);
+    if (rows_kernel) {
+        VPP_CUDA_TRY(cudaFuncSetAttribute(vpp_rnd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vpp_rnd_rows_kernel<<<(unsigned)((long)n * H), VR_NT, smem, st>>>(l, r, g, g_occ, pattern, pattern_offsets, rng_seed, ws, a, cfg);
+        VPP_LAUNCH_CHECK("vpp_rnd_rows_kernel");
+    }
     const long total = (long)n * H * C;
-    vpp_rnd_replay_kernel<<<cdiv(total, 128), 128, 0, st>>>(l, r, g, g_occ, pattern, pattern_offsets, rng_seed, ws, a, total);
+    vpp_rnd_replay_kernel<<<cdiv(total, 128), 128, 0, st>>>(l, r, g, g_occ, pattern, pattern_offsets, rng_seed, ws, a, total,
+                                                            rows_kernel ? 1 : 0);
     VPP_LAUNCH_CHECK("vpp_rnd_replay_kernel");
     return VPPB200_OK;
 }
