@@ -205,13 +205,20 @@ __device__ __forceinline__ HintGeom hint_geom(const VppArgs &a, float gv, int x)
     return h;
 }
 
-// on-device pattern generation (pattern == NULL): splitmix64 finaliser of (seed, frame, stream position)
-__device__ __forceinline__ uint8_t counter_pattern(uint64_t frame_key, uint64_t idx)
+// on-device pattern generation (pattern == NULL): counter based, value = 32-bit finaliser of (frame key, stream position
+// modulo 2^32)
+__device__ __forceinline__ uint32_t frame_key32(uint64_t rng_seed, long f)
 {
-    uint64_t z = frame_key + (idx + 1) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return (uint8_t)((z ^ (z >> 31)) >> 24);
+    const uint64_t k = rng_seed ^ ((uint64_t)f * 0x9E3779B97F4A7C15ull);
+    return (uint32_t)k ^ ((uint32_t)(k >> 32) * 0x85EBCA6Bu);
+}
+__device__ __forceinline__ uint8_t counter_pattern(uint32_t key, uint32_t idx)
+{
+    uint32_t h = (idx * 0x9E3779B1u) ^ key;
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return (uint8_t)(h >> 24);
 }
 
 // ---- rnd: ordered replay, one thread per (frame, row yy, channel j) ------------------------------------------
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
     Splat s{a, l + ((f * H + yy) * W) * a.C + j, r + ((f * H + yy) * W) * a.C + j};
     const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
     const long long pat_len = pattern ? pattern_offsets[f + 1] - pattern_offsets[f] : 0;
-    const uint64_t frame_key = rng_seed ^ ((uint64_t)f * 0x9E3779B97F4A7C15ull);
+    const uint32_t frame_key = frame_key32(rng_seed, f);
     for (int y = max(0, yy - n); y <= min(H - 1, yy + n); y++) {
         const long row = f * H + y;
         const int cnt = ws.cnt[row];
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
                                       : (long long)a.C * draw_prefix + (long long)j * inb + (long long)rows_before * nx;
             for (int xx = xlo; xx <= xhi; xx++) {
                 const int xw = xx - x;
-                const uint8_t rv = pat ? ((idx >= 0 && idx < pat_len) ? pat[idx] : 0) : counter_pattern(frame_key, (uint64_t)idx);
+                const uint8_t rv = pat ? ((idx >= 0 && idx < pat_len) ? pat[idx] : 0) : counter_pattern(frame_key, (uint32_t)idx);
                 if (!a.uniform) idx++;
                 splat_pixel<true>(s, (double)rv, xx, hg.xd0 + xw, hg.xd1 + xw, hg.xd + xw, occ, hg.b32, hg.b64);
             }
@@ -274,33 +281,6 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
 // records than the shared-memory bins hold; patches wider than 15) are flagged and left to vpp_rnd_replay_kernel.
 struct RowsCfg { int cap_rec, cap_hint; };
 static constexpr int VR_NT = 256;
-
-__device__ __forceinline__ uint8_t blend_plain(const VppArgs &a, double pv, uint8_t old)
-{
-    // tr8(colour + old * (1 - c)) with colour = pv * c in the reference's typing (splat_pixel: non-occluded left / right, rnd)
-    double rc, om;
-    if (a.arith == 0) { rc = (double)__fmul_rn((float)pv, a.c32); om = __dsub_rn(1.0, (double)a.c32); }
-    else { rc = __dmul_rn(pv, a.c64); om = __dsub_rn(1.0, a.c64); }
-    return tr8(__dadd_rn(rc, __dmul_rn((double)old, om)));
-}
-__device__ __forceinline__ uint8_t blend_r0(const VppArgs &a, double pv, uint8_t r0, float b32, double b64)
-{
-    double rc, om, rb;
-    const double b = a.arith == 0 ? (double)b32 : b64;
-    const double omb = __dsub_rn(1.0, b);
-    if (a.arith == 0) { rc = (double)__fmul_rn((float)pv, a.c32); om = __dsub_rn(1.0, (double)a.c32); rb = (double)__fmul_rn((float)r0, b32); }
-    else { rc = __dmul_rn(pv, a.c64); om = __dsub_rn(1.0, a.c64); rb = __dmul_rn((double)r0, b64); }
-    return tr8(__dadd_rn(__dmul_rn(__dadd_rn(rc, __dmul_rn((double)r0, om)), omb), rb));
-}
-__device__ __forceinline__ uint8_t blend_r1(const VppArgs &a, double pv, uint8_t r1, float b32, double b64)
-{
-    double rc, om;
-    const double b = a.arith == 0 ? (double)b32 : b64;
-    const double omb = __dsub_rn(1.0, b);
-    if (a.arith == 0) { rc = (double)__fmul_rn((float)pv, a.c32); om = __dsub_rn(1.0, (double)a.c32); }
-    else { rc = __dmul_rn(pv, a.c64); om = __dsub_rn(1.0, a.c64); }
-    return tr8(__dadd_rn(__dmul_rn(__dadd_rn(rc, __dmul_rn((double)r1, om)), b), __dmul_rn((double)r1, omb)));
-}
 
 // the write records of one (hint, xw): calls emit(target, type) with target in [0, W) = left pixel, [W, 2W) = right pixel;
 // type 0 / 1 = interpolated right blend at x0 / x1, 2 = plain blend
@@ -360,11 +340,11 @@ __global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict
         if (tid == 0) ws.rowflag[fr] = (uint8_t)(nh != 0);
         return;
     }
-    // shared memory: offs[2W+1], cur[2W], keys[cap_rec], hint table (gv, row-relative prefix, x, flags)
-    uint32_t *offs = reinterpret_cast<uint32_t *>(vsm);
+    // shared memory: recs[cap_rec] (64-bit), offs[2W+1], cur[2W], hint table (gv, row-relative prefix, x, flags)
+    unsigned long long *recs = reinterpret_cast<unsigned long long *>(vsm);
+    uint32_t *offs = reinterpret_cast<uint32_t *>(recs + cfg.cap_rec);
     uint32_t *cur = offs + (2 * W + 1);
-    uint32_t *keys = cur + 2 * W;
-    float *hgv = reinterpret_cast<float *>(keys + cfg.cap_rec);
+    float *hgv = reinterpret_cast<float *>(cur + 2 * W);
     uint32_t *hpr = reinterpret_cast<uint32_t *>(hgv + cfg.cap_hint);
     uint16_t *hxx = reinterpret_cast<uint16_t *>(hpr + cfg.cap_hint);
     uint8_t *hfl = reinterpret_cast<uint8_t *>(hxx + cfg.cap_hint);        // bit 0: occluded, bits 1..4: source row index
@@ -428,60 +408,98 @@ __global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict
         return;
     }
     if (tid == 0) ws.rowflag[fr] = 0;
-    // (2c) fill: key = scan order of the record = (hint, xw, type)
+    // (2c) fill.  A record is 64 bits: high word = scan order (hint, xw, type) with the hint's patch size in between, low
+    // word = stream position (mod 2^32) of the record's pattern value for channel 0, so the replay decodes nothing
     for (int h = tid; h < nh; h += VR_NT) {
-        const int x = hxx[h];
+        const int x = hxx[h], yr = hfl[h] >> 1;
         const bool occ = hfl[h] & 1;
-        for (int xw = max(-n, -x); xw <= min(n, W - 1 - x); xw++)
+        const int y = ylo_row + yr;
+        const int ylo = max(y - n, 0), ny = min(y + n, H - 1) - ylo + 1;
+        const int xlo = max(x - n, 0), nx = min(x + n, W - 1) - xlo + 1;
+        const uint32_t stride = a.uniform ? 1u : (uint32_t)(nx * ny);                       // <= 225
+        const uint32_t base = a.uniform ? (uint32_t)((long long)C * (rowhb[yr] + (h - rowstart[yr])))
+                                        : (uint32_t)((long long)C * (rowdb[yr] + hpr[h])) + (uint32_t)((yy - ylo) * nx - xlo);
+        for (int xw = max(-n, -x); xw <= min(n, W - 1 - x); xw++) {
+            const uint32_t idx0 = a.uniform ? base : base + (uint32_t)(x + xw);
             vr_records(a, x, hgv[h], occ, xw, [&](int target, int type) {
-                keys[atomicAdd(&cur[target], 1u)] = ((uint32_t)h << 6) | ((uint32_t)(xw + n) << 2) | (uint32_t)type;
+                const uint32_t key = ((uint32_t)h << 14) | (stride << 6) | ((uint32_t)(xw + n) << 2) | (uint32_t)type;
+                recs[atomicAdd(&cur[target], 1u)] = ((unsigned long long)key << 32) | idx0;
             });
+        }
     }
     __syncthreads();
-    // (3) replay per target pixel
-    const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
-    const long long pat_len = pattern ? pattern_offsets[f + 1] - pattern_offsets[f] : 0;
-    const uint64_t frame_key = rng_seed ^ ((uint64_t)f * 0x9E3779B97F4A7C15ull);
-    for (int t = tid; t < 2 * W; t += VR_NT) {
-        const int k0 = (int)offs[t], k1 = (int)offs[t + 1];
-        if (k0 == k1) continue;
-        for (int i = k0 + 1; i < k1; i++) {                // insertion sort: the lists are a handful of records
-            const uint32_t key = keys[i];
-            int q = i - 1;
-            while (q >= k0 && keys[q] > key) { keys[q + 1] = keys[q]; q--; }
-            keys[q + 1] = key;
-        }
-        uint8_t *px = (t < W ? l + (fr * W + t) * C : r + (fr * W + (t - W)) * C);
-        uint8_t v[4];
-        for (int j = 0; j < C; j++) v[j] = px[j];
-        for (int i = k0; i < k1; i++) {
-            const uint32_t key = keys[i];
-            const int h = (int)(key >> 6), xw = (int)((key >> 2) & 15u) - n, type = (int)(key & 3u);
-            const int x = hxx[h], yr = hfl[h] >> 1;
-            const float gv = hgv[h];
-            const int y = ylo_row + yr;
-            const int ylo = max(y - n, 0), ny = min(y + n, H - 1) - ylo + 1;
-            const int xlo = max(x - n, 0), nx = min(x + n, W - 1) - xlo + 1;
-            const long long inb = (long long)nx * ny;
-            const int d0 = (int)floorf(gv);
-            const float b32 = __fsub_rn(gv, (float)d0);
-            const double b64 = __dsub_rn((double)gv, (double)d0);
-            long long idx = a.uniform ? (long long)C * (rowhb[yr] + (h - rowstart[yr]))
-                                      : (long long)C * (rowdb[yr] + hpr[h]) + (long long)(yy - ylo) * nx + (x + xw - xlo);
-            for (int j = 0; j < C; j++) {
-                const long long ij = a.uniform ? idx + j : idx + (long long)j * inb;
-                const uint8_t rv = pat ? ((ij >= 0 && ij < pat_len) ? pat[ij] : 0) : counter_pattern(frame_key, (uint64_t)ij);
-                const double pv = (double)rv;
-                v[j] = type == 2 ? blend_plain(a, pv, v[j]) : (type == 0 ? blend_r0(a, pv, v[j], b32, b64) : blend_r1(a, pv, v[j], b32, b64));
+    // (3) active targets -> dense list (the `cur` bins are free again), each list sorted by scan order by one thread
+    __shared__ int s_nact;
+    if (tid == 0) s_nact = 0;
+    __syncthreads();
+    uint32_t *act = cur;
+    for (int t0 = 0; t0 < 2 * W; t0 += VR_NT) {
+        const int t = t0 + tid;
+        const int k0 = t < 2 * W ? (int)offs[t] : 0, k1 = t < 2 * W ? (int)offs[t + 1] : 0;
+        const bool on = k1 > k0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, on);
+        int base = 0;
+        if ((tid & 31) == 0 && m) base = atomicAdd(&s_nact, __popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (on) {
+            act[base + __popc(m & ((1u << (tid & 31)) - 1u))] = (uint32_t)t;
+            for (int i = k0 + 1; i < k1; i++) {            // insertion sort: the lists are a handful of records
+                const unsigned long long rec = recs[i];
+                int q = i - 1;
+                while (q >= k0 && recs[q] > rec) { recs[q + 1] = recs[q]; q--; }
+                recs[q + 1] = rec;
             }
         }
-        for (int j = 0; j < C; j++) px[j] = v[j];
+    }
+    // the colour term pv * c and the kept share old * (1 - c) only depend on a byte each: two 256-entry tables per CTA,
+    // filled with the reference's typing
+    __shared__ double lut_c[256], lut_o[256];
+    {
+        const double pv = (double)tid;
+        if (a.arith == 0) { lut_c[tid] = (double)__fmul_rn((float)pv, a.c32); lut_o[tid] = __dmul_rn(pv, __dsub_rn(1.0, (double)a.c32)); }
+        else { lut_c[tid] = __dmul_rn(pv, a.c64); lut_o[tid] = __dmul_rn(pv, __dsub_rn(1.0, a.c64)); }
+    }
+    __syncthreads();
+    // (4) replay: one thread per (active target pixel, channel)
+    const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
+    const uint32_t pat_len = pattern ? (uint32_t)min((long long)0xFFFFFFFFll, (long long)(pattern_offsets[f + 1] - pattern_offsets[f])) : 0u;
+    const uint32_t frame_key = frame_key32(rng_seed, f);
+    const int items = s_nact * C;
+    for (int it = tid; it < items; it += VR_NT) {
+        const int t = (int)act[it / C], j = it % C;
+        const int k0 = (int)offs[t], k1 = (int)offs[t + 1];
+        uint8_t *px = (t < W ? l + (fr * W + t) * C : r + (fr * W + (t - W)) * C) + j;
+        uint32_t v = *px;
+        for (int i = k0; i < k1; i++) {
+            const unsigned long long rec = recs[i];
+            const uint32_t key = (uint32_t)(rec >> 32);
+            const uint32_t type = key & 3u;
+            const uint32_t idx = (uint32_t)rec + (uint32_t)j * ((key >> 6) & 255u);
+            const uint32_t rv = pat ? (idx < pat_len ? pat[idx] : 0) : counter_pattern(frame_key, idx);
+            const double mix = __dadd_rn(lut_c[rv], lut_o[v]);                   // colour + old * (1 - c)
+            if (type == 2) {
+                v = tr8(mix);
+            } else {
+                const float gv = hgv[key >> 14];
+                const int d0 = (int)floorf(gv);
+                const float b32 = __fsub_rn(gv, (float)d0);
+                const double b = a.arith == 0 ? (double)b32 : __dsub_rn((double)gv, (double)d0);
+                const double omb = __dsub_rn(1.0, b);
+                if (type == 0) {
+                    const double rb = a.arith == 0 ? (double)__fmul_rn((float)v, b32) : __dmul_rn((double)v, b);
+                    v = tr8(__dadd_rn(__dmul_rn(mix, omb), rb));
+                } else {
+                    v = tr8(__dadd_rn(__dmul_rn(mix, b), __dmul_rn((double)v, omb)));
+                }
+            }
+        }
+        *px = (uint8_t)v;
     }
 }
 
 static size_t vr_smem_bytes(int W, const RowsCfg &c)
 {
-    return (size_t)(4 * W + 1) * 4 + (size_t)c.cap_rec * 4 + (size_t)c.cap_hint * (4 + 4 + 2 + 1) + 16;
+    return (size_t)(4 * W + 1) * 4 + (size_t)c.cap_rec * 8 + (size_t)c.cap_hint * (4 + 4 + 2 + 1) + 16;
 }
 
 // ---- maxDistance: one warp per (frame, channel), sequential over hints ------------------------------------------
@@ -669,12 +687,14 @@ extern "C" int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int 
     int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st);
     if (rc) return rc;
     // per-pixel replay for every row it can take; the rows it flags go to the ordered per-row replay
-    const RowsCfg cfg{8192, 2048};
+    const RowsCfg cfg{4096, 1024};
     const size_t smem = vr_smem_bytes(W, cfg);
     int dev = 0, smem_optin = 0;
     VPP_CUDA_TRY(cudaGetDevice(&dev));
     VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const bool rows_kernel = g_vpp_rows_on && smem <= (size_t)smem_optin && (long)n * H < (1L << 31);
+    // (the per-pixel replay addresses a frame's pattern stream with 32 bits)
+    const bool rows_kernel = g_vpp_rows_on && smem <= (size_t)smem_optin && (long)n * H < (1L << 31) &&
+                             (double)C * W * H * wsize * wsize < 4.0e9;
     if (rows_kernel) {
         VPP_CUDA_TRY(cudaFuncSetAttribute(vpp_rnd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         vpp_rnd_rows_kernel<<<(unsigned)((long)n * H), VR_NT, smem, st>>>(l, r, g, g_occ, pattern, pattern_offsets, rng_seed, ws, a, cfg);
