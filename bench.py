@@ -46,35 +46,64 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML in-process every
+    10 ms (a timed region of a few hundred ms still gets tens of samples); nvidia-smi polling if NVML is unavailable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.source = index, [], False, "nvml"
+        self.nv = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis:
+                ent = vis.split(",")[index].strip()
+                phys = int(ent) if ent.isdigit() else index
+            self.nv, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self._sample_nvml()                         # fail here, not in the thread
+            self.samples.clear()
+        except Exception:
+            self.nv, self.source = None, "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self.nv
+        mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(bits & 0x8), bool(bits & 0x40), bool(bits & 0x20), bool(bits & 0x4)]   # hw, hw_thermal, sw_thermal, sw_power_cap
+        self.samples.append((int(mhz), int(self.max_mhz), flags))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        s = [x.strip() for x in out.split(",")]
+        if len(s) >= 6 and s[0].isdigit():
+            self.samples.append((int(s[0]), int(s[1]) if s[1].isdigit() else 0, [x.lower().startswith("active") for x in s[2:6]]))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self.nv else self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.01 if self.nv else 0.2)
 
     def summary(self):
         self.stop_flag = True
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": reasons,
+                "samples": len(self.samples), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------- CPU reference arm
@@ -239,6 +268,9 @@ def main():
     pipe = VppRsgmPipeline(H, W, C, batch=B, dmax=D, device=dev)
     gather_buf = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
     L = _lib.lib()
+    for key, env in ((_lib.TUNE_SGM_BYTE_SUMS, "VPPB200_BYTE_SUMS"),):           # A/B experiments only
+        if env in os.environ:
+            _lib.set_tuning(key, int(os.environ[env]))
 
     def step_device():
         out = pipe.run_device(left, right, hints, inputs_ready=True)     # the inputs are resident in HBM (definition of `value`)

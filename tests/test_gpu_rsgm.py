@@ -179,6 +179,7 @@ def tuning(mods):
     yield lambda key, value: _lib.set_tuning(key, value)
     _lib.set_tuning(_lib.TUNE_SGM_MAX_STRIP, 0)
     _lib.set_tuning(_lib.TUNE_SGM_SWEEP, 1)
+    _lib.set_tuning(_lib.TUNE_SGM_BYTE_SUMS, 0)
 
 
 @pytest.mark.parametrize("strip", [32, 64, 100])
@@ -195,6 +196,13 @@ def test_sweep_cluster_strips(mods, orc, tuning, strip, shape, D, channels):
     for f, p in enumerate(frames):
         want = orc.compute_rsgm(p["left"], p["left"], p["right"], dmax=D)
         assert_same(st["out"][f], want, f"sweep strip={strip} {shape} D={D} frame {f}")
+    # the production path (last sweep fused with WTA): uint8 partial-sum volumes, then one read-modify-written uint16 S
+    fused16 = rsgm.compute_rsgm(left, left, right, dmax=D)
+    assert_same(fused16, st["out"], f"fused sweep with uint16 S, strip={strip}")
+    tuning(_lib.TUNE_SGM_BYTE_SUMS, 1)
+    fused8 = rsgm.compute_rsgm(left, left, right, dmax=D)
+    assert_same(fused8, st["out"], f"fused sweep with byte partial sums, strip={strip}")
+    tuning(_lib.TUNE_SGM_BYTE_SUMS, 0)
     # the aggregated volume itself, against the stand-alone operator (generic per-path kernel) on the same inputs
     tuning(_lib.TUNE_SGM_SWEEP, 0)
     st0 = rsgm.compute_rsgm_stages(left, left, right, dmax=D)

@@ -52,7 +52,7 @@ def lib():
     return _lib
 
 
-TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS, TUNE_VPP_ROWS = 0, 1, 2, 3
+TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS, TUNE_VPP_ROWS, TUNE_SGM_BYTE_SUMS = 0, 1, 2, 3, 4
 
 
 def set_tuning(key, value):

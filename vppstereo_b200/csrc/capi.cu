@@ -154,7 +154,7 @@ static size_t rsgm_ws_layout(const RsgmDims &d, int n, int sets, int set, void *
         float *dl = (float *)take(np * 4), *dr = (float *)take(np * 4);
         if (k == set) { w.guide = guide; w.dsi = dsi; w.dl = dl; w.dr = dr; }
     }
-    w.S = (uint16_t *)take(vol * 2);
+    w.S = (uint16_t *)take(vol * 3);                          // one uint16 S, or three uint8 partial-sum volumes
     w.S_xyd = (uint16_t *)take(np * d.D * 2);                 // the reference's xyd order (WTA input, test tap)
     w.halo = (void *)take(sweep_halo_bytes(d.D));
     w.dlf = (float *)take(np * 4); w.drf = (float *)take(np * 4);
@@ -261,6 +261,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_SGM_SWEEP: sweep_set_enabled(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_CLUSTERS: sweep_set_clusters(value); return VPPB200_OK;
         case VPPB200_TUNE_VPP_ROWS: vpp_set_rows_kernel(value); return VPPB200_OK;
+        case VPPB200_TUNE_SGM_BYTE_SUMS: sweep_set_byte_sums(value); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }
 }
@@ -416,10 +417,10 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
             const StageHook hook = {StageMarks::hook, &tm};
             if (!want_volume) {
                 // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
-                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, &hook, st)))
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, hints == nullptr, &hook, st)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
             } else {
-                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, &hook, st)))
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, false, &hook, st)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
                 if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
                 S_final = w.S_xyd;
