@@ -268,7 +268,8 @@ def main():
     pipe = VppRsgmPipeline(H, W, C, batch=B, dmax=D, device=dev)
     gather_buf = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
     L = _lib.lib()
-    for key, env in ((_lib.TUNE_SGM_BYTE_SUMS, "VPPB200_BYTE_SUMS"),):           # A/B experiments only
+    for key, env in ((_lib.TUNE_SGM_BYTE_SUMS, "VPPB200_BYTE_SUMS"), (_lib.TUNE_SGM_CLUSTERS, "VPPB200_TEAMS"),
+                     (_lib.TUNE_SGM_MAX_STRIP, "VPPB200_MAX_STRIP")):           # A/B experiments only
         if env in os.environ:
             _lib.set_tuning(key, int(os.environ[env]))
 

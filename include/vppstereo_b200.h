@@ -192,6 +192,17 @@ int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int
 int vppb200_gt_reshape(const float *gt, int W, int H, float *out, int32_t *count_out, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- occlusion mask for VPP: occlusion_heuristic(dmap, rx=9, ry=7, l=2, g=0.4375, th_conf=1, th_filter=0.1)
+ * -> (dmap, conf_map)                                                                        filter.py:246-292
+ * (left_warp :7-48, weighted_conf :113-164, filter :167-194, left_unwarp :50-79, conf_unwarp :81-111,
+ * interpolate_disparity(dmap, 3) :196-243).  test.py:154 passes the sparse hints and uses [1] as g_occ.
+ * dmap float32 [n][H][W] (0 = no hint); dmap_out float32 / conf_out uint8 (0 = visible hint, 1 elsewhere), either may
+ * be NULL.  rx, ry are the un-halved radii as in the reference signature. */
+size_t vppb200_occlusion_workspace_bytes(int H, int W, int n);
+int vppb200_occlusion_heuristic(const float *dmap, float *dmap_out, uint8_t *conf_out, int W, int H, int rx, int ry,
+                                double l, double g, double th_conf, double th_filter, void *workspace,
+                                size_t workspace_bytes, int n, void *stream);
+
 /* ---- hand-off to the networks (test.py:179-200): uint8 [n][H][W][C] -> float32 [n][C][H+pt+pb][W+pl+pr],
  * value = float32(u8 / 255.0) (test.py:179-180), replicate padding as F.pad(..., mode='replicate') (test.py:192-197). */
 int vppb200_u8hwc_to_f32chw(const uint8_t *src, float *dst, int H, int W, int C, int pad_top, int pad_bottom,

@@ -1,4 +1,4 @@
-"""ctypes front-end of the C oracle (oracle/rsgm_oracle.c, oracle/vpp_oracle.c).
+"""ctypes front-end of the C oracle (oracle/rsgm_oracle.c, oracle/vpp_oracle.c, oracle/filter_oracle.c).
 
 TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
 The product package (vppstereo_b200/) must never import this module.
@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(BUILD_DIR, "liboracle.so")
-SOURCES = [os.path.join(HERE, f) for f in ("rsgm_oracle.c", "vpp_oracle.c")]
+SOURCES = [os.path.join(HERE, f) for f in ("rsgm_oracle.c", "vpp_oracle.c", "filter_oracle.c")]
 _lib = None
 
 
@@ -268,3 +268,15 @@ def vpp(left, right, gt, wsize=3, wsizeAgg_x=64, wsizeAgg_y=3, left2right=True, 
         virtual_projection_scan_rnd(lc, rc, gt, W, H, Cn, uniform_color, wsize, direction, blending, c_occ, g_occ,
                                     discard_occ, interpolate, stream=stream, mode=mode)
     return lc, rc
+
+
+# ---------------------------------------------------------------- filter.py
+def occlusion_heuristic(dmap, rx=9, ry=7, l=2, g=0.4375, th_conf=1, th_filter=0.1):
+    """filter.py:246-292: (filtered + interpolated disparity map, binary occlusion mask: 0 = visible hint)."""
+    dmap = _c(dmap, np.float32)
+    H, W = dmap.shape
+    out = np.empty((H, W), np.float32)
+    conf = np.empty((H, W), np.uint8)
+    lib().orc_occlusion_heuristic(_p(dmap), _p(out), _p(conf), W, H, int(rx), int(ry), C.c_double(l), C.c_double(g),
+                                  C.c_double(th_conf), C.c_double(th_filter))
+    return out, conf

@@ -2,7 +2,7 @@
 """Generate the committed golden vectors from the UNMODIFIED reference (oracle/_ref, built from /root/reference).
 
 Run where /root/reference exists:   python tests/golden/make_golden.py
-Outputs (small, committed): tests/golden/rsgm_*.npz, tests/golden/vpp_cases.npz, tests/golden/rcp_lut.npz
+Outputs (small, committed): tests/golden/rsgm_*.npz, tests/golden/vpp_cases.npz, tests/golden/occ_cases.npz, tests/golden/rcp_lut.npz
 
 What is pinned
   * rSGM: inputs + the reference's per-stage outputs (census, sha256 of the cost volume and of the aggregated volume,
@@ -13,6 +13,7 @@ What is pinned
   * the RCPSS table of the CPU that produced the sub-pixel values (the instruction is vendor specific).
   * VPP: inputs, pattern stream and outputs of the reference Cython module (`init_rand(seed)`, libc stream) and of the
     numba twin (`vpp()`, generator seeded in-jit) for a set of flag combinations, both methods.
+  * occlusion mask: hint maps with foreground boxes and the outputs of the reference's filter.occlusion_heuristic.
 """
 import hashlib
 import itertools
@@ -85,6 +86,23 @@ def make_rsgm(r):
     rsgm_case(r, "synth_guided", p["left"], vl, vr, 48, hints=g, valid=(g > 0).astype(np.float32))
 
 
+def make_occ(r):
+    """filter.occlusion_heuristic (filter.py:246-292) on hint maps with foreground boxes, default and non-default windows."""
+    cases = {}
+    combos = [((60, 100), "random", 0.08, {}), ((90, 160), "lidar", 0.05, {}), ((48, 64), "random", 0.3, dict(rx=5, ry=9, l=1, g=0.25, th_conf=2)),
+              ((70, 120), "random", 0.15, dict(th_filter=1.5)), ((33, 47), "random", 0.5, {})]
+    for idx, (shape, kind, density, kw) in enumerate(combos):
+        p = synth.make_pair(300 + idx, shape=shape, hints=kind, density=density, foreground=3)
+        g = p["hints"].astype(np.float32)
+        d, c = r.filter.occlusion_heuristic(g.copy(), **kw)
+        full = dict(rx=9, ry=7, l=2, g=0.4375, th_conf=1, th_filter=0.1); full.update(kw)
+        k = f"o{idx}_"
+        cases.update({k + "g": g, k + "dmap": d, k + "conf": c,
+                      k + "params": np.array([full[n] for n in ("rx", "ry", "l", "g", "th_conf", "th_filter")], np.float64)})
+        print("occ case", idx, shape, kind, "hints", int((g > 0).sum()), "occluded hints", int((c[g > 0] != 0).sum()), "kept", int((d > 0).sum()))
+    np.savez_compressed(os.path.join(OUT, "occ_cases.npz"), **cases)
+
+
 def make_vpp(r):
     from numba import njit
 
@@ -144,8 +162,13 @@ def make_vpp(r):
 
 if __name__ == "__main__":
     r = ref.load_pinned()
-    np.savez_compressed(os.path.join(OUT, "rcp_lut.npz"), lut=orc.rcp_lut())
-    make_rsgm(r)
-    make_vpp(r)
+    parts = sys.argv[1:] or ["rsgm", "vpp", "occ"]          # e.g. `make_golden.py occ` regenerates one family only
+    if "rsgm" in parts:
+        np.savez_compressed(os.path.join(OUT, "rcp_lut.npz"), lut=orc.rcp_lut())
+        make_rsgm(r)
+    if "vpp" in parts:
+        make_vpp(r)
+    if "occ" in parts:
+        make_occ(r)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

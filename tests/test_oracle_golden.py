@@ -1,11 +1,12 @@
 """CPU: the C oracle against the committed golden vectors recorded from the unmodified reference
 (tests/golden/make_golden.py).  This is what pins the oracle on boxes where /root/reference does not exist."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
 
-from conftest import assert_same, golden_rsgm_names, load_golden_rsgm
+from conftest import GOLDEN, assert_same, golden_rsgm_names, load_golden_rsgm
 
 
 @pytest.mark.parametrize("name", golden_rsgm_names())
@@ -99,3 +100,16 @@ def test_libc_stream_matches_golden(golden_vpp):
         want = G[f"c{i}_stream_libc"]
         core.init_rand(seed)
         assert_same(core.draw_pattern(want.size), want, f"libc stream seed {seed}")
+
+
+def test_occlusion_heuristic_golden(orc):
+    """filter.occlusion_heuristic (filter.py:246-292): oracle against the outputs recorded from the reference's numba code."""
+    g = dict(np.load(os.path.join(GOLDEN, "occ_cases.npz")))
+    n = len([k for k in g if k.endswith("_g")])
+    assert n >= 5
+    for i in range(n):
+        k = f"o{i}_"
+        rx, ry, l, gg, thc, thf = g[k + "params"]
+        d, c = orc.occlusion_heuristic(g[k + "g"], rx=int(rx), ry=int(ry), l=l, g=gg, th_conf=thc, th_filter=thf)
+        assert_same(c, g[k + "conf"], f"occlusion mask, case {i}")
+        assert_same(d, g[k + "dmap"], f"filtered hints, case {i}")

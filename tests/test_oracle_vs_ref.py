@@ -107,3 +107,18 @@ def test_vpp_flag_space_vs_reference(orc, R):
         la, ra = S.vpp(li, ri, g, method="maxDistance", g_occ=g_occ.astype(np.float32), **kw)
         lb, rb = orc.vpp(li, ri, g, method="maxDistance", mode=1, g_occ=g_occ, **kw)
         assert_same(lb, la, "numba maxDistance L"); assert_same(rb, ra, "numba maxDistance R")
+
+
+@pytest.mark.parametrize("shape,kind,density,fg,kw", [
+    ((96, 200), "lidar", 0.05, 0, {}), ((120, 160), "random", 0.05, 4, {}), ((64, 64), "random", 0.4, 2, {}),
+    ((80, 140), "random", 0.1, 3, dict(rx=5, ry=11, l=1, g=0.3, th_conf=2)), ((375, 1242), "lidar", 0.05, 6, {}),
+    ((50, 90), "random", 0.2, 3, dict(th_filter=2)),
+])
+def test_occlusion_heuristic_vs_reference(orc, R, shape, kind, density, fg, kw):
+    """filter.py:246-292 (numba) against oracle/filter_oracle.c: mask and filtered hints, bit for bit."""
+    from vppstereo_b200 import synth
+    g = synth.make_pair(7, shape=shape, hints=kind, density=density, foreground=fg)["hints"].astype(np.float32)
+    d_ref, c_ref = R.filter.occlusion_heuristic(g.copy(), **kw)
+    d, c = orc.occlusion_heuristic(g, **kw)
+    assert c_ref.dtype == np.uint8 and d_ref.dtype == np.float32
+    assert_same(c, c_ref, "occlusion mask"); assert_same(d, d_ref, "filtered hints")

@@ -25,6 +25,7 @@ SYMBOLS = [
     "vppb200_rsgm_workspace_bytes_sets", "vppb200_compute_rsgm_phases",
     "vppb200_vpp_workspace_bytes", "vppb200_vpp_scan_rnd", "vppb200_vpp_scan_max_dist", "vppb200_gt_reshape",
     "vppb200_u8hwc_to_f32chw", "vppb200_set_tuning",
+    "vppb200_occlusion_workspace_bytes", "vppb200_occlusion_heuristic",
 ]
 
 _lib = None
@@ -48,6 +49,7 @@ def lib():
         l.vppb200_rsgm_workspace_bytes.restype = C.c_size_t
         l.vppb200_vpp_workspace_bytes.restype = C.c_size_t
         l.vppb200_rsgm_workspace_bytes_sets.restype = C.c_size_t
+        l.vppb200_occlusion_workspace_bytes.restype = C.c_size_t
         _lib = l
     return _lib
 

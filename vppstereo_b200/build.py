@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvppstereo_b200.so")
-SOURCES = ["capi.cu", "rsgm_ops.cu", "sgm.cu", "sgm_sweep.cu", "vpp.cu"]
+SOURCES = ["capi.cu", "rsgm_ops.cu", "sgm.cu", "sgm_sweep.cu", "vpp.cu", "filter.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "vppstereo_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",

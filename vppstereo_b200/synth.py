@@ -21,14 +21,23 @@ def _blur5(img, sigma=1.2):
     return np.clip(np.floor(a + 0.5), 0, 255).astype(np.uint8)
 
 
-def make_pair(f, shape="K", hints="lidar", channels=3, density=0.05):
-    """Returns dict(left, right uint8 [H,W,C]; gt float32 [H,W]; hints float32 [H,W] (0 = none))."""
+def make_pair(f, shape="K", hints="lidar", channels=3, density=0.05, foreground=0):
+    """Returns dict(left, right uint8 [H,W,C]; gt float32 [H,W]; hints float32 [H,W] (0 = none)).
+    foreground = k adds k fronto-parallel boxes 20..45 px closer than the background, so that background hints next to
+    their left edges are occluded in the right view (the case filter.occlusion_heuristic exists for)."""
     H, W = SHAPES[shape] if isinstance(shape, str) else shape
     rng = np.random.default_rng(1000 + f)
     base = _blur5(rng.integers(0, 256, (H, W + 256, channels), dtype=np.uint8))
     left = np.ascontiguousarray(base[:, 128:128 + W])
     yy, xx = np.mgrid[0:H, 0:W]
     dgt = (8.0 + 120.0 * yy / max(H - 1, 1) + 6.0 * np.sin(xx / 97.0)).astype(np.float32)
+    if foreground:
+        brng = np.random.default_rng(77000 + f)
+        for _ in range(int(foreground)):
+            bh, bw = int(brng.integers(max(H // 8, 4), max(H // 3, 6))), int(brng.integers(max(W // 12, 4), max(W // 4, 6)))
+            by, bx = int(brng.integers(0, max(H - bh, 1))), int(brng.integers(0, max(W - bw, 1)))
+            dgt[by:by + bh, bx:bx + bw] = np.float32(dgt[by:by + bh, bx:bx + bw].max() + brng.uniform(20, 45))
+        dgt = np.minimum(dgt, np.float32(190.0))
     src = np.clip(128 + xx + np.rint(dgt).astype(np.int64), 0, W + 255)
     right = np.ascontiguousarray(base[yy, src])
     if hints == "random":
