@@ -86,6 +86,7 @@ int vppb200_stage_times(float *ms_out, int *calls_out);
 #define VPPB200_TUNE_SGM_SWEEP 1
 #define VPPB200_TUNE_VPP_ROWS 3       /* 0 = VPP rnd by the ordered per-row replay only, 1 = per-pixel replay where possible (default) */
 #define VPPB200_TUNE_SGM_CLUSTERS 2   /* upper bound on frames in flight in the v-sweep (0 = all SMs); experiments only */
+#define VPPB200_TUNE_VPP_MD_WAVE 5    /* 0 = VPP maxDistance by the serial one-warp-per-(frame, channel) kernel, 1 = row wavefront (default) */
 #define VPPB200_TUNE_SGM_BYTE_SUMS 4  /* 0 = sweeps read-modify-write one uint16 S (default), 1 = uint8 partial-sum volumes where exact */
 int vppb200_set_tuning(int key, int value);
 
@@ -181,7 +182,10 @@ int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, i
                          uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream);
 
 /* virtual_projection_scan_max_dist(l, r, g, width, height, channels, uniform_color, wsize, wsize_agg_x, wsize_agg_y,
- *                                  direction, c, c_occ, g_occ, discard_occluded, interpolate) -> #hints  pyx:133-341 */
+ *                                  direction, c, c_occ, g_occ, discard_occluded, interpolate) -> #hints  pyx:133-341
+ * Workspace: vppb200_vpp_max_dist_workspace_bytes (adds the per-hint dependency table of the row-wavefront kernel);
+ * with only vppb200_vpp_workspace_bytes the call still works but runs the hints of a (frame, channel) one after another. */
+size_t vppb200_vpp_max_dist_workspace_bytes(int H, int W, int C, int wsize, int wsize_agg_y, int n);
 int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
                               int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
                               const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,

@@ -23,7 +23,7 @@ SYMBOLS = [
     "vppb200_match_wta_right", "vppb200_subpixel_refine", "vppb200_median3x3",
     "vppb200_rsgm_workspace_bytes", "vppb200_compute_rsgm", "vppb200_compute_rsgm_tapped",
     "vppb200_rsgm_workspace_bytes_sets", "vppb200_compute_rsgm_phases",
-    "vppb200_vpp_workspace_bytes", "vppb200_vpp_scan_rnd", "vppb200_vpp_scan_max_dist", "vppb200_gt_reshape",
+    "vppb200_vpp_workspace_bytes", "vppb200_vpp_max_dist_workspace_bytes", "vppb200_vpp_scan_rnd", "vppb200_vpp_scan_max_dist", "vppb200_gt_reshape",
     "vppb200_u8hwc_to_f32chw", "vppb200_set_tuning",
     "vppb200_occlusion_workspace_bytes", "vppb200_occlusion_heuristic",
 ]
@@ -48,13 +48,14 @@ def lib():
         l.vppb200_launch_count.restype = C.c_uint64
         l.vppb200_rsgm_workspace_bytes.restype = C.c_size_t
         l.vppb200_vpp_workspace_bytes.restype = C.c_size_t
+        l.vppb200_vpp_max_dist_workspace_bytes.restype = C.c_size_t
         l.vppb200_rsgm_workspace_bytes_sets.restype = C.c_size_t
         l.vppb200_occlusion_workspace_bytes.restype = C.c_size_t
         _lib = l
     return _lib
 
 
-TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS, TUNE_VPP_ROWS, TUNE_SGM_BYTE_SUMS = 0, 1, 2, 3, 4
+TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS, TUNE_VPP_ROWS, TUNE_SGM_BYTE_SUMS, TUNE_VPP_MD_WAVE = 0, 1, 2, 3, 4, 5
 
 
 def set_tuning(key, value):

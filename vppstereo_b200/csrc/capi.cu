@@ -261,6 +261,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_SGM_SWEEP: sweep_set_enabled(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_CLUSTERS: sweep_set_clusters(value); return VPPB200_OK;
         case VPPB200_TUNE_VPP_ROWS: vpp_set_rows_kernel(value); return VPPB200_OK;
+        case VPPB200_TUNE_VPP_MD_WAVE: vpp_set_md_wave(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_BYTE_SUMS: sweep_set_byte_sums(value); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }

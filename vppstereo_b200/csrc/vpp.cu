@@ -118,13 +118,15 @@ __device__ __forceinline__ uint8_t tr8(double v) { return (uint8_t)(int)v; }    
 struct Splat {
     const VppArgs &a;
     uint8_t *lrow, *rrow;      // row pointers at channel j (pixel stride = C)
-    __device__ __forceinline__ uint8_t &L(int x) const { return lrow[(long)x * a.C]; }
-    __device__ __forceinline__ uint8_t &R(int x) const { return rrow[(long)(x < 0 ? x + a.W : x) * a.C]; }  // negative index wraps
+    __device__ __forceinline__ uint8_t getL(int x) const { return lrow[(long)x * a.C]; }
+    __device__ __forceinline__ void setL(int x, uint8_t v) const { lrow[(long)x * a.C] = v; }
+    __device__ __forceinline__ uint8_t getR(int x) const { return rrow[(long)(x < 0 ? x + a.W : x) * a.C]; }  // negative index wraps
+    __device__ __forceinline__ void setR(int x, uint8_t v) const { rrow[(long)(x < 0 ? x + a.W : x) * a.C] = v; }
 };
 
 // pv: pattern value (rnd: the drawn uint8; maxDistance: (pa+pb)/2 as double)
-template <bool RND>
-__device__ __forceinline__ void splat_pixel(const Splat &s, double pv, int xl, int x0, int x1, int xr, bool occluded,
+template <bool RND, class S>
+__device__ __forceinline__ void splat_pixel(const S &s, double pv, int xl, int x0, int x1, int xr, bool occluded,
                                             float b32, double b64)
 {
     const VppArgs &a = s.a;
@@ -154,37 +156,37 @@ __device__ __forceinline__ void splat_pixel(const Splat &s, double pv, int xl, i
     if (0 <= x0 && x0 <= W - 1) {
         if (!occluded) {
             const double rc = colour(false), om = omc(false);
-            s.L(xl) = tr8(blend(rc, s.L(xl), om));
+            s.setL(xl, tr8(blend(rc, s.getL(xl), om)));
             if (a.interpolate) {
-                const uint8_t r0 = s.R(x0);
-                s.R(x0) = tr8(__dadd_rn(__dmul_rn(blend(rc, r0, om), omb), r_times_b(r0)));
+                const uint8_t r0 = s.getR(x0);
+                s.setR(x0, tr8(__dadd_rn(__dmul_rn(blend(rc, r0, om), omb), r_times_b(r0))));
                 if (0 <= x1 && x1 <= W - 1) {
-                    const uint8_t r1 = s.R(x1);
-                    s.R(x1) = tr8(__dadd_rn(__dmul_rn(blend(rc, r1, om), b), __dmul_rn((double)r1, omb)));
+                    const uint8_t r1 = s.getR(x1);
+                    s.setR(x1, tr8(__dadd_rn(__dmul_rn(blend(rc, r1, om), b), __dmul_rn((double)r1, omb))));
                 }
             } else {
-                s.R(xr) = tr8(blend(rc, s.R(xr), om));
+                s.setR(xr, tr8(blend(rc, s.getR(xr), om)));
             }
         } else if (!a.discard) {
             const double rc = colour(true), omo = omc(true), om = omc(false);
             if (a.interpolate) {
-                const uint8_t r0 = s.R(x0);
-                s.R(x0) = tr8(__dadd_rn(__dmul_rn(blend(rc, r0, omo), omb), r_times_b(r0)));
+                const uint8_t r0 = s.getR(x0);
+                s.setR(x0, tr8(__dadd_rn(__dmul_rn(blend(rc, r0, omo), omb), r_times_b(r0))));
                 if (0 <= x1 && x1 <= W - 1) {
-                    const uint8_t r1 = s.R(x1);
-                    s.R(x1) = tr8(__dadd_rn(__dmul_rn(blend(rc, r1, omo), b), __dmul_rn((double)r1, omb)));
+                    const uint8_t r1 = s.getR(x1);
+                    s.setR(x1, tr8(__dadd_rn(__dmul_rn(blend(rc, r1, omo), b), __dmul_rn((double)r1, omb))));
                 }
-                const double mix = __dadd_rn(__dmul_rn((double)s.R(x0), omb), r_times_b(s.R(x1)));
+                const double mix = __dadd_rn(__dmul_rn((double)s.getR(x0), omb), r_times_b(s.getR(x1)));
                 const double cc = a.arith == 0 ? (double)a.c32 : a.c64;
-                s.L(xl) = tr8(__dadd_rn(__dmul_rn(mix, cc), __dmul_rn((double)s.L(xl), om)));
+                s.setL(xl, tr8(__dadd_rn(__dmul_rn(mix, cc), __dmul_rn((double)s.getL(xl), om))));
             } else {
-                s.R(xr) = tr8(blend(rc, s.R(xr), omo));
-                const double rcl = a.arith == 0 ? (double)__fmul_rn((float)s.R(xr), a.c32) : __dmul_rn((double)s.R(xr), a.c64);
-                s.L(xl) = tr8(__dadd_rn(rcl, __dmul_rn((double)s.L(xl), om)));
+                s.setR(xr, tr8(blend(rc, s.getR(xr), omo)));
+                const double rcl = a.arith == 0 ? (double)__fmul_rn((float)s.getR(xr), a.c32) : __dmul_rn((double)s.getR(xr), a.c64);
+                s.setL(xl, tr8(__dadd_rn(rcl, __dmul_rn((double)s.getL(xl), om))));
             }
         }
     } else {
-        s.L(xl) = tr8(blend(colour(false), s.L(xl), omc(false)));    // left-side occlusion (pyx:123-124)
+        s.setL(xl, tr8(blend(colour(false), s.getL(xl), omc(false))));    // left-side occlusion (pyx:123-124)
     }
 }
 
@@ -527,10 +529,25 @@ __device__ __forceinline__ void fold_chunk(MaxDistState &st, bool has_l, int vl,
     }
 }
 
-__device__ double max_dist_colour(const VppArgs &a, const uint8_t *limg, const uint8_t *rimg, int j, int cy, int cx, int shift,
-                                  bool occ, bool uniform_branch, int lane)
+// window sample sources: the images themselves (serial kernel) or the per-hint shared-memory region (wavefront kernel)
+struct MdGlobalSrc {
+    const uint8_t *limg, *rimg;       // frame base + channel j
+    int W, C;
+    __device__ __forceinline__ int L(int yy, int xx) const { return limg[((long)yy * W + xx) * C]; }
+    __device__ __forceinline__ int R(int yy, int xx, int xr) const { (void)xx; return rimg[((long)yy * W + xr) * C]; }
+};
+struct MdRegionSrc {
+    const uint8_t *sL, *sR;           // [RH][RW] samples of L at (oy+ry, ox+cx) and of R at (oy+ry, ox+cx-shift)
+    int oy, ox, RW;
+    __device__ __forceinline__ int L(int yy, int xx) const { return sL[(yy - oy) * RW + (xx - ox)]; }
+    __device__ __forceinline__ int R(int yy, int xx, int xr) const { (void)xr; return sR[(yy - oy) * RW + (xx - ox)]; }
+};
+
+template <class Src>
+__device__ __forceinline__ double max_dist_colour(const VppArgs &a, const Src &src, int cy, int cx, int shift,
+                                                  bool occ, bool uniform_branch, int lane)
 {
-    const int W = a.W, H = a.H, C = a.C;
+    const int W = a.W, H = a.H;
     const int wx = 2 * a.nax + 1, wy = 2 * a.nay + 1, npos = wx * wy;
     MaxDistState st{0, 255, 0};
     // Cython's uniform branch only counts samples that pass the range test (pyx:235-237,:248-250); a zero sample never
@@ -546,8 +563,8 @@ __device__ double max_dist_colour(const VppArgs &a, const uint8_t *limg, const u
                 const int xr = xx - shift;
                 has_r = (0 <= xr && xr <= W - 1);
                 has_l = (!occ) || !has_r;
-                if (has_l) vl = limg[((long)yy * W + xx) * C + j];
-                if (has_r) vr = rimg[((long)yy * W + xr) * C + j];
+                if (has_l) vl = src.L(yy, xx);
+                if (has_r) vr = src.R(yy, xx, xr);
             }
         }
         if (count_all)
@@ -566,8 +583,8 @@ __device__ double max_dist_colour(const VppArgs &a, const uint8_t *limg, const u
                 if (yy < 0 || yy > H - 1 || xx < 0 || xx > W - 1) continue;
                 const int xr = xx - shift;
                 const bool hr = (0 <= xr && xr <= W - 1);
-                if (((!occ) || !hr) && limg[((long)yy * W + xx) * C + j] == k) cntk++;
-                if (hr && rimg[((long)yy * W + xr) * C + j] == k) cntk++;
+                if (((!occ) || !hr) && src.L(yy, xx) == k) cntk++;
+                if (hr && src.R(yy, xx, xr) == k) cntk++;
             }
             if (a.arith == 1) cntk &= 255;
             // warp arg-min, first index on ties
@@ -594,6 +611,7 @@ __global__ void __launch_bounds__(32) vpp_max_dist_kernel(uint8_t *l, uint8_t *r
     const long f = unit / a.C;
     const int W = a.W, H = a.H, n = a.n;
     uint8_t *limg = l + f * (long)H * W * a.C, *rimg = r + f * (long)H * W * a.C;
+    const MdGlobalSrc src{limg + j, rimg + j, W, a.C};
     for (int y = 0; y < H; y++) {
         const long row = f * H + y;
         const int cnt = ws.cnt[row];
@@ -604,12 +622,12 @@ __global__ void __launch_bounds__(32) vpp_max_dist_kernel(uint8_t *l, uint8_t *r
             const bool occ = g_occ[row * W + x] != 0;
             const HintGeom hg = hint_geom(a, gv, x);
             double pv = 0.0;
-            if (a.uniform) pv = max_dist_colour(a, limg, rimg, j, y, x, x - hg.xd, occ, true, lane);
+            if (a.uniform) pv = max_dist_colour(a, src, y, x, x - hg.xd, occ, true, lane);
             for (int yw = -n; yw <= n; yw++) {
                 if (y + yw < 0 || y + yw > H - 1) continue;
                 for (int xw = -n; xw <= n; xw++) {
                     if (x + xw < 0 || x + xw > W - 1) continue;
-                    if (!a.uniform) pv = max_dist_colour(a, limg, rimg, j, y + yw, x + xw, x - hg.xd, occ, false, lane);
+                    if (!a.uniform) pv = max_dist_colour(a, src, y + yw, x + xw, x - hg.xd, occ, false, lane);
                     if (lane == 0) {
                         Splat s{a, limg + ((long)(y + yw) * W) * a.C + j, rimg + ((long)(y + yw) * W) * a.C + j};
                         splat_pixel<false>(s, pv, x + xw, hg.xd0 + xw, hg.xd1 + xw, hg.xd + xw, occ, hg.b32, hg.b64);
@@ -617,6 +635,236 @@ __global__ void __launch_bounds__(32) vpp_max_dist_kernel(uint8_t *l, uint8_t *r
                     __syncwarp();                     // lane 0's stores are visible to the next window fetch
                 }
             }
+        }
+    }
+}
+
+// The same fold for the wavefront kernel, out of the staged region: window rows are walked 32 columns at a time (no
+// div/mod), the next sample that can move (pa, pb) is found with ONE warp min-reduction over keys (order << 8 | value),
+// zero samples are counted per lane and summed once.  Falls back to max_dist_colour for the n_bins == 0 corner.
+__device__ __forceinline__ double md_colour_region(const VppArgs &a, const MdRegionSrc &src, int cy, int cx, int shift, bool occ,
+                                                   bool uniform_branch, int lane)
+{
+    const int W = a.W, H = a.H, wx = 2 * a.nax + 1;
+    const bool count_all = !(a.arith == 0 && uniform_branch);
+    int pa = 0, pb = 255, zeros = 0;
+    const int keyl0 = (2 * lane) << 8, keyr0 = (2 * lane + 1) << 8;
+    for (int yy = max(cy - a.nay, 0); yy <= min(cy + a.nay, H - 1); yy++) {
+        const int base = (yy - src.oy) * src.RW + (cx - a.nax - src.ox);
+        for (int c0 = 0; c0 < wx; c0 += 32) {
+            const int dx = c0 + lane, xx = cx - a.nax + dx, xr = xx - shift;
+            const bool in = dx < wx && xx >= 0 && xx <= W - 1;
+            const bool has_r = in && xr >= 0 && xr <= W - 1;
+            const bool has_l = in && (!occ || !has_r);
+            const int vl = has_l ? (int)src.sL[base + dx] : -1;
+            const int vr = has_r ? (int)src.sR[base + dx] : -1;
+            zeros += (vl == 0) + (vr == 0);
+            const int keyl = keyl0 | (vl & 255), keyr = keyr0 | (vr & 255);
+            int done = -1;
+            while (true) {
+                const bool pl = vl > pa && vl < pb && keyl > done;
+                const bool pr = vr > pa && vr < pb && keyr > done;
+                const unsigned key = pl ? (unsigned)keyl : (pr ? (unsigned)keyr : 0xFFFFFFFFu);
+                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, key);
+                if (m == 0xFFFFFFFFu) break;
+                const int v = (int)(m & 255u);
+                done = (int)m;
+                if (v - pa > pb - v) pb = v;
+                else if (v - pa < pb - v) pa = v;
+            }
+        }
+    }
+    if (count_all && __reduce_add_sync(0xFFFFFFFFu, zeros) == 256)
+        return max_dist_colour(a, src, cy, cx, shift, occ, uniform_branch, lane);
+    return (double)(pa + pb) / 2.0;
+}
+
+// ---- maxDistance, wavefront version: one warp per (frame, channel, hint row), rows pipelined behind each other -----
+// The scan is sequential, but two hints only interact when one writes what the other reads or writes.  Writes of a hint
+// stay within rows y-n..y+n and columns x-n..x+n (left) / x-d1-n..x-d0+n (right), reads within n+nay rows and n+nax
+// columns of those, so hints of rows further apart than RD = 2n+nay never interact and a hint of row y only has to wait
+// for the LAST hint of each row y-1..y-RD whose footprint overlaps its own (vpp_md_deps_kernel finds them; rows run in
+// scan order, so "hint k' of that row is done" covers all earlier ones).  Rows are handed out through a ticket counter in
+// raster order, so everything a row waits for is already running or finished: no deadlock.  Every hint is still applied
+// after all earlier hints it could observe and before all later hints that could observe it: bit-exact.
+// A hint's working set (the union of its patch pixels' windows in both images) is staged once in shared memory; the
+// folds of the 9 patch pixels and lane 0's blends then run out of it (blends write through to global memory).
+struct MdWs {
+    uint16_t *dep;       // [n][H][RD][W] per hint (parallel to hx): 1 + index of the last interacting hint of row y-1-r, 0 = none
+    int *prog;           // [n*C][H] hints of that row already applied
+    int *ticket;         // [1]
+};
+
+static size_t md_ws_layout(int H, int W, int C, int n, int RD, void *base, size_t base_off, MdWs *ws)
+{
+    size_t off = align256(base_off);
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? b + o : (char *)nullptr; };
+    uint16_t *dep = (uint16_t *)take((size_t)n * H * RD * W * 2);
+    int *prog = (int *)take(((size_t)n * C * H + 64) * 4);
+    if (ws) { ws->dep = dep; ws->prog = prog; ws->ticket = prog + (size_t)n * C * H; }
+    return off;
+}
+
+struct MdFoot {                    // column footprints of one hint; intervals are clipped to the image, empty = hi < lo
+    int wl_lo, wl_hi, fl_lo, fl_hi;        // left image: written / touched
+    int wr_lo, wr_hi, fr_lo, fr_hi;        // right image: written (and read back by the blend) / touched
+    int wrap_lo;                           // right-image accesses at negative columns wrap to [wrap_lo, W-1]; W = none
+};
+__device__ __forceinline__ MdFoot md_foot(const VppArgs &a, int x, float gv)
+{
+    const HintGeom hg = hint_geom(a, gv, x);
+    const int W = a.W, n = a.n, m = a.n + a.nax;
+    MdFoot f;
+    f.wl_lo = max(x - n, 0); f.wl_hi = min(x + n, W - 1);
+    f.fl_lo = max(x - m, 0); f.fl_hi = min(x + m, W - 1);
+    const int lo = min(hg.xd1, hg.xd) - n, hi = max(hg.xd0, hg.xd) + n;
+    f.wr_lo = max(lo, 0); f.wr_hi = min(hi, W - 1);
+    f.fr_lo = max(min(lo, hg.xd - m), 0); f.fr_hi = min(max(hi, hg.xd + m), W - 1);
+    f.wrap_lo = (lo < 0 && hi >= 0) ? max(W + lo, 0) : W;
+    return f;
+}
+__device__ __forceinline__ bool md_ov(int alo, int ahi, int blo, int bhi) { return max(alo, blo) <= min(ahi, bhi); }
+__device__ __forceinline__ bool md_conflict(const MdFoot &p, const MdFoot &q, int W)
+{
+    if (md_ov(p.wl_lo, p.wl_hi, q.fl_lo, q.fl_hi) || md_ov(p.fl_lo, p.fl_hi, q.wl_lo, q.wl_hi)) return true;
+    if (md_ov(p.wr_lo, p.wr_hi, q.fr_lo, q.fr_hi) || md_ov(p.fr_lo, p.fr_hi, q.wr_lo, q.wr_hi)) return true;
+    if (p.wrap_lo < W && (q.wrap_lo < W || q.fr_hi >= p.wrap_lo)) return true;
+    if (q.wrap_lo < W && p.fr_hi >= q.wrap_lo) return true;
+    return false;
+}
+
+// one CTA per (frame, row): for every hint of the row, the last interacting hint of each of the RD rows above
+__global__ void __launch_bounds__(128) vpp_md_deps_kernel(const float *__restrict__ g, VppWs ws, MdWs md, VppArgs a, int RD)
+{
+    const long row = blockIdx.x;
+    const int W = a.W, H = a.H;
+    const int y = (int)(row % H);
+    const int cnt = ws.cnt[row];
+    const uint16_t *hx = ws.hx + row * W;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        const int x = hx[k];
+        const MdFoot me = md_foot(a, x, g[row * W + x]);
+        for (int r = 0; r < RD; r++) {
+            int dep = 0;
+            if (y - 1 - r >= 0) {
+                const long prow = row - 1 - r;
+                const uint16_t *phx = ws.hx + prow * W;
+                for (int kk = ws.cnt[prow] - 1; kk >= 0; kk--) {
+                    const int px = phx[kk];
+                    if (md_conflict(me, md_foot(a, px, g[prow * W + px]), W)) { dep = kk + 1; break; }
+                }
+            }
+            md.dep[(row * RD + r) * W + k] = (uint16_t)dep;
+        }
+    }
+}
+
+__device__ __forceinline__ int md_ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void md_st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct MdSplat {
+    const VppArgs &a;
+    uint8_t *lrow, *rrow;      // global row pointers at channel j
+    uint8_t *sl, *sr;          // region row of the same image row
+    int ox, shift, RW;
+    __device__ __forceinline__ uint8_t getL(int x) const { return sl[x - ox]; }                 // patch pixels are inside the region
+    __device__ __forceinline__ void setL(int x, uint8_t v) const { sl[x - ox] = v; lrow[(long)x * a.C] = v; }
+    __device__ __forceinline__ uint8_t getR(int x) const
+    {
+        if (x < 0) x += a.W;
+        const int c = x + shift - ox;
+        return (c >= 0 && c < RW) ? sr[c] : __ldcg(rrow + (long)x * a.C);
+    }
+    __device__ __forceinline__ void setR(int x, uint8_t v) const
+    {
+        if (x < 0) x += a.W;
+        const int c = x + shift - ox;
+        if (c >= 0 && c < RW) sr[c] = v;
+        rrow[(long)x * a.C] = v;
+    }
+};
+
+__global__ void __launch_bounds__(32) vpp_max_dist_wave_kernel(uint8_t *l, uint8_t *r, const float *__restrict__ g,
+                                                               const uint8_t *__restrict__ g_occ, VppWs ws, MdWs md, VppArgs a,
+                                                               int units, int RD)
+{
+    extern __shared__ uint8_t md_smem[];
+    const int lane = threadIdx.x;
+    const int W = a.W, H = a.H, C = a.C, n = a.n;
+    const int RH = 2 * (n + a.nay) + 1, RW = 2 * (n + a.nax) + 1;
+    uint8_t *sL = md_smem, *sR = md_smem + RH * RW;
+    const long total = (long)units * H;
+    while (true) {
+        long t = 0;
+        if (lane == 0) t = atomicAdd(md.ticket, 1);
+        t = __shfl_sync(0xFFFFFFFFu, (int)t, 0);
+        if (t >= total) return;
+        const int y = (int)(t / units), unit = (int)(t % units);
+        const int j = unit % C;
+        const long f = unit / C;
+        const long row = f * H + y;
+        const int cnt = ws.cnt[row];
+        if (cnt == 0) continue;
+        uint8_t *limg = l + f * (long)H * W * C + j, *rimg = r + f * (long)H * W * C + j;
+        int *prog = md.prog + (long)unit * H;
+        const uint16_t *hx = ws.hx + row * W;
+        for (int k = 0; k < cnt; k++) {
+            const int x = hx[k];
+            const float gv = g[row * W + x];
+            const bool occ = g_occ[row * W + x] != 0;
+            const HintGeom hg = hint_geom(a, gv, x);
+            const int shift = x - hg.xd;
+            // wait for the hints of the rows above that interact with this one
+            for (int rr = 0; rr < RD && y - 1 - rr >= 0; rr++) {
+                const int need = md.dep[(row * RD + rr) * W + k];
+                if (need == 0) continue;
+                const int *p = prog + (y - 1 - rr);
+                unsigned ns = 32;
+                while (md_ld_acquire(p) < need) { __nanosleep(ns); ns = min(ns * 2, 1024u); }
+            }
+            // stage the working set
+            const int oy = y - n - a.nay, ox = x - n - a.nax;
+            for (int ry = 0; ry < RH; ry++) {
+                const int yy = oy + ry;
+                const bool yin = yy >= 0 && yy <= H - 1;
+                const uint8_t *lp = limg + (long)yy * W * C, *rp = rimg + (long)yy * W * C;
+#pragma unroll 3
+                for (int c = lane; c < RW; c += 32) {
+                    const int xx = ox + c, xr = xx - shift;
+                    uint8_t vl = 0, vr = 0;             // (the right sample is staged even where xx is outside: the blends read it)
+                    if (yin && xx >= 0 && xx <= W - 1) vl = __ldcg(lp + (long)xx * C);
+                    if (yin && xr >= 0 && xr <= W - 1) vr = __ldcg(rp + (long)xr * C);
+                    sL[ry * RW + c] = vl; sR[ry * RW + c] = vr;
+                }
+            }
+            __syncwarp();
+            const MdRegionSrc src{sL, sR, oy, ox, RW};
+            double pv = 0.0;
+            if (a.uniform) pv = md_colour_region(a, src, y, x, shift, occ, true, lane);
+            for (int yw = -n; yw <= n; yw++) {
+                if (y + yw < 0 || y + yw > H - 1) continue;
+                for (int xw = -n; xw <= n; xw++) {
+                    if (x + xw < 0 || x + xw > W - 1) continue;
+                    if (!a.uniform) pv = md_colour_region(a, src, y + yw, x + xw, shift, occ, false, lane);
+                    if (lane == 0) {
+                        const int ry = y + yw - oy;
+                        MdSplat s{a, limg + ((long)(y + yw) * W) * C, rimg + ((long)(y + yw) * W) * C, sL + ry * RW, sR + ry * RW,
+                                  ox, shift, RW};
+                        splat_pixel<false>(s, pv, x + xw, hg.xd0 + xw, hg.xd1 + xw, hg.xd + xw, occ, hg.b32, hg.b64);
+                    }
+                    __syncwarp();                     // lane 0's updates of the region are visible to the next fold
+                }
+            }
+            if (lane == 0) md_st_release(prog + y, k + 1);
         }
     }
 }
@@ -649,6 +897,8 @@ static int prepare_hints(const float *g, int W, int H, int n_patch, int directio
 
 static int g_vpp_rows_on = 1;       // test hook: 0 = ordered per-row replay only
 void vpp_set_rows_kernel(int on) { g_vpp_rows_on = on != 0; }
+static int g_vpp_md_wave = 1;       // test hook: 0 = maxDistance by the serial one-warp-per-(frame, channel) kernel only
+void vpp_set_md_wave(int on) { g_vpp_md_wave = on < 0 ? 0 : on; }   // > 1: rows in flight per SM (experiments)
 
 static VppArgs make_args(int W, int H, int C, int uniform, int wsize, int wax, int way, int direction, double c, double c_occ,
                          int discard, int interpolate, int arith)
@@ -724,9 +974,42 @@ extern "C" int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g,
     int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st);
     if (rc) return rc;
     const int total = n * C;
+    // wavefront kernel when the caller's workspace holds the dependency table (vppb200_vpp_max_dist_workspace_bytes) and a
+    // hint's working set fits shared memory; the serial one-warp-per-(frame, channel) kernel otherwise
+    const int RD = 2 * a.n + a.nay;
+    const size_t base_bytes = vpp_ws_layout(H, W, n, nullptr, nullptr);
+    const size_t smem = 2 * (size_t)(2 * (a.n + a.nay) + 1) * (2 * (a.n + a.nax) + 1);
+    int dev = 0, smem_optin = 0, sms = 0;
+    VPP_CUDA_TRY(cudaGetDevice(&dev));
+    VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    VPP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const bool wave = g_vpp_md_wave && RD >= 1 && smem <= (size_t)smem_optin && (long)total * H < (1L << 30) &&
+                      workspace_bytes >= md_ws_layout(H, W, C, n, RD, nullptr, base_bytes, nullptr);
+    if (wave) {
+        MdWs md;
+        md_ws_layout(H, W, C, n, RD, workspace, base_bytes, &md);
+        VPP_CUDA_TRY(cudaMemsetAsync(md.prog, 0, ((size_t)total * H + 64) * 4, st));
+        vpp_md_deps_kernel<<<(unsigned)((long)n * H), 128, 0, st>>>(g, ws, md, a, RD);
+        VPP_LAUNCH_CHECK("vpp_md_deps_kernel");
+        VPP_CUDA_TRY(cudaFuncSetAttribute(vpp_max_dist_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long rows = (long)total * H;
+        long resident = (long)sms * (smem <= 4096 ? 32 : max((size_t)1, (size_t)200 * 1024 / (smem + 1024)));
+        if (g_vpp_md_wave > 1) resident = min(resident, (long)sms * g_vpp_md_wave);
+        vpp_max_dist_wave_kernel<<<(unsigned)min(rows, resident), 32, smem, st>>>(l, r, g, g_occ, ws, md, a, total, RD);
+        VPP_LAUNCH_CHECK("vpp_max_dist_wave_kernel");
+        return VPPB200_OK;
+    }
     vpp_max_dist_kernel<<<total, 32, 0, st>>>(l, r, g, g_occ, ws, a, total);
     VPP_LAUNCH_CHECK("vpp_max_dist_kernel");
     return VPPB200_OK;
+}
+
+extern "C" size_t vppb200_vpp_max_dist_workspace_bytes(int H, int W, int C, int wsize, int wsize_agg_y, int n)
+{
+    if (H <= 0 || W <= 0 || C <= 0 || n <= 0 || wsize < 1 || wsize_agg_y < 1) return 0;
+    const int RD = 2 * ((wsize - 1) / 2) + (wsize_agg_y - 1) / 2;
+    const size_t base = vpp_ws_layout(H, W, n, nullptr, nullptr);
+    return RD >= 1 ? md_ws_layout(H, W, C, n, RD, nullptr, base, nullptr) : base;
 }
 
 extern "C" int vppb200_gt_reshape(const float *gt, int W, int H, float *out, int32_t *count_out, void *workspace,

@@ -103,7 +103,10 @@ def _scan(kind, l, r, g, width, height, channels, uniform_color, wsize, wagg, di
         raise ValueError("operand sizes do not match width/height/channels")
     L = _lib.lib()
     dev = lt.device
-    ws = _lib.workspace(L.vppb200_vpp_workspace_bytes(height, width, channels, n), dev, "vpp")
+    if kind == "rnd":
+        ws = _lib.workspace(L.vppb200_vpp_workspace_bytes(height, width, channels, n), dev, "vpp")
+    else:
+        ws = _lib.workspace(L.vppb200_vpp_max_dist_workspace_bytes(height, width, channels, wsize, int(wagg[1]), n), dev, "vpp")
     counts = torch.empty(n, dtype=torch.int32, device=dev)
     # Cython receives c, c_occ as C float; numba as Python floats
     cc, co = float(c), float(c_occ)
