@@ -28,12 +28,6 @@ def run(shape, N, wave, reps):
     return lt, rt
 
 if __name__ == "__main__":
-    if "--sweep" in sys.argv:
-        for k in (2, 4, 8, 16, 32):
-            run("M", 1, k, 2)
-        for k in (8, 16, 32):
-            run("K", 64, k, 2)
-        sys.exit(0)
     a = run("M", 1, 1, 3)
     if "--serial" in sys.argv:
         b = run("M", 1, 0, 1)

@@ -648,29 +648,31 @@ __device__ __forceinline__ double md_colour_region(const VppArgs &a, const MdReg
     const int W = a.W, H = a.H, wx = 2 * a.nax + 1;
     const bool count_all = !(a.arith == 0 && uniform_branch);
     int pa = 0, pb = 255, zeros = 0;
-    const int keyl0 = (2 * lane) << 8, keyr0 = (2 * lane + 1) << 8;
-    for (int yy = max(cy - a.nay, 0); yy <= min(cy + a.nay, H - 1); yy++) {
-        const int base = (yy - src.oy) * src.RW + (cx - a.nax - src.ox);
-        for (int c0 = 0; c0 < wx; c0 += 32) {
-            const int dx = c0 + lane, xx = cx - a.nax + dx, xr = xx - shift;
-            const bool in = dx < wx && xx >= 0 && xx <= W - 1;
-            const bool has_r = in && xr >= 0 && xr <= W - 1;
-            const bool has_l = in && (!occ || !has_r);
-            const int vl = has_l ? (int)src.sL[base + dx] : -1;
-            const int vr = has_r ? (int)src.sR[base + dx] : -1;
-            zeros += (vl == 0) + (vr == 0);
-            const int keyl = keyl0 | (vl & 255), keyr = keyr0 | (vr & 255);
-            int done = -1;
-            while (true) {
-                const bool pl = vl > pa && vl < pb && keyl > done;
-                const bool pr = vr > pa && vr < pb && keyr > done;
-                const unsigned key = pl ? (unsigned)keyl : (pr ? (unsigned)keyr : 0xFFFFFFFFu);
-                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, key);
-                if (m == 0xFFFFFFFFu) break;
-                const int v = (int)(m & 255u);
-                done = (int)m;
-                if (v - pa > pb - v) pb = v;
-                else if (v - pa < pb - v) pa = v;
+    {
+        const int keyl0 = (2 * lane) << 8, keyr0 = (2 * lane + 1) << 8;
+        for (int yy = max(cy - a.nay, 0); yy <= min(cy + a.nay, H - 1); yy++) {
+            const int base = (yy - src.oy) * src.RW + (cx - a.nax - src.ox);
+            for (int c0 = 0; c0 < wx; c0 += 32) {
+                const int dx = c0 + lane, xx = cx - a.nax + dx, xr = xx - shift;
+                const bool in = dx < wx && xx >= 0 && xx <= W - 1;
+                const bool has_r = in && xr >= 0 && xr <= W - 1;
+                const bool has_l = in && (!occ || !has_r);
+                const int vl = has_l ? (int)src.sL[base + dx] : -1;
+                const int vr = has_r ? (int)src.sR[base + dx] : -1;
+                zeros += (vl == 0) + (vr == 0);
+                const int keyl = keyl0 | (vl & 255), keyr = keyr0 | (vr & 255);
+                int done = -1;
+                while (true) {
+                    const bool pl = vl > pa && vl < pb && keyl > done;
+                    const bool pr = vr > pa && vr < pb && keyr > done;
+                    const unsigned key = pl ? (unsigned)keyl : (pr ? (unsigned)keyr : 0xFFFFFFFFu);
+                    const unsigned m = __reduce_min_sync(0xFFFFFFFFu, key);
+                    if (m == 0xFFFFFFFFu) break;
+                    const int v = (int)(m & 255u);
+                    done = (int)m;
+                    if (v - pa > pb - v) pb = v;
+                    else if (v - pa < pb - v) pa = v;
+                }
             }
         }
     }
@@ -771,6 +773,8 @@ __device__ __forceinline__ void md_st_release(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+static constexpr int MD_IMAX = 11;
+
 struct MdSplat {
     const VppArgs &a;
     uint8_t *lrow, *rrow;      // global row pointers at channel j
@@ -803,6 +807,12 @@ __global__ void __launch_bounds__(32) vpp_max_dist_wave_kernel(uint8_t *l, uint8
     const int RH = 2 * (n + a.nay) + 1, RW = 2 * (n + a.nax) + 1;
     uint8_t *sL = md_smem, *sR = md_smem + RH * RW;
     const long total = (long)units * H;
+    int pos[MD_IMAX];                 // region position lane + 32 i as (row << 16 | column); row >= RH = beyond the region
+#pragma unroll
+    for (int i = 0; i < MD_IMAX; i++) {
+        const int p = lane + 32 * i;
+        pos[i] = ((p / RW) << 16) | (p % RW);
+    }
     while (true) {
         long t = 0;
         if (lane == 0) t = atomicAdd(md.ticket, 1);
@@ -817,33 +827,62 @@ __global__ void __launch_bounds__(32) vpp_max_dist_wave_kernel(uint8_t *l, uint8
         uint8_t *limg = l + f * (long)H * W * C + j, *rimg = r + f * (long)H * W * C + j;
         int *prog = md.prog + (long)unit * H;
         const uint16_t *hx = ws.hx + row * W;
+        // hint k+1's column, value, mask and dependencies are fetched while hint k is folded; lane rr holds the
+        // dependency on row y-1-rr and polls it itself
+        auto fetch = [&](int k, int &x, float &gv, bool &occ, int &need) {
+            x = hx[k];
+            gv = g[row * W + x];
+            occ = g_occ[row * W + x] != 0;
+            need = (lane < RD && y - 1 - lane >= 0) ? (int)md.dep[(row * RD + lane) * W + k] : 0;
+        };
+        int nx_x, nx_need;
+        float nx_gv;
+        bool nx_occ;
+        fetch(0, nx_x, nx_gv, nx_occ, nx_need);
+        const int *mydep = prog + max(y - 1 - lane, 0);
         for (int k = 0; k < cnt; k++) {
-            const int x = hx[k];
-            const float gv = g[row * W + x];
-            const bool occ = g_occ[row * W + x] != 0;
+            const int x = nx_x, need = nx_need;
+            const float gv = nx_gv;
+            const bool occ = nx_occ;
             const HintGeom hg = hint_geom(a, gv, x);
             const int shift = x - hg.xd;
             // wait for the hints of the rows above that interact with this one
-            for (int rr = 0; rr < RD && y - 1 - rr >= 0; rr++) {
-                const int need = md.dep[(row * RD + rr) * W + k];
-                if (need == 0) continue;
-                const int *p = prog + (y - 1 - rr);
+            {
                 unsigned ns = 32;
-                while (md_ld_acquire(p) < need) { __nanosleep(ns); ns = min(ns * 2, 1024u); }
+                while (__any_sync(0xFFFFFFFFu, need != 0 && md_ld_acquire(mydep) < need)) { __nanosleep(ns); ns = min(ns * 2, 1024u); }
+                __syncwarp();                         // ... which orders every lane's loads below
             }
-            // stage the working set
+            if (k + 1 < cnt) fetch(k + 1, nx_x, nx_gv, nx_occ, nx_need);
+            // stage the working set: all loads first (IMAX x 32 positions cover the default 5 x 67 region), then the stores
             const int oy = y - n - a.nay, ox = x - n - a.nax;
-            for (int ry = 0; ry < RH; ry++) {
-                const int yy = oy + ry;
-                const bool yin = yy >= 0 && yy <= H - 1;
-                const uint8_t *lp = limg + (long)yy * W * C, *rp = rimg + (long)yy * W * C;
-#pragma unroll 3
-                for (int c = lane; c < RW; c += 32) {
-                    const int xx = ox + c, xr = xx - shift;
-                    uint8_t vl = 0, vr = 0;             // (the right sample is staged even where xx is outside: the blends read it)
-                    if (yin && xx >= 0 && xx <= W - 1) vl = __ldcg(lp + (long)xx * C);
-                    if (yin && xr >= 0 && xr <= W - 1) vr = __ldcg(rp + (long)xr * C);
-                    sL[ry * RW + c] = vl; sR[ry * RW + c] = vr;
+            if (RH * RW <= 32 * MD_IMAX) {
+                uint8_t vl[MD_IMAX], vr[MD_IMAX];
+#pragma unroll
+                for (int i = 0; i < MD_IMAX; i++) {
+                    const int ry = pos[i] >> 16, c = pos[i] & 0xFFFF;
+                    const int yy = oy + ry, xx = ox + c, xr = xx - shift;
+                    const bool yin = ry < RH && yy >= 0 && yy <= H - 1;
+                    vl[i] = 0; vr[i] = 0;               // (the right sample is staged even where xx is outside: the blends read it)
+                    if (yin && xx >= 0 && xx <= W - 1) vl[i] = __ldcg(limg + ((long)yy * W + xx) * C);
+                    if (yin && xr >= 0 && xr <= W - 1) vr[i] = __ldcg(rimg + ((long)yy * W + xr) * C);
+                }
+#pragma unroll
+                for (int i = 0; i < MD_IMAX; i++) {
+                    const int ry = pos[i] >> 16, c = pos[i] & 0xFFFF;
+                    if (ry < RH) { sL[ry * RW + c] = vl[i]; sR[ry * RW + c] = vr[i]; }
+                }
+            } else {
+                for (int ry = 0; ry < RH; ry++) {
+                    const int yy = oy + ry;
+                    const bool yin = yy >= 0 && yy <= H - 1;
+                    const uint8_t *lp = limg + (long)yy * W * C, *rp = rimg + (long)yy * W * C;
+                    for (int c = lane; c < RW; c += 32) {
+                        const int xx = ox + c, xr = xx - shift;
+                        uint8_t vl = 0, vr = 0;
+                        if (yin && xx >= 0 && xx <= W - 1) vl = __ldcg(lp + (long)xx * C);
+                        if (yin && xr >= 0 && xr <= W - 1) vr = __ldcg(rp + (long)xr * C);
+                        sL[ry * RW + c] = vl; sR[ry * RW + c] = vr;
+                    }
                 }
             }
             __syncwarp();
@@ -983,7 +1022,7 @@ extern "C" int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g,
     VPP_CUDA_TRY(cudaGetDevice(&dev));
     VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     VPP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const bool wave = g_vpp_md_wave && RD >= 1 && smem <= (size_t)smem_optin && (long)total * H < (1L << 30) &&
+    const bool wave = g_vpp_md_wave && RD >= 1 && RD <= 32 && smem <= (size_t)smem_optin && (long)total * H < (1L << 30) &&
                       workspace_bytes >= md_ws_layout(H, W, C, n, RD, nullptr, base_bytes, nullptr);
     if (wave) {
         MdWs md;
