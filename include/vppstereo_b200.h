@@ -191,6 +191,29 @@ int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int
                               const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
                               int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream);
 
+/* The adaptive patches of vpp() (TPAMI extension, numba twin only: vpp_standalone.py:6-11 distance-based patch size,
+ * :371-394 _bilateral_filling, guards :153-154 / :334-335).  The scans take two optional device operands:
+ *   filled_g          float32 [n][H][W], the output of vppb200_bilateral_filling: a patch pixel is projected (and, in rnd mode,
+ *                     its pattern value drawn) only where |g[y,x] - filled_g[yy,xx]| < 0.1 (float64); NULL = always
+ *   patch_thresholds  float32 [n][wsize-1], ascending: patch size of a hint = 1 + #{k : g >= thr[k]} (the caller tabulates the
+ *                     reference's float32-ratio / libm-pow / round-half-even size function into these steps, so the device
+ *                     evaluates no pow()); NULL = wsize for every hint
+ * vppb200_bilateral_filling: gray = uint8 context image [n][H][W]; weights = DEVICE float64 [(2p+1)^2][256] table of
+ * exp(-((yw^2+xw^2)/(2 o_xy^2) + di^2/(2 o_i^2))) indexed by (patch offset, |intensity difference|), tabulated by the caller
+ * with the host libm (numba calls the same function); th = bilateral_th. */
+int vppb200_bilateral_filling(const float *dmap, const uint8_t *gray, float *out, int W, int H, int n_patch,
+                              const double *weights, double th, int n, void *stream);
+int vppb200_vpp_scan_rnd_adaptive(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                  int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                                  int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                                  uint64_t rng_seed, const float *filled_g, const float *patch_thresholds, int n_thresholds,
+                                  int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream);
+int vppb200_vpp_scan_max_dist_adaptive(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color,
+                                       int wsize, int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                                       const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
+                                       const float *filled_g, const float *patch_thresholds, int n_thresholds,
+                                       int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream);
+
 /* gt_reshape(gt f32[H,W]) -> f32[N,4] = (x, y, d, 1) in raster order           vpp_core_opt.pyx:352-371.
  * out must hold W*H rows; count_out int32 [1] device. */
 int vppb200_gt_reshape(const float *gt, int W, int H, float *out, int32_t *count_out, void *workspace,

@@ -245,9 +245,21 @@ def gt_reshape(gt):
     return out[:n]
 
 
-def vpp(left, right, gt, wsize=3, wsizeAgg_x=64, wsizeAgg_y=3, left2right=True, blending=0.4, uniform_color=False,
+def bilateral_filling(dmap, img, n, o_xy=2, o_i=1, th=.001):
+    """vpp_standalone.py:371-394."""
+    dmap = _c(dmap, np.float32)
+    img = _c(img, np.uint8)
+    H, W = dmap.shape
+    assert img.shape == dmap.shape
+    out = np.empty((H, W), np.float32)
+    lib().orc_bilateral_filling(_p(dmap), _p(img), W, H, int(n), C.c_double(o_xy), C.c_double(o_i), C.c_double(th), _p(out))
+    return out
+
+
+def vpp(left, right, gt, wsize=3, wsizeAgg_x=64, wsizeAgg_y=3, left2right=True, blending=0.4, use_distance_patch=False,
+        use_bilateral_patch=False, distance_gamma=0.3, bilateral_o_xy=2, bilateral_o_i=1, bilateral_th=.001, uniform_color=False,
         method="rnd", c_occ=0.0, g_occ=None, discard_occ=False, interpolate=True, stream=None, mode=1):
-    """vpp_standalone.py:396-432 (core flags only; mode 1 = numba arithmetic as test.py uses it)."""
+    """vpp_standalone.py:396-432 (mode 1 = numba arithmetic as test.py uses it; the adaptive-patch flags exist in numba only)."""
     lc, rc = np.copy(left), np.copy(right)
     gt = gt.astype(np.float32)
     assert method in ["rnd", "maxDistance"]
@@ -261,6 +273,29 @@ def vpp(left, right, gt, wsize=3, wsizeAgg_x=64, wsizeAgg_y=3, left2right=True, 
         g_occ = np.zeros(gt.shape, np.uint8)
     g_occ = (np.asarray(g_occ) != 0).astype(np.uint8)
     H, W, Cn = lc.shape
+    if use_distance_patch or use_bilateral_patch:
+        assert mode == 1
+        dmin, dmax = gt[gt > 0].min(), gt[gt > 0].max()
+        if use_distance_patch and dmin == dmax:
+            raise ZeroDivisionError("division by zero")               # numba's python error model (:7)
+        gray = bgr2gray(lc) if Cn == 3 else np.ascontiguousarray(lc[..., 0])
+        filled = bilateral_filling(gt, gray, (wsize - 1) // 2, bilateral_o_xy, bilateral_o_i, bilateral_th) if use_bilateral_patch \
+            else gt.copy()
+        gt_c, filled, occ_c = _c(gt, np.float32), _c(filled, np.float32), _c(g_occ, np.uint8)
+        if method == "maxDistance":
+            lib().orc_vpp_scan_max_dist_adaptive(_p(lc), _p(rc), _p(gt_c), _p(filled), W, H, Cn, int(bool(uniform_color)), int(wsize),
+                                                 int(wsizeAgg_x), int(wsizeAgg_y), direction, C.c_double(blending), C.c_double(c_occ),
+                                                 _p(occ_c), int(bool(discard_occ)), int(bool(interpolate)), int(bool(use_distance_patch)),
+                                                 int(bool(use_bilateral_patch)), C.c_float(dmin), C.c_float(dmax), C.c_double(distance_gamma))
+        else:
+            st = _c(stream if stream is not None else np.zeros(0, np.uint8), np.uint8)
+            used = C.c_long(0)
+            lib().orc_vpp_scan_rnd_adaptive(_p(lc), _p(rc), _p(gt_c), _p(filled), W, H, Cn, int(bool(uniform_color)), int(wsize),
+                                            direction, C.c_double(blending), C.c_double(c_occ), _p(occ_c), int(bool(discard_occ)),
+                                            int(bool(interpolate)), _p(st), C.c_long(st.size), C.byref(used),
+                                            int(bool(use_distance_patch)), int(bool(use_bilateral_patch)), C.c_float(dmin),
+                                            C.c_float(dmax), C.c_double(distance_gamma))
+        return lc, rc
     if method == "maxDistance":
         virtual_projection_scan_max_dist(lc, rc, gt, W, H, Cn, uniform_color, wsize, wsizeAgg_x, wsizeAgg_y, direction,
                                          blending, c_occ, g_occ, discard_occ, interpolate, mode=mode)

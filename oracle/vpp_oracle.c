@@ -121,14 +121,67 @@ static inline int round_mode(const blend_t *B, float g)
     return (int)nearbyint((double)g);                          /* numba round: half to even */
 }
 
+/* ---- TPAMI extensions of vpp_standalone.py (numba only) ------------------------------------- */
+typedef struct {
+    int use_distance, use_bilateral;
+    float dmin, dmax;            /* numpy float32 scalars (vpp_standalone.py:410-411) */
+    double gamma;                /* python float */
+    const float *filled;         /* [H][W] bilateral-filled hints (only read when use_bilateral) */
+} adapt_t;
+
+/* _get_patch_size_based_on_distance  vpp_standalone.py:6-11: float32 ratio, float64 pow (libm), round half to even */
+static inline int adapt_radius(const adapt_t *A, float gv, int wsize)
+{
+    if (!A || !A->use_distance) return (wsize - 1) / 2;
+    const float ratio = (gv - A->dmin) / (A->dmax - A->dmin);
+    const double w = pow((double)ratio, 1.0 / A->gamma);
+    const long ws = (long)nearbyint(w * (double)(wsize - 1) + 1.0);
+    /* Python floor division of (ws - 1) by 2 */
+    long q = (ws - 1) / 2;
+    if ((ws - 1) % 2 != 0 && (ws - 1) < 0) q -= 1;
+    return (int)q;
+}
+/* vpp_standalone.py:153-154 / :334-335: abs(g[y,x] - filled_g[yy,xx]) < 0.1.  _bilateral_filling returns FLOAT64 (numba
+ * types np.where(cmap>th, aug_dmap, 0) as float64), so the difference is float32 - float64 -> float64 (exact). */
+static inline int adapt_keep(const adapt_t *A, float gv, int W, int yy, int xx)
+{
+    if (!A || !A->use_bilateral) return 1;
+    return fabs((double)gv - (double)A->filled[(size_t)yy * W + xx]) < 0.1;
+}
+
+/* _bilateral_filling  vpp_standalone.py:371-394: img is the uint8 gray context, cmap float32, weights float64 (libm exp);
+ * o_xy / o_i are passed as doubles (numba types the defaults as int64; 2*(o**2) is exact either way for integers). */
+ORC_API void orc_bilateral_filling(const float *dmap, const uint8_t *img, int W, int H, int n, double o_xy, double o_i, double th,
+                                   float *out)
+{
+    float *cmap = (float *)calloc((size_t)W * H, sizeof(float));
+    memcpy(out, dmap, (size_t)W * H * sizeof(float));
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const float d_ref = dmap[(size_t)y * W + x];
+            if (!(d_ref > 0)) continue;
+            const int i_ref = img[(size_t)y * W + x];
+            for (int yw = -n; yw <= n; yw++)
+                for (int xw = -n; xw <= n; xw++) {
+                    if (y + yw < 0 || y + yw > H - 1 || x + xw < 0 || x + xw > W - 1) continue;
+                    const long di = (long)img[(size_t)(y + yw) * W + x + xw] - i_ref;
+                    const double weight = exp(-((double)(yw * yw + xw * xw) / (2.0 * (o_xy * o_xy)) + (double)(di * di) / (2.0 * (o_i * o_i))));
+                    float *cm = cmap + (size_t)(y + yw) * W + x + xw;
+                    if ((double)*cm < weight) { *cm = (float)weight; out[(size_t)(y + yw) * W + x + xw] = d_ref; }
+                }
+        }
+    for (size_t i = 0; i < (size_t)W * H; i++)
+        if (!((double)cmap[i] > th)) out[i] = 0.0f;
+    free(cmap);
+}
+
 /* virtual_projection_scan_rnd  vpp_core_opt.pyx:53-131 / vpp_standalone.py:243-369.
  * `stream` holds the pre-drawn pattern values; returns the number of hints; *consumed = values used. */
-ORC_API int orc_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
-                             int direction, double c, double c_occ, const uint8_t *g_occ, int discard, int interpolate,
-                             int mode, const uint8_t *stream, long stream_len, long *consumed)
+static int scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                    int direction, double c, double c_occ, const uint8_t *g_occ, int discard, int interpolate,
+                    int mode, const uint8_t *stream, long stream_len, long *consumed, const adapt_t *A)
 {
     blend_t B = { mode, (float)c, (float)c_occ, c, c_occ };
-    const int n = (wsize - 1) / 2;
     long si = 0;
     int count = 0;
     for (int y = 0; y < H; y++) {
@@ -141,12 +194,14 @@ ORC_API int orc_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int 
                 const double b64 = (double)gv - (double)d0;            /* numba: float32 - int64 -> float64 */
                 const int xd = x - d, xd0 = x - d0, xd1 = x - d1;
                 const int occ = g_occ[(size_t)y * W + x] != 0;
+                const int n = adapt_radius(A, gv, wsize);
                 for (int j = 0; j < C; j++) {
                     uint8_t rv = 0;
                     if (uniform_color) rv = si < stream_len ? stream[si] : 0, si++;
                     for (int yw = -n; yw <= n; yw++)
                         for (int xw = -n; xw <= n; xw++) {
                             if (y + yw < 0 || y + yw > H - 1 || x + xw < 0 || x + xw > W - 1) continue;
+                            if (!adapt_keep(A, gv, W, y + yw, x + xw)) continue;
                             if (!uniform_color) rv = si < stream_len ? stream[si] : 0, si++;
                             splat_pixel(&B, 1, (double)rv, l + (size_t)(y + yw) * W * C, r + (size_t)(y + yw) * W * C, W, C, j,
                                         x + xw, xd0 + xw, xd1 + xw, xd + xw, occ, discard, interpolate, b32, b64);
@@ -159,6 +214,25 @@ ORC_API int orc_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int 
     }
     if (consumed) *consumed = si;
     return count;
+}
+
+ORC_API int orc_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                             int direction, double c, double c_occ, const uint8_t *g_occ, int discard, int interpolate,
+                             int mode, const uint8_t *stream, long stream_len, long *consumed)
+{
+    return scan_rnd(l, r, g, W, H, C, uniform_color, wsize, direction, c, c_occ, g_occ, discard, interpolate, mode, stream,
+                    stream_len, consumed, NULL);
+}
+
+/* the numba scan with the adaptive-patch flags (vpp_standalone.py:243-369 with :318-322 and :334-335) */
+ORC_API int orc_vpp_scan_rnd_adaptive(uint8_t *l, uint8_t *r, const float *g, const float *filled_g, int W, int H, int C,
+                                      int uniform_color, int wsize, int direction, double c, double c_occ, const uint8_t *g_occ,
+                                      int discard, int interpolate, const uint8_t *stream, long stream_len, long *consumed,
+                                      int use_distance, int use_bilateral, float dmin, float dmax, double gamma)
+{
+    adapt_t A = { use_distance, use_bilateral, dmin, dmax, gamma, filled_g };
+    return scan_rnd(l, r, g, W, H, C, uniform_color, wsize, direction, c, c_occ, g_occ, discard, interpolate, 1, stream,
+                    stream_len, consumed, &A);
 }
 
 /* histogram "max distance" colour of one window (vpp_core_opt.pyx:216-260 uniform, :269-313 per pixel;
@@ -209,12 +283,12 @@ static double max_dist_colour(const uint8_t *l, const uint8_t *r, int W, int H, 
 }
 
 /* virtual_projection_scan_max_dist  vpp_core_opt.pyx:133-341 / vpp_standalone.py:14-232 */
-ORC_API int orc_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
-                                  int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
-                                  const uint8_t *g_occ, int discard, int interpolate, int mode)
+static int scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                         int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                         const uint8_t *g_occ, int discard, int interpolate, int mode, const adapt_t *A)
 {
     blend_t B = { mode, (float)c, (float)c_occ, c, c_occ };
-    const int n = (wsize - 1) / 2, nax = (wsize_agg_x - 1) / 2, nay = (wsize_agg_y - 1) / 2;
+    const int nax = (wsize_agg_x - 1) / 2, nay = (wsize_agg_y - 1) / 2;
     int count = 0;
     for (int y = 0; y < H; y++) {
         int x = direction == 0 ? W - 1 : 0;
@@ -226,12 +300,14 @@ ORC_API int orc_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W,
                 const double b64 = (double)gv - (double)d0;
                 const int xd = x - d, xd0 = x - d0, xd1 = x - d1;
                 const int occ = g_occ[(size_t)y * W + x] != 0;
+                const int n = adapt_radius(A, gv, wsize);
                 for (int j = 0; j < C; j++) {
                     double pv = 0;
                     if (uniform_color) pv = max_dist_colour(l, r, W, H, C, j, y, x, x - xd, nax, nay, occ, 1, mode);
                     for (int yw = -n; yw <= n; yw++)
                         for (int xw = -n; xw <= n; xw++) {
                             if (y + yw < 0 || y + yw > H - 1 || x + xw < 0 || x + xw > W - 1) continue;
+                            if (!adapt_keep(A, gv, W, y + yw, x + xw)) continue;
                             if (!uniform_color)
                                 pv = max_dist_colour(l, r, W, H, C, j, y + yw, x + xw, x - xd, nax, nay, occ, 0, mode);
                             splat_pixel(&B, 0, pv, l + (size_t)(y + yw) * W * C, r + (size_t)(y + yw) * W * C, W, C, j,
@@ -244,6 +320,25 @@ ORC_API int orc_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W,
         }
     }
     return count;
+}
+
+ORC_API int orc_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                  int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                                  const uint8_t *g_occ, int discard, int interpolate, int mode)
+{
+    return scan_max_dist(l, r, g, W, H, C, uniform_color, wsize, wsize_agg_x, wsize_agg_y, direction, c, c_occ, g_occ, discard,
+                         interpolate, mode, NULL);
+}
+
+/* the numba scan with the adaptive-patch flags (vpp_standalone.py:14-232 with :93-96 and :153-154) */
+ORC_API int orc_vpp_scan_max_dist_adaptive(uint8_t *l, uint8_t *r, const float *g, const float *filled_g, int W, int H, int C,
+                                           int uniform_color, int wsize, int wsize_agg_x, int wsize_agg_y, int direction, double c,
+                                           double c_occ, const uint8_t *g_occ, int discard, int interpolate, int use_distance,
+                                           int use_bilateral, float dmin, float dmax, double gamma)
+{
+    adapt_t A = { use_distance, use_bilateral, dmin, dmax, gamma, filled_g };
+    return scan_max_dist(l, r, g, W, H, C, uniform_color, wsize, wsize_agg_x, wsize_agg_y, direction, c, c_occ, g_occ, discard,
+                         interpolate, 1, &A);
 }
 
 /* gt_reshape  vpp_core_opt.pyx:352-371: raster-order compaction to (x, y, d, 1) */

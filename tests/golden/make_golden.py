@@ -2,7 +2,7 @@
 """Generate the committed golden vectors from the UNMODIFIED reference (oracle/_ref, built from /root/reference).
 
 Run where /root/reference exists:   python tests/golden/make_golden.py
-Outputs (small, committed): tests/golden/rsgm_*.npz, tests/golden/vpp_cases.npz, tests/golden/occ_cases.npz, tests/golden/rcp_lut.npz
+Outputs (small, committed): tests/golden/rsgm_*.npz, tests/golden/vpp_cases.npz, tests/golden/vpp_adaptive_cases.npz, tests/golden/occ_cases.npz, tests/golden/rcp_lut.npz
 
 What is pinned
   * rSGM: inputs + the reference's per-stage outputs (census, sha256 of the cost volume and of the aggregated volume,
@@ -160,14 +160,64 @@ def make_vpp(r):
     np.savez_compressed(os.path.join(OUT, "vpp_cases.npz"), **cases)
 
 
+def make_vpp_adaptive(r):
+    """vpp() with the TPAMI adaptive patches (vpp_standalone.py:6-11, :371-394), recorded from the reference's numba code."""
+    from numba import njit
+
+    @njit
+    def nb_seed(s):
+        np.random.seed(s)
+
+    @njit
+    def nb_draw(n):
+        out = np.empty(n, np.uint8)
+        for i in range(n):
+            out[i] = np.random.randint(0, 256)
+        return out
+
+    S = r.vpp_standalone
+    cases = {}
+    combos = [  # C, wsize, distance, bilateral, uniform, direction, o_i
+        (3, 7, 1, 1, 0, 1, 3), (3, 5, 0, 1, 0, 0, 1), (1, 7, 1, 0, 1, 1, 1), (3, 9, 1, 1, 1, 1, 5), (1, 5, 1, 1, 0, 0, 2),
+    ]
+    H, W = 44, 80
+    for idx, (C, wsize, distance, bilateral, uniform, direction, o_i) in enumerate(combos):
+        p = synth.make_pair(300 + idx, shape=(H, W), hints="random", channels=3, density=0.04, foreground=2)
+        l0 = p["left"][..., :C].copy(); r0 = p["right"][..., :C].copy()
+        g = (p["hints"] * 0.25).astype(np.float32)
+        g_occ = (np.random.default_rng(idx).random((H, W)) < 0.2).astype(np.uint8)
+        li = l0 if C == 3 else l0[..., 0]; ri = r0 if C == 3 else r0[..., 0]
+        n = orc.stream_length(g, wsize, C, uniform)
+        kw = dict(wsize=wsize, wsizeAgg_x=16, wsizeAgg_y=3, left2right=bool(direction), blending=0.4, use_distance_patch=bool(distance),
+                  use_bilateral_patch=bool(bilateral), distance_gamma=0.3, bilateral_o_xy=2, bilateral_o_i=o_i, bilateral_th=.001,
+                  uniform_color=bool(uniform), c_occ=0.1, g_occ=g_occ.astype(np.float32))
+        seed = 500 + idx
+        nb_seed(seed); st_n = nb_draw(n); nb_seed(seed)
+        ln, rn = S.vpp(li, ri, g, method="rnd", **kw)
+        lm, rm = S.vpp(li, ri, g, method="maxDistance", **kw)
+        k = f"a{idx}_"
+        cases.update({k + "params": np.array([C, wsize, distance, bilateral, uniform, direction, o_i], np.int64), k + "l": l0, k + "r": r0,
+                      k + "g": g, k + "g_occ": g_occ, k + "stream_numba": st_n, k + "rnd_l": ln, k + "rnd_r": rn, k + "max_l": lm,
+                      k + "max_r": rm})
+        if bilateral:
+            import cv2
+            gray = cv2.cvtColor(l0, cv2.COLOR_BGR2GRAY) if C == 3 else l0[..., 0]
+            cases[k + "filled"] = S._bilateral_filling(g, gray, (wsize - 1) // 2, 2, o_i, .001).astype(np.float32)
+        print("vpp adaptive case", idx, combos[idx], "changed px", int((ln != l0.reshape(ln.shape)).sum()))
+    cases["n_cases"] = np.int64(len(combos))
+    np.savez_compressed(os.path.join(OUT, "vpp_adaptive_cases.npz"), **cases)
+
+
 if __name__ == "__main__":
     r = ref.load_pinned()
-    parts = sys.argv[1:] or ["rsgm", "vpp", "occ"]          # e.g. `make_golden.py occ` regenerates one family only
+    parts = sys.argv[1:] or ["rsgm", "vpp", "adaptive", "occ"]          # e.g. `make_golden.py occ` regenerates one family only
     if "rsgm" in parts:
         np.savez_compressed(os.path.join(OUT, "rcp_lut.npz"), lut=orc.rcp_lut())
         make_rsgm(r)
     if "vpp" in parts:
         make_vpp(r)
+    if "adaptive" in parts:
+        make_vpp_adaptive(r)
     if "occ" in parts:
         make_occ(r)
     for f in sorted(os.listdir(OUT)):

@@ -120,3 +120,23 @@ def test_glibc_generator_state_continues():
     libc = ctypes.CDLL("libc.so.6")
     libc.srand(42)
     assert np.array_equal(a[:64], np.array([libc.rand() % 256 for _ in range(64)], np.uint8))
+
+
+def test_patch_threshold_tabulation():
+    """vpp(use_distance_patch=True): the device evaluates the reference's patch-size function (float32 ratio, libm pow, round
+    half to even; vpp_standalone.py:6-9) through per-frame disparity thresholds found on the host; the thresholds must
+    reproduce the direct evaluation for every disparity, including the neighbours of each step."""
+    from vppstereo_b200 import vpp_standalone as vs
+    rng = np.random.default_rng(0)
+    for dmin, dmax, wsize, gamma in [(1.5, 190.25, 7, 0.3), (0.5, 3.0, 9, 0.3), (10.0, 10.5, 5, 1.0), (2.0, 64.0, 3, 0.1), (1.0, 200.0, 1, 0.3)]:
+        dmin, dmax = np.float32(dmin), np.float32(dmax)
+        thr = vs._patch_thresholds(dmin, dmax, wsize, gamma)
+        assert thr.shape == (wsize - 1,) and (np.diff(thr) >= 0).all()
+        ds = np.concatenate([rng.uniform(dmin, dmax, 2000).astype(np.float32), [dmin, dmax]]).astype(np.float32)
+        for t in thr[np.isfinite(thr)]:
+            ds = np.concatenate([ds, [np.nextafter(t, np.float32(0)), t, np.nextafter(t, np.float32(1e9))]]).astype(np.float32)
+        ds = ds[(ds >= dmin) & (ds <= dmax)]
+        for d in ds:
+            assert 1 + int((d >= thr).sum()) == vs._patch_size(d, dmin, dmax, wsize, gamma), (d, dmin, dmax, wsize, gamma)
+    with pytest.raises(ZeroDivisionError):
+        vs._patch_thresholds(np.float32(4.0), np.float32(4.0), 5, 0.3)

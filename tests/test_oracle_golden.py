@@ -91,6 +91,31 @@ def test_vpp_cases(orc, golden_vpp):
         assert_same(ln, G[k + "nb_max_l"], f"case {i} numba maxDistance L"); assert_same(rn, G[k + "nb_max_r"], f"case {i} numba maxDistance R")
 
 
+def _adaptive_cases():
+    G = dict(np.load(os.path.join(GOLDEN, "vpp_adaptive_cases.npz")))
+    for i in range(int(G["n_cases"])):
+        k = f"a{i}_"
+        C, wsize, distance, bilateral, uniform, direction, o_i = [int(v) for v in G[k + "params"]]
+        l0, r0 = G[k + "l"], G[k + "r"]
+        kw = dict(wsize=wsize, wsizeAgg_x=16, wsizeAgg_y=3, left2right=bool(direction), blending=0.4, use_distance_patch=bool(distance),
+                  use_bilateral_patch=bool(bilateral), distance_gamma=0.3, bilateral_o_xy=2, bilateral_o_i=o_i, bilateral_th=.001,
+                  uniform_color=bool(uniform), c_occ=0.1, g_occ=G[k + "g_occ"])
+        yield i, G, k, (l0 if C == 3 else l0[..., 0]), (r0 if C == 3 else r0[..., 0]), kw
+
+
+def test_vpp_adaptive_cases(orc):
+    """vpp() with distance-based / bilateral adaptive patches: oracle against outputs recorded from the reference's numba code."""
+    for i, G, k, li, ri, kw in _adaptive_cases():
+        ln, rn = orc.vpp(li, ri, G[k + "g"], method="rnd", stream=G[k + "stream_numba"], mode=1, **kw)
+        assert_same(ln, G[k + "rnd_l"], f"adaptive case {i} rnd L"); assert_same(rn, G[k + "rnd_r"], f"adaptive case {i} rnd R")
+        lm, rm = orc.vpp(li, ri, G[k + "g"], method="maxDistance", mode=1, **kw)
+        assert_same(lm, G[k + "max_l"], f"adaptive case {i} maxDistance L"); assert_same(rm, G[k + "max_r"], f"adaptive case {i} maxDistance R")
+        if k + "filled" in G:
+            gray = orc.bgr2gray(G[k + "l"]) if G[k + "l"].shape[-1] == 3 else np.ascontiguousarray(G[k + "l"][..., 0])
+            assert_same(orc.bilateral_filling(G[k + "g"], gray, (kw["wsize"] - 1) // 2, 2, kw["bilateral_o_i"], .001), G[k + "filled"],
+                        f"adaptive case {i} bilateral filling")
+
+
 def test_libc_stream_matches_golden(golden_vpp):
     """the product's glibc rand() restatement (C-ABI host helper) regenerates the recorded libc streams"""
     from vppstereo_b200 import vpp_core_opt as core

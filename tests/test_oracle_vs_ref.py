@@ -122,3 +122,49 @@ def test_occlusion_heuristic_vs_reference(orc, R, shape, kind, density, fg, kw):
     d, c = orc.occlusion_heuristic(g, **kw)
     assert c_ref.dtype == np.uint8 and d_ref.dtype == np.float32
     assert_same(c, c_ref, "occlusion mask"); assert_same(d, d_ref, "filtered hints")
+
+
+@pytest.mark.parametrize("C,wsize,distance,bilateral,uniform,method", [
+    (3, 7, 1, 1, 0, "rnd"), (3, 5, 0, 1, 0, "rnd"), (1, 7, 1, 0, 1, "rnd"), (3, 9, 1, 1, 1, "rnd"),
+    (3, 7, 1, 1, 0, "maxDistance"), (1, 5, 0, 1, 1, "maxDistance"), (3, 5, 1, 0, 0, "maxDistance"),
+])
+def test_vpp_adaptive_patches_vs_reference(orc, R, C, wsize, distance, bilateral, uniform, method):
+    """TPAMI extensions of vpp() (distance-based patch size vpp_standalone.py:6-11, bilateral adaptive patch :371-394 and
+    the guards :153-154/:334-335): oracle against the reference's numba code, bit for bit, with numba's own random stream."""
+    from numba import njit
+    from vppstereo_b200 import synth
+
+    @njit
+    def nb_seed(s):
+        np.random.seed(s)
+
+    @njit
+    def nb_draw(n):
+        out = np.empty(n, np.uint8)
+        for i in range(n):
+            out[i] = np.random.randint(0, 256)
+        return out
+
+    S = R.vpp_standalone
+    H, W = 48, 96
+    p = synth.make_pair(40 + wsize, shape=(H, W), hints="random", channels=3, density=0.04, foreground=2)
+    l0 = p["left"][..., :C].copy(); r0 = p["right"][..., :C].copy()
+    g = (p["hints"] * 0.25).astype(np.float32)
+    g_occ = (np.random.default_rng(3).random((H, W)) < 0.2).astype(np.uint8)
+    li = l0 if C == 3 else l0[..., 0]; ri = r0 if C == 3 else r0[..., 0]
+    kw = dict(wsize=wsize, wsizeAgg_x=16, wsizeAgg_y=3, blending=0.4, use_distance_patch=bool(distance), use_bilateral_patch=bool(bilateral),
+              distance_gamma=0.3, bilateral_o_xy=2, bilateral_o_i=3, bilateral_th=.001, uniform_color=bool(uniform), method=method,
+              c_occ=0.1)
+    nb_seed(21); stn = nb_draw(orc.stream_length(g, wsize, C, uniform)); nb_seed(21)
+    la, ra = S.vpp(li, ri, g, g_occ=g_occ.astype(np.float32), **kw)
+    lb, rb = orc.vpp(li, ri, g, g_occ=g_occ, stream=stn, mode=1, **kw)
+    assert_same(lb, la, "left"); assert_same(rb, ra, "right")
+    assert (la != (l0 if C == 3 else l0)).any()
+    if bilateral:
+        gray = orc.bgr2gray(l0) if C == 3 else l0[..., 0]
+        import cv2
+        if C == 3:
+            assert_same(gray, cv2.cvtColor(l0, cv2.COLOR_BGR2GRAY), "BGR2GRAY")
+        want = S._bilateral_filling(g, gray, (wsize - 1) // 2, 2, 3, .001)
+        assert want.dtype == np.float64 and np.array_equal(want, want.astype(np.float32))      # float32 values in a float64 array
+        assert_same(orc.bilateral_filling(g, gray, (wsize - 1) // 2, 2, 3, .001), want.astype(np.float32), "bilateral filling")

@@ -23,7 +23,25 @@ struct VppArgs {
     int uniform, n, nax, nay, direction, discard, interpolate, arith;
     float c32, cocc32;
     double c64, cocc64;
+    // adaptive patches of vpp() (vpp_standalone.py:6-11,:153-154,:334-335); both NULL = fixed (2n+1)^2 patches
+    const float *filled;   // [frames][H][W] bilateral-filled hints: a patch pixel is kept iff |g - filled| < 0.1 (float64)
+    const float *thr;      // [frames][nthr] ascending disparity thresholds: patch size = 1 + #{k : g >= thr[k]}
+    int nthr;
 };
+
+// per-hint patch radius and per-pixel keep test of the adaptive modes
+__device__ __forceinline__ int patch_radius(const VppArgs &a, long f, float gv)
+{
+    if (!a.thr) return a.n;
+    int ws = 1;
+    for (int k = 0; k < a.nthr; k++) ws += gv >= a.thr[f * a.nthr + k];
+    return (ws - 1) >> 1;
+}
+__device__ __forceinline__ bool patch_keep(const VppArgs &a, long f, float gv, int yy, int xx)
+{
+    if (!a.filled) return true;
+    return fabs((double)gv - (double)a.filled[(f * a.H + yy) * a.W + xx]) < 0.1;
+}
 
 struct VppWs {
     uint16_t *hx;        // [n][H][W] hint columns of each row in scan order
@@ -504,6 +522,116 @@ static size_t vr_smem_bytes(int W, const RowsCfg &c)
     return (size_t)(4 * W + 1) * 4 + (size_t)c.cap_rec * 8 + (size_t)c.cap_hint * (4 + 4 + 2 + 1) + 16;
 }
 
+// ---- rnd with adaptive patches (per-hint radius, per-pixel keep test) -------------------------------------------
+// The pattern draw of a patch pixel only happens when the pixel is kept (vpp_standalone.py:334-340), so the stream position
+// of a draw is the number of kept in-image patch pixels before it.  Pass 1 counts them per hint (K_h) and scans them per
+// row (hpre, draws; vpp_scan_rows_kernel then gives the per-frame prefix); pass 2 is the ordered per-row replay.
+__global__ void __launch_bounds__(128) vpp_adaptive_counts_kernel(const float *__restrict__ g, VppWs ws, VppArgs a, long total_rows)
+{
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int W = a.W, H = a.H;
+    const int y = (int)(row % H);
+    const long f = row / H;
+    const int cnt = ws.cnt[row];
+    const uint16_t *hx = ws.hx + row * W;
+    long long run = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int k = base + lane;
+        int kept = 0;
+        if (k < cnt) {
+            const int x = hx[k];
+            const float gv = g[row * W + x];
+            const int nh = patch_radius(a, f, gv);
+            for (int yy = max(y - nh, 0); yy <= min(y + nh, H - 1); yy++)
+                for (int xx = max(x - nh, 0); xx <= min(x + nh, W - 1); xx++) kept += patch_keep(a, f, gv, yy, xx);
+        }
+        int incl = kept;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (k < cnt) ws.hpre[row * W + k] = (uint32_t)(run + incl - kept);
+        run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) ws.draws[row] = run;
+}
+
+__global__ void __launch_bounds__(128) vpp_rnd_adaptive_kernel(uint8_t *__restrict__ l, uint8_t *__restrict__ r,
+                                                               const float *__restrict__ g, const uint8_t *__restrict__ g_occ,
+                                                               const uint8_t *__restrict__ pattern,
+                                                               const int64_t *__restrict__ pattern_offsets, uint64_t rng_seed,
+                                                               VppWs ws, VppArgs a, long total)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int j = (int)(t % a.C);
+    const int yy = (int)((t / a.C) % a.H);
+    const long f = t / ((long)a.C * a.H);
+    const int W = a.W, H = a.H, n = a.n;
+    Splat s{a, l + ((f * H + yy) * W) * a.C + j, r + ((f * H + yy) * W) * a.C + j};
+    const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
+    const long long pat_len = pattern ? pattern_offsets[f + 1] - pattern_offsets[f] : 0;
+    const uint32_t frame_key = frame_key32(rng_seed, f);
+    for (int y = max(0, yy - n); y <= min(H - 1, yy + n); y++) {
+        const long row = f * H + y;
+        const int cnt = ws.cnt[row];
+        const uint16_t *hx = ws.hx + row * W;
+        const long long draw_base = ws.dbase[row], hint_prefix = ws.hbase[row], row_draws = ws.draws[row];
+        for (int k = 0; k < cnt; k++) {
+            const int x = hx[k];
+            const float gv = g[row * W + x];
+            const int nh = patch_radius(a, f, gv);
+            if (yy < y - nh || yy > y + nh) continue;
+            const bool occ = g_occ[row * W + x] != 0;
+            const HintGeom hg = hint_geom(a, gv, x);
+            const long long pre = ws.hpre[row * W + k];
+            const long long K = (k + 1 < cnt ? (long long)ws.hpre[row * W + k + 1] : row_draws) - pre;
+            const int xlo = max(x - nh, 0), xhi = min(x + nh, W - 1);
+            long long rank = 0;                            // kept pixels of the patch rows above the slice
+            for (int py = max(y - nh, 0); py < yy; py++)
+                for (int px = xlo; px <= xhi; px++) rank += patch_keep(a, f, gv, py, px);
+            long long idx = a.uniform ? (long long)a.C * (hint_prefix + k) + j : (long long)a.C * (draw_base + pre) + (long long)j * K + rank;
+            for (int xx = xlo; xx <= xhi; xx++) {
+                if (!patch_keep(a, f, gv, yy, xx)) continue;
+                const int xw = xx - x;
+                const uint8_t rv = pat ? ((idx >= 0 && idx < pat_len) ? pat[idx] : 0) : counter_pattern(frame_key, (uint32_t)idx);
+                if (!a.uniform) idx++;
+                splat_pixel<true>(s, (double)rv, xx, hg.xd0 + xw, hg.xd1 + xw, hg.xd + xw, occ, hg.b32, hg.b64);
+            }
+        }
+    }
+}
+
+// ---- _bilateral_filling (vpp_standalone.py:371-394): one thread per TARGET pixel ---------------------------------
+// The reference scatters from every hint, in raster order, to the pixels of its patch and keeps the largest weight (first
+// one on ties, cmap stored as float32 and compared as float64).  Gathering the candidate hints of one target in the same
+// raster order reproduces it exactly.  weights[((yw+n)*(2n+1) + (xw+n))*256 + |di|] = exp(-(r^2/(2 o_xy^2) + di^2/(2 o_i^2)))
+// is tabulated by the caller with the host's libm (the function numba calls), so no device exp() is involved.
+__global__ void __launch_bounds__(256) bilateral_filling_kernel(const float *__restrict__ dmap, const uint8_t *__restrict__ gray,
+                                                                float *__restrict__ out, int W, int H, int n,
+                                                                const double *__restrict__ weights, double th, long total)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int tx = (int)(t % W), ty = (int)((t / W) % H);
+    const long fo = (t / ((long)W * H)) * (long)W * H;
+    const int it = gray[t];
+    float cmap = 0.0f, aug = dmap[t];
+    const int side = 2 * n + 1;
+    for (int y = max(ty - n, 0); y <= min(ty + n, H - 1); y++)
+        for (int x = max(tx - n, 0); x <= min(tx + n, W - 1); x++) {
+            const float d = dmap[fo + (long)y * W + x];
+            if (!(d > 0.0f)) continue;
+            const int di = abs(it - (int)gray[fo + (long)y * W + x]);
+            const double w = weights[(((ty - y) + n) * side + ((tx - x) + n)) * 256 + di];
+            if ((double)cmap < w) { cmap = (float)w; aug = d; }
+        }
+    out[t] = ((double)cmap > th) ? aug : 0.0f;
+}
+
 // ---- maxDistance: one warp per (frame, channel), sequential over hints ------------------------------------------
 // fold of the ordered window samples into (pa, pb)  (pyx:216-313): lane p of a chunk holds window position
 // chunk*32+p with up to two samples (left first, then right).
@@ -621,12 +749,14 @@ __global__ void __launch_bounds__(32) vpp_max_dist_kernel(uint8_t *l, uint8_t *r
             const float gv = g[row * W + x];
             const bool occ = g_occ[row * W + x] != 0;
             const HintGeom hg = hint_geom(a, gv, x);
+            const int nh = patch_radius(a, f, gv);
             double pv = 0.0;
             if (a.uniform) pv = max_dist_colour(a, src, y, x, x - hg.xd, occ, true, lane);
-            for (int yw = -n; yw <= n; yw++) {
+            for (int yw = -nh; yw <= nh; yw++) {
                 if (y + yw < 0 || y + yw > H - 1) continue;
-                for (int xw = -n; xw <= n; xw++) {
+                for (int xw = -nh; xw <= nh; xw++) {
                     if (x + xw < 0 || x + xw > W - 1) continue;
+                    if (!patch_keep(a, f, gv, y + yw, x + xw)) continue;
                     if (!a.uniform) pv = max_dist_colour(a, src, y + yw, x + xw, x - hg.xd, occ, false, lane);
                     if (lane == 0) {
                         Splat s{a, limg + ((long)(y + yw) * W) * a.C + j, rimg + ((long)(y + yw) * W) * a.C + j};
@@ -887,12 +1017,14 @@ __global__ void __launch_bounds__(32) vpp_max_dist_wave_kernel(uint8_t *l, uint8
             }
             __syncwarp();
             const MdRegionSrc src{sL, sR, oy, ox, RW};
+            const int nh = patch_radius(a, f, gv);
             double pv = 0.0;
             if (a.uniform) pv = md_colour_region(a, src, y, x, shift, occ, true, lane);
-            for (int yw = -n; yw <= n; yw++) {
+            for (int yw = -nh; yw <= nh; yw++) {
                 if (y + yw < 0 || y + yw > H - 1) continue;
-                for (int xw = -n; xw <= n; xw++) {
+                for (int xw = -nh; xw <= nh; xw++) {
                     if (x + xw < 0 || x + xw > W - 1) continue;
+                    if (!patch_keep(a, f, gv, y + yw, x + xw)) continue;
                     if (!a.uniform) pv = md_colour_region(a, src, y + yw, x + xw, shift, occ, false, lane);
                     if (lane == 0) {
                         const int ry = y + yw - oy;
@@ -924,11 +1056,15 @@ __global__ void gt_reshape_kernel(const float *__restrict__ gt, VppWs ws, int W,
 }
 
 static int prepare_hints(const float *g, int W, int H, int n_patch, int direction, const VppWs &ws, int32_t *n_hints_out, int n,
-                         cudaStream_t st)
+                         cudaStream_t st, const VppArgs *adaptive = nullptr)
 {
     const long rows = (long)n * H;
     vpp_compact_rows_kernel<<<cdiv(rows * 32, 128), 128, 0, st>>>(g, ws, W, H, n_patch, direction, rows);
     VPP_LAUNCH_CHECK("vpp_compact_rows_kernel");
+    if (adaptive) {          // draws per hint = kept in-image patch pixels: recount (hpre, draws) before the row scan
+        vpp_adaptive_counts_kernel<<<cdiv(rows * 32, 128), 128, 0, st>>>(g, ws, *adaptive, rows);
+        VPP_LAUNCH_CHECK("vpp_adaptive_counts_kernel");
+    }
     vpp_scan_rows_kernel<<<cdiv((long)n * 32, 128), 128, 0, st>>>(ws, H, n, n_hints_out);
     VPP_LAUNCH_CHECK("vpp_scan_rows_kernel");
     return VPPB200_OK;
@@ -946,6 +1082,7 @@ static VppArgs make_args(int W, int H, int C, int uniform, int wsize, int wax, i
     a.W = W; a.H = H; a.C = C; a.uniform = uniform != 0; a.n = (wsize - 1) / 2; a.nax = (wax - 1) / 2; a.nay = (way - 1) / 2;
     a.direction = direction; a.discard = discard != 0; a.interpolate = interpolate != 0; a.arith = arith;
     a.c32 = (float)c; a.cocc32 = (float)c_occ; a.c64 = c; a.cocc64 = c_occ;
+    a.filled = nullptr; a.thr = nullptr; a.nthr = 0;
     return a;
 }
 
@@ -960,19 +1097,30 @@ extern "C" size_t vppb200_vpp_workspace_bytes(int H, int W, int C, int n)
     return vpp_ws_layout(H, W, n, nullptr, nullptr);
 }
 
-extern "C" int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
-                                    int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
-                                    int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
-                                    uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream)
+static int scan_rnd_impl(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                         int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                         int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                         uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream,
+                         const float *filled_g, const float *thresholds, int n_thresholds)
 {
     if (!l || !r || !g || !g_occ || (pattern && !pattern_offsets) || W <= 0 || H <= 0 || C <= 0 || n <= 0 || wsize < 1 || W > 65535 ||
-        (arith != 0 && arith != 1))
+        (arith != 0 && arith != 1) || (thresholds && n_thresholds != wsize - 1))
         return VPPB200_ERR_ARG;
     if (!workspace || workspace_bytes < vpp_ws_layout(H, W, n, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     VppWs ws;
     vpp_ws_layout(H, W, n, workspace, &ws);
     VppArgs a = make_args(W, H, C, uniform_color, wsize, 1, 1, direction, c, c_occ, discard_occluded, interpolate, arith);
+    if (filled_g || thresholds) {
+        // adaptive patches: recounted stream positions, ordered per-row replay with per-hint radius and keep test
+        a.filled = filled_g; a.thr = thresholds; a.nthr = thresholds ? n_thresholds : 0;
+        int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st, &a);
+        if (rc) return rc;
+        const long total = (long)n * H * C;
+        vpp_rnd_adaptive_kernel<<<cdiv(total, 128), 128, 0, st>>>(l, r, g, g_occ, pattern, pattern_offsets, rng_seed, ws, a, total);
+        VPP_LAUNCH_CHECK("vpp_rnd_adaptive_kernel");
+        return VPPB200_OK;
+    }
     int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st);
     if (rc) return rc;
     // per-pixel replay for every row it can take; the rows it flags go to the ordered per-row replay
@@ -996,13 +1144,45 @@ extern "C" int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int 
     return VPPB200_OK;
 }
 
-extern "C" int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
-                                         int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
-                                         const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
-                                         int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream)
+extern "C" int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                    int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                                    int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                                    uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream)
+{
+    return scan_rnd_impl(l, r, g, W, H, C, uniform_color, wsize, direction, c, c_occ, g_occ, discard_occluded, interpolate, arith,
+                         pattern, pattern_offsets, rng_seed, n_hints_out, workspace, workspace_bytes, n, stream, nullptr, nullptr, 0);
+}
+
+extern "C" int vppb200_vpp_scan_rnd_adaptive(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                             int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                                             int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                                             uint64_t rng_seed, const float *filled_g, const float *patch_thresholds,
+                                             int n_thresholds, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n,
+                                             void *stream)
+{
+    return scan_rnd_impl(l, r, g, W, H, C, uniform_color, wsize, direction, c, c_occ, g_occ, discard_occluded, interpolate, arith,
+                         pattern, pattern_offsets, rng_seed, n_hints_out, workspace, workspace_bytes, n, stream, filled_g,
+                         patch_thresholds, n_thresholds);
+}
+
+extern "C" int vppb200_bilateral_filling(const float *dmap, const uint8_t *gray, float *out, int W, int H, int n_patch,
+                                         const double *weights, double th, int n, void *stream)
+{
+    if (!dmap || !gray || !out || !weights || W <= 0 || H <= 0 || n_patch < 0 || n <= 0) return VPPB200_ERR_ARG;
+    const long total = (long)n * H * W;
+    bilateral_filling_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dmap, gray, out, W, H, n_patch, weights, th, total);
+    VPP_LAUNCH_CHECK("bilateral_filling_kernel");
+    return VPPB200_OK;
+}
+
+static int scan_max_dist_impl(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                              int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                              const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
+                              int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream,
+                              const float *filled_g, const float *thresholds, int n_thresholds)
 {
     if (!l || !r || !g || !g_occ || W <= 0 || H <= 0 || C <= 0 || n <= 0 || wsize < 1 || wsize_agg_x < 1 || wsize_agg_y < 1 ||
-        W > 65535 || (arith != 0 && arith != 1))
+        W > 65535 || (arith != 0 && arith != 1) || (thresholds && n_thresholds != wsize - 1))
         return VPPB200_ERR_ARG;
     if (!workspace || workspace_bytes < vpp_ws_layout(H, W, n, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1010,6 +1190,7 @@ extern "C" int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g,
     vpp_ws_layout(H, W, n, workspace, &ws);
     VppArgs a = make_args(W, H, C, uniform_color, wsize, wsize_agg_x, wsize_agg_y, direction, c, c_occ, discard_occluded,
                           interpolate, arith);
+    a.filled = filled_g; a.thr = thresholds; a.nthr = thresholds ? n_thresholds : 0;     // footprints stay those of the full patch
     int rc = prepare_hints(g, W, H, a.n, direction, ws, n_hints_out, n, st);
     if (rc) return rc;
     const int total = n * C;
@@ -1041,6 +1222,27 @@ extern "C" int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g,
     vpp_max_dist_kernel<<<total, 32, 0, st>>>(l, r, g, g_occ, ws, a, total);
     VPP_LAUNCH_CHECK("vpp_max_dist_kernel");
     return VPPB200_OK;
+}
+
+extern "C" int vppb200_vpp_scan_max_dist(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                         int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                                         const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
+                                         int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream)
+{
+    return scan_max_dist_impl(l, r, g, W, H, C, uniform_color, wsize, wsize_agg_x, wsize_agg_y, direction, c, c_occ, g_occ,
+                              discard_occluded, interpolate, arith, n_hints_out, workspace, workspace_bytes, n, stream, nullptr,
+                              nullptr, 0);
+}
+
+extern "C" int vppb200_vpp_scan_max_dist_adaptive(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color,
+                                                  int wsize, int wsize_agg_x, int wsize_agg_y, int direction, double c, double c_occ,
+                                                  const uint8_t *g_occ, int discard_occluded, int interpolate, int arith,
+                                                  const float *filled_g, const float *patch_thresholds, int n_thresholds,
+                                                  int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream)
+{
+    return scan_max_dist_impl(l, r, g, W, H, C, uniform_color, wsize, wsize_agg_x, wsize_agg_y, direction, c, c_occ, g_occ,
+                              discard_occluded, interpolate, arith, n_hints_out, workspace, workspace_bytes, n, stream, filled_g,
+                              patch_thresholds, n_thresholds);
 }
 
 extern "C" size_t vppb200_vpp_max_dist_workspace_bytes(int H, int W, int C, int wsize, int wsize_agg_y, int n)

@@ -86,7 +86,7 @@ def _check_views(l, r, g, g_occ, width, height, channels):
 
 
 def _scan(kind, l, r, g, width, height, channels, uniform_color, wsize, wagg, direction, c, c_occ, g_occ,
-          discard_occluded, interpolate, pattern, arith, device_rng_seed=None, want_counts=True):
+          discard_occluded, interpolate, pattern, arith, device_rng_seed=None, want_counts=True, adaptive=None):
     width, height, channels, wsize, direction = int(width), int(height), int(channels), int(wsize), int(direction)
     _check_views(l, r, g, g_occ, width, height, channels)
     torch = _lib.require_cuda()
@@ -110,10 +110,17 @@ def _scan(kind, l, r, g, width, height, channels, uniform_color, wsize, wagg, di
     counts = torch.empty(n, dtype=torch.int32, device=dev)
     # Cython receives c, c_occ as C float; numba as Python floats
     cc, co = float(c), float(c_occ)
+    filled, thr = adaptive if adaptive is not None else (None, None)
+    adaptive_on = filled is not None or thr is not None
+    n_thr = int(thr.shape[-1]) if thr is not None else 0
     with torch.cuda.device(dev):
         if kind == "rnd":
             pt = ot_off = None
             if device_rng_seed is None:
+                if adaptive_on and n > 1:
+                    raise ValueError("an explicit pattern with adaptive patches is supported for single frames only "
+                                     "(the draws per frame depend on the kept patch pixels); use the device generator")
+                # (adaptive patches consume at most the full-patch count: a longer pattern is fine)
                 per = draws_per_frame(gt.reshape(n, height, width), wsize, channels, bool(uniform_color))
                 offs = np.zeros(n + 1, np.int64)
                 offs[1:] = np.cumsum(per)
@@ -125,11 +132,25 @@ def _scan(kind, l, r, g, width, height, channels, uniform_color, wsize, wagg, di
                 if pt.numel() == 0:
                     pt = torch.zeros(1, dtype=torch.uint8, device=dev)
                 ot_off = torch.from_numpy(offs).to(dev)
-            rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
-                                        int(bool(uniform_color)), wsize, direction, C.c_double(cc), C.c_double(co),
-                                        _lib.ptr(ot), int(bool(discard_occluded)), int(bool(interpolate)), int(arith),
-                                        _lib.ptr(pt), _lib.ptr(ot_off), C.c_uint64(int(device_rng_seed or 0) & (2**64 - 1)),
-                                        _lib.ptr(counts), _lib.ptr(ws), C.c_size_t(ws.numel()), n, _lib.stream_ptr(dev))
+            if adaptive_on:
+                rc = L.vppb200_vpp_scan_rnd_adaptive(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
+                                                     int(bool(uniform_color)), wsize, direction, C.c_double(cc), C.c_double(co),
+                                                     _lib.ptr(ot), int(bool(discard_occluded)), int(bool(interpolate)), int(arith),
+                                                     _lib.ptr(pt), _lib.ptr(ot_off), C.c_uint64(int(device_rng_seed or 0) & (2**64 - 1)),
+                                                     _lib.ptr(filled), _lib.ptr(thr), n_thr, _lib.ptr(counts), _lib.ptr(ws),
+                                                     C.c_size_t(ws.numel()), n, _lib.stream_ptr(dev))
+            else:
+                rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
+                                            int(bool(uniform_color)), wsize, direction, C.c_double(cc), C.c_double(co),
+                                            _lib.ptr(ot), int(bool(discard_occluded)), int(bool(interpolate)), int(arith),
+                                            _lib.ptr(pt), _lib.ptr(ot_off), C.c_uint64(int(device_rng_seed or 0) & (2**64 - 1)),
+                                            _lib.ptr(counts), _lib.ptr(ws), C.c_size_t(ws.numel()), n, _lib.stream_ptr(dev))
+        elif adaptive_on:
+            rc = L.vppb200_vpp_scan_max_dist_adaptive(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
+                                                      int(bool(uniform_color)), wsize, int(wagg[0]), int(wagg[1]), direction,
+                                                      C.c_double(cc), C.c_double(co), _lib.ptr(ot), int(bool(discard_occluded)),
+                                                      int(bool(interpolate)), int(arith), _lib.ptr(filled), _lib.ptr(thr), n_thr,
+                                                      _lib.ptr(counts), _lib.ptr(ws), C.c_size_t(ws.numel()), n, _lib.stream_ptr(dev))
         else:
             rc = L.vppb200_vpp_scan_max_dist(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
                                              int(bool(uniform_color)), wsize, int(wagg[0]), int(wagg[1]), direction,
