@@ -235,6 +235,10 @@ int vppb200_occlusion_heuristic(const float *dmap, float *dmap_out, uint8_t *con
 int vppb200_u8hwc_to_f32chw(const uint8_t *src, float *dst, int H, int W, int C, int pad_top, int pad_bottom,
                             int pad_left, int pad_right, int n, void *stream);
 
+/* The other direction, test.py:158-159 and :210-212: float32 [n][C][H][W] in [0,1] -> uint8 [n][H][W][C] = (uint8)(255.0f * v)
+ * (float32 product, truncation), so the loader's normalised tensors reach vpp() / compute_rsgm() without a host hop. */
+int vppb200_f32chw_to_u8hwc(const float *src, uint8_t *dst, int H, int W, int C, int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,6 +253,23 @@ def test_kitti_shape_properties(mods, orc):
     assert np.median(np.abs(got[0] - gt)[sel]) < 4.0    # the synthetic right view is warped with d(u), not d(x)
 
 
+def test_middlebury_shape_vs_oracle(mods, orc):
+    """Full-resolution Middlebury shape (2880x1988 -> padded 2880x2000, D=192; SURVEY.md 8 sizes 'M'): VPP-projected pair
+    through compute_rsgm on device tensors, bit-exact against the oracle.  The frame spans an 18-CTA team in the sweeps."""
+    import torch
+    from vppstereo_b200 import vpp_standalone
+    rsgm, synth = mods[1], mods[2]
+    p = synth.make_pair(2, shape="M", hints="random")
+    pattern = np.random.default_rng(2).integers(0, 256, orc.stream_length(p["hints"], 3, 3, 0), dtype=np.uint8)
+    L, R, G = (torch.from_numpy(p[k]).cuda() for k in ("left", "right", "hints"))
+    lv, rv = vpp_standalone.vpp(L, R, G, pattern=pattern)
+    got = rsgm.compute_rsgm(L, lv, rv, dmax=192)
+    lw, rw = orc.vpp(p["left"], p["right"], p["hints"], stream=pattern, mode=1)
+    assert_same(lv.cpu().numpy(), lw, "VPP left"); assert_same(rv.cpu().numpy(), rw, "VPP right")
+    want = orc.compute_rsgm(p["left"], lw, rw, dmax=192)
+    assert_same(got.cpu().numpy(), want, "M-shape compute_rsgm")
+
+
 def test_pipeline_streaming_matches_synchronous(mods):
     """VppRsgmPipeline.submit_host/collect (copies overlapped on their own streams, two batches in flight) returns what the
     synchronous run_host returns for the same batches and pattern seeds."""

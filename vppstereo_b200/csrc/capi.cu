@@ -499,7 +499,27 @@ __global__ void u8hwc_to_f32chw_kernel(const uint8_t *__restrict__ src, float *_
     const uint8_t v = src[((f * H + sy) * W + sx) * C + c];
     dst[t] = (float)__ddiv_rn((double)v, 255.0);                                       // float32(u8 / 255.0)
 }
+
+// (255 * im).astype(np.uint8) of a [C,H,W] float32 image in HWC order (test.py:158-159,:210-212): float32 product, truncation
+__global__ void f32chw_to_u8hwc_kernel(const float *__restrict__ src, uint8_t *__restrict__ dst, int H, int W, int C, long total)
+{
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int c = (int)(t % C), x = (int)((t / C) % W), y = (int)((t / ((long)C * W)) % H);
+    const long f = t / ((long)C * W * H);
+    const float v = __fmul_rn(255.0f, src[((f * C + c) * H + y) * W + x]);
+    dst[t] = (uint8_t)(int)v;                       // values are in [0, 255]; the reference's cast is undefined outside
+}
 }  // namespace vppb200
+
+extern "C" int vppb200_f32chw_to_u8hwc(const float *src, uint8_t *dst, int H, int W, int C, int n, void *stream)
+{
+    if (!src || !dst || H <= 0 || W <= 0 || C <= 0 || n <= 0) return VPPB200_ERR_ARG;
+    const long total = (long)n * C * H * W;
+    f32chw_to_u8hwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, C, total);
+    VPP_LAUNCH_CHECK("f32chw_to_u8hwc_kernel");
+    return VPPB200_OK;
+}
 
 extern "C" int vppb200_u8hwc_to_f32chw(const uint8_t *src, float *dst, int H, int W, int C, int pad_top, int pad_bottom,
                                        int pad_left, int pad_right, int n, void *stream)

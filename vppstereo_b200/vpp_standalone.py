@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from . import vpp_core_opt as _core
 
-__all__ = ["vpp", "vpp_to_network"]
+__all__ = ["vpp", "vpp_to_network", "network_to_vpp", "sample_hints"]
 
 
 def vpp(left, right, gt, wsize=3, wsizeAgg_x=64, wsizeAgg_y=3, left2right=True, blending=0.4, use_distance_patch=False,
@@ -162,3 +162,30 @@ def vpp_to_network(img_u8, pad_to=32):
                                                  _lib.stream_ptr(t.device))
     _lib.check(rc, "vpp_to_network")
     return out, (pl, pr, pt, pb)
+
+
+def network_to_vpp(img_f32):
+    """float32 [C,H,W] / [N,C,H,W] CUDA tensor in [0,1] (the loader's normalised image) -> uint8 [H,W,C] / [N,H,W,C] =
+    (255*im.permute(1,2,0)).astype(np.uint8) of test.py:158-159,:210-212, on the device."""
+    torch = _lib.require_cuda()
+    t = _lib.as_device(img_f32, torch.float32)
+    single = t.dim() == 3
+    if single:
+        t = t[None]
+    t = t.contiguous()
+    N, Cn, H, W = t.shape
+    out = torch.empty((N, H, W, Cn), dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        rc = _lib.lib().vppb200_f32chw_to_u8hwc(_lib.ptr(t), _lib.ptr(out), H, W, Cn, N, _lib.stream_ptr(t.device))
+    _lib.check(rc, "network_to_vpp")
+    return out[0] if single else out
+
+
+def sample_hints(hints, validhints, probability=0.20, generator=None):
+    """losses.py:5-10 on whatever device the tensors live on (torch ops only: plumbing, no kernel of ours)."""
+    torch = _lib.torch_mod()
+    rnd = torch.rand(validhints.shape, dtype=torch.float32, device=validhints.device, generator=generator)
+    new_validhints = (validhints * (rnd < probability)).float()
+    new_hints = hints * new_validhints
+    new_hints[new_validhints == 0] = 0
+    return new_hints, new_validhints
