@@ -81,4 +81,19 @@ struct TailBufs { uint8_t *u8; int *label; int *count; };
 int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d, int subpixel, TailBufs tb, int n, cudaStream_t st);
 const float *device_rcp_lut(cudaStream_t st);   // library-owned table for this host CPU (lazy, per device)
 
+
+// t = (f * H + y) * W + x without 64-bit divisions (each costs ~100 instructions): 32-bit arithmetic whenever t fits
+__device__ __forceinline__ void split_fyx(long t, int W, int H, int &x, int &y, long &f)
+{
+    if (t < 0x7FFFFFFFL) {
+        const unsigned u = (unsigned)t, r = u / (unsigned)W, ff = r / (unsigned)H;
+        x = (int)(u - r * (unsigned)W); y = (int)(r - ff * (unsigned)H); f = (long)ff;
+    } else {
+        x = (int)(t % W); y = (int)((t / W) % H); f = t / ((long)W * H);
+    }
+}
+__device__ __forceinline__ int mod_w(long t, int W)
+{
+    return t < 0x7FFFFFFFL ? (int)((unsigned)t % (unsigned)W) : (int)(t % W);
+}
 }  // namespace vppb200

@@ -22,8 +22,9 @@ __global__ void pad_gray_kernel(const uint8_t *__restrict__ src, uint8_t *__rest
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const int x = (int)(t % d.Wp), y = (int)((t / d.Wp) % d.Hp);
-    const long f = t / ((long)d.Wp * d.Hp);
+    int x, y;
+    long f;
+    split_fyx(t, d.Wp, d.Hp, x, y, f);
     const int sy = reflect_idx(y - d.pt, d.H), sx = reflect_idx(x - d.pl, d.W);
     const uint8_t *p = src + ((f * d.H + sy) * d.W + sx) * d.C;
     uint32_t v;
@@ -38,12 +39,13 @@ __global__ void pad_flatbytes_kernel(const uint8_t *__restrict__ src, uint8_t *_
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const long np = (long)d.Wp * d.Hp;
-    const long f = t / np;
-    const long b = t % np;                     // byte index inside the padded interleaved buffer
-    const long px = b / d.C;
-    const int ch = (int)(b % d.C);
-    const int x = (int)(px % d.Wp), y = (int)(px / d.Wp);
+    int bx, by;                                // byte index inside the padded interleaved buffer = by * Wp + bx
+    long f;
+    split_fyx(t, d.Wp, d.Hp, bx, by, f);
+    const unsigned b = (unsigned)by * (unsigned)d.Wp + (unsigned)bx;
+    const unsigned px = b / (unsigned)d.C;
+    const int ch = (int)(b - px * (unsigned)d.C);
+    const int y = (int)(px / (unsigned)d.Wp), x = (int)(px - (unsigned)y * (unsigned)d.Wp);
     const int sy = reflect_idx(y - d.pt, d.H), sx = reflect_idx(x - d.pl, d.W);
     guide[t] = src[((f * d.H + sy) * d.W + sx) * d.C + ch];
 }
@@ -103,13 +105,15 @@ __global__ void __launch_bounds__(256) census5x5_kernel(const uint8_t *__restric
 {
     long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= total_quads) return;
-    const long f = q / quads_per_frame;
-    const long c0 = (q % quads_per_frame) * 4;         // flat index of the first of 4 centres (W % 16 == 0 => same row)
+    int qx, row;
+    long f;
+    split_fyx(q, W / 4, H, qx, row, f);                // (W % 16 == 0: the 4 centres share a row)
+    const int col = qx * 4;
+    const long c0 = (long)row * W + col;               // flat index of the first of 4 centres
     const long n = (long)W * H;
     const uint8_t *img = src + f * n;
     const long lo = 2L * W + 2, hi = (long)W * (H - 2) - 17;
     uint4 out = make_uint4(0, 0, 0, 0);
-    const int row = (int)(c0 / W), col = (int)(c0 % W);
     const bool any_body = (c0 + 3 >= lo) && (c0 <= hi);
     const bool tail_row = (row == H - 3) && (col >= W - 16);
     if (any_body || tail_row) {
@@ -386,7 +390,10 @@ __global__ void median3x3_kernel(const float *__restrict__ src, float *__restric
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const long n = (long)W * H;
-    const long c = t % n;
+    int cx, cy;
+    long cf;
+    split_fyx(t, W, H, cx, cy, cf);
+    const long c = (long)cy * W + cx;
     const float *s = src + (t - c);
     if (c < W + 1 || c > n - W - 5) { dst[t] = s[c]; return; }
     float v0 = s[c - W - 1], v1 = s[c - W], v2 = s[c - W + 1], v3 = s[c - 1], v4 = s[c], v5 = s[c + 1], v6 = s[c + W - 1],
@@ -471,8 +478,9 @@ __global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__r
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const int x = (int)(t % d.W), y = (int)((t / d.W) % d.H);
-    const long f = t / ((long)d.W * d.H);
+    int x, y;
+    long f;
+    split_fyx(t, d.W, d.H, x, y, f);
     const float *lrow = dl + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
     const float *rrow = dr + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
     float v = lrow[x];
@@ -553,7 +561,9 @@ __global__ void speckle_merge_kernel(const uint8_t *__restrict__ u8, int *label,
     if (t >= total) return;
     const int v = u8[t];
     if (!v) return;
-    const int x = (int)(t % W), y = (int)((t / W) % H);
+    int x, y;
+    long f_unused;
+    split_fyx(t, W, H, x, y, f_unused);
     if (y + 1 >= H) return;
     const int q = u8[t + W];
     if (!spk_conn(v, q)) return;
@@ -570,7 +580,7 @@ __global__ void speckle_count_kernel(const uint8_t *__restrict__ u8, int *label,
     if (t >= total) return;
     const int v = u8[t];
     if (!v) return;
-    const int x = (int)(t % W);
+    const int x = mod_w(t, W);
     const bool run_end = (x == W - 1) || !spk_conn(v, u8[t + 1]);
     if (!run_end) return;
     // first pixel of this run: a non-start pixel still holds it (row kernel); a start pixel's own label may already
@@ -594,8 +604,9 @@ __global__ void speckle_apply_kernel(const uint8_t *__restrict__ u8, const int *
     }
     float v = (float)b;
     if (subpixel && b) {
-        const int x = (int)(t % d.W), y = (int)((t / d.W) % d.H);
-        const long f = t / ((long)d.W * d.H);
+        int x, y;
+        long f;
+        split_fyx(t, d.W, d.H, x, y, f);
         v = dl[(f * d.Hp + y + d.pt) * d.Wp + d.pl + x];
     }
     out[t] = v;
