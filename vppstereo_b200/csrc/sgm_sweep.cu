@@ -275,7 +275,8 @@ __device__ __forceinline__ uint32_t &u4c(uint4 &v, int i) { return i == 0 ? v.x 
 // S8 ("byte partial sums", unguided costs only: C <= 24 and P2 <= 50 bound every L by 74 and a sweep's three paths by 222):
 // the sweeps do not read-modify-write a uint16 S; each writes its own uint8 volume in the cost volume's layout (MODE 0 -> a0,
 // the v-sweeps -> a1, a2) and MODE 2 adds the three to its own path on the fly.  Same integers, 37 % less DRAM traffic.
-template <int NW, int MODE, int DIR, bool S8>
+// FULLK: K2 == NW * 32, every lane's NW pairs are real disparities (no validity selects)
+template <int NW, int MODE, int DIR, bool S8, bool FULLK>
 __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__restrict__ img, const uint16_t *__restrict__ cost,
                                                             uint32_t *__restrict__ S, TL t, long total_rows,
                                                             float *__restrict__ disp_l, float *__restrict__ disp_r,
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     const uint16_t *arow[3] = {a0 + aoff, a1 + aoff, a2 + aoff};
     bool wv[NW];
 #pragma unroll
-    for (int j = 0; j < NW; j++) wv[j] = NW * lane + j < K2;
+    for (int j = 0; j < NW; j++) wv[j] = FULLK || NW * lane + j < K2;
     const int nchunks = W / 8;                      // W % 16 == 0
     const int xs = DIR > 0 ? 0 : W - 1;
     const int d0 = 2 * NW * lane;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     uint32_t bucket[2 * NW];                        // WTA right: best (cost << 16 | d) of the in-flight target pixels
 #pragma unroll
     for (int k = 0; k < 2 * NW; k++) bucket[k] = 0xFFFFFFFFu;
-    int step = 0;
+    int step = 0, ring = 0;
     for (int q = 0; q < nchunks; q++) {
         cp_async_wait<1>();
         __syncwarp();
@@ -381,8 +382,10 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             }
         }
         float out_l = 0.0f, out_r = 0.0f;            // lane p keeps the results of the chunk's pixel p
-        // per-warp scratch behind the stages: final S of the current and of the previous pixel (sub-pixel lookups)
-        uint32_t *scr = reinterpret_cast<uint32_t *>(hsm + (size_t)HWARPS * 2 * stage_b) + warp * 2 * K2;
+        // per-warp scratch behind the stages: final S of the current and of the previous pixel (sub-pixel lookups); a ring
+        // of three buffers, so the buffer written at step s+1 is not one a slower lane still reads at step s
+        uint32_t *scr = reinterpret_cast<uint32_t *>(hsm + (size_t)HWARPS * 2 * stage_b) + warp * 3 * K2;
+        const bool nomask = xlo >= D - 1;             // every d <= x in this chunk: the left arg-min needs no range mask
 #pragma unroll
         for (int pp = 0; pp < 8; pp++, step++) {
             const int p = DIR > 0 ? pp : 7 - pp;
@@ -434,13 +437,20 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                 // left: first arg-min over d <= min(D-1, x)
                 const int end = min(D - 1, x);
                 uint32_t m = 0xFFFFFFFFu;
+                if (nomask) {
 #pragma unroll
-                for (int k = 0; k < 2 * NW; k++) m = min(m, (d0 + k <= end) ? key[k] : 0xFFFFFFFFu);
+                    for (int k = 0; k < 2 * NW; k++) m = min(m, key[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 2 * NW; k++) m = min(m, (d0 + k <= end) ? key[k] : 0xFFFFFFFFu);
+                }
                 m = __reduce_min_sync(0xFFFFFFFFu, m);
                 const int best = (int)(m & 0xFFFFu);
                 float o = (float)best;
-                // final S of this pixel -> scratch (two buffers by step parity: the other one still holds pixel x+1)
-                uint32_t *sc = scr + (step & 1) * K2;
+                // final S of this pixel -> scratch (the previous buffer of the ring still holds pixel x+1)
+                uint32_t *sc = scr + ring * K2;
+                const uint32_t *sc_prev = scr + (ring == 0 ? 2 : ring - 1) * K2;
+                ring = ring == 2 ? 0 : ring + 1;
 #pragma unroll
                 for (int j = 0; j < NW; j++) if (wv[j]) sc[NW * lane + j] = fin[j];
                 __syncwarp();
@@ -449,14 +459,13 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                         const uint16_t *s16 = reinterpret_cast<const uint16_t *>(sc);
                         const int c0 = s16[best - 1], c1 = (int)(m >> 16);
                         // best = D-1 reads the next pixel's d = 0 (xyd stream order)
-                        const int c2 = best + 1 < D ? s16[best + 1] : reinterpret_cast<const uint16_t *>(scr + ((step & 1) ^ 1) * K2)[0];
+                        const int c2 = best + 1 < D ? s16[best + 1] : reinterpret_cast<const uint16_t *>(sc_prev)[0];
                         const int lower = min(c1 - c0, c1 - c2);            // <= 0
                         o = __fadd_rn((float)best, __fmul_rn((float)(c2 - c0), lut[-lower]));
                     } else {
                         o = -10.0f;
                     }
                 }
-                __syncwarp();
                 if (lane == p) out_l = o;
                 // right: every in-flight target absorbs its disparity slot, slot 0 retires to disp_r[x]
 #pragma unroll
@@ -513,8 +522,8 @@ static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const 
     const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
     const size_t stage = S8 ? (size_t)t.K2 * HCROW * (MODE == 2 ? 4 : 1) : h_stage_bytes(t.K2);
-    const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * 2 * t.K2 * 4 : 0);
-    auto kern = sgm_h_kernel<NW, MODE, DIR, S8>;
+    const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * 3 * t.K2 * 4 : 0);
+    auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, S8, true> : sgm_h_kernel<NW, MODE, DIR, S8, false>;
     if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows, dl, dr, lut, bv.a0, bv.a1, bv.a2);
     VPP_LAUNCH_CHECK("sgm_h_kernel");
