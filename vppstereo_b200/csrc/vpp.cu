@@ -485,11 +485,7 @@ __global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict
     const uint32_t pat_len = pattern ? (uint32_t)min((long long)0xFFFFFFFFll, (long long)(pattern_offsets[f + 1] - pattern_offsets[f])) : 0u;
     const uint32_t frame_key = frame_key32(rng_seed, f);
     const int items = s_nact * C;
-    for (int it = tid; it < items; it += VR_NT) {
-        const int t = (int)act[it / C], j = it % C;
-        const int k0 = (int)offs[t], k1 = (int)offs[t + 1];
-        uint8_t *px = (t < W ? l + (fr * W + t) * C : r + (fr * W + (t - W)) * C) + j;
-        uint32_t v = *px;
+    auto replay = [&](uint32_t v, int k0, int k1, int j) -> uint32_t {
         for (int i = k0; i < k1; i++) {
             const unsigned long long rec = recs[i];
             const uint32_t key = (uint32_t)(rec >> 32);
@@ -513,7 +509,29 @@ __global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict
                 }
             }
         }
-        *px = (uint8_t)v;
+        return v;
+    };
+    // the (pixel, channel) items are distinct bytes: four pixel loads in flight per thread instead of one
+    constexpr int RB = 4;
+    for (int it0 = tid; it0 < items; it0 += VR_NT * RB) {
+        uint8_t *px[RB];
+        uint32_t v[RB];
+        int k0[RB], k1[RB], jj[RB];
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int it = it0 + u * VR_NT;
+            px[u] = nullptr; v[u] = 0; k0[u] = k1[u] = jj[u] = 0;
+            if (it < items) {
+                const int t = (int)act[it / C];
+                jj[u] = it % C;
+                k0[u] = (int)offs[t]; k1[u] = (int)offs[t + 1];
+                px[u] = (t < W ? l + (fr * W + t) * C : r + (fr * W + (t - W)) * C) + jj[u];
+                v[u] = *px[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; u++)
+            if (px[u]) *px[u] = (uint8_t)replay(v[u], k0[u], k1[u], jj[u]);
     }
 }
 
