@@ -31,7 +31,7 @@ H, W, C, D = 375, 1242, 3, 192
 HP, WP = 384, 1248
 ALG_BYTES_AGG = 4 * WP * HP * D + WP * HP            # aggregate, per frame (368.5 MB)
 ALG_BYTES_VSWEEP = 5 * WP * HP * D + WP * HP         # one v-sweep launch, per frame: uint8 costs in, uint16 S in and out (460 MB)
-NCU_TRAFFIC_VSWEEP = 29.388e9                        # dram read+write per launch, profiles/r01_summary_v3.md (ncu --set full, batch 64)
+NCU_TRAFFIC_VSWEEP = 29.395e9                        # dram read+write per launch, profiles/r01_summary_v4.md (ncu --set full, batch 64)
 ALG_BYTES_VPP = 4 * H * W * C + 4 * H * W + H * W    # + C * in-image patch pixels of the hints (added at run time)
 STAGES = ["pad_gray", "census", "cost_volume", "sgm_h_fwd", "sgm_v_down", "sgm_v_up", "sgm_h_bwd_wta", "wta_unfused", "median_interp",
           "tail"]
