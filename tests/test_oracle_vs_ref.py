@@ -168,3 +168,30 @@ def test_vpp_adaptive_patches_vs_reference(orc, R, C, wsize, distance, bilateral
         want = S._bilateral_filling(g, gray, (wsize - 1) // 2, 2, 3, .001)
         assert want.dtype == np.float64 and np.array_equal(want, want.astype(np.float32))      # float32 values in a float64 array
         assert_same(orc.bilateral_filling(g, gray, (wsize - 1) // 2, 2, 3, .001), want.astype(np.float32), "bilateral filling")
+
+
+def test_vpp_random_flag_space_vs_reference(orc, R):
+    """Seeded random sweep over the signature of vpp() (tests/fuzz_vpp.py): oracle against the reference's numba code with
+    numba's own random stream."""
+    from numba import njit
+    import fuzz_vpp
+
+    @njit
+    def nb_seed(s):
+        np.random.seed(s)
+
+    @njit
+    def nb_draw(n):
+        out = np.empty(n, np.uint8)
+        for i in range(n):
+            out[i] = np.random.randint(0, 256)
+        return out
+
+    S = R.vpp_standalone
+    for i, li, ri, g, g_occ, stream, kw in fuzz_vpp.cases(40, 77, max_hw=(40, 100)):
+        if not (g > 0).any():
+            continue
+        nb_seed(i); st = nb_draw(stream.size); nb_seed(i)
+        la, ra = S.vpp(li, ri, g, g_occ=g_occ.astype(np.float32), **kw)
+        lb, rb = orc.vpp(li, ri, g, g_occ=g_occ, stream=st, mode=1, **kw)
+        assert_same(lb, la, f"case {i} left {kw}"); assert_same(rb, ra, f"case {i} right {kw}")
