@@ -249,6 +249,10 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = None
+    if os.environ.get("VPPB200_NUMA_BIND", "1") != "0":
+        from vppstereo_b200.dist import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local_rank)      # before the pinned staging buffers are allocated
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -386,6 +390,7 @@ def main():
             "config": {"workload": "configs[1]: KITTI-shape 1242x375x3 pairs, LiDAR-like 5% hints, VPP rnd 3x3 blending 0.4 + rSGM D=192, batch 64 per GPU",
                        "batch_per_gpu": B, "frames_per_step": world * B, "l2": "inputs per step (298 MB) and cost volumes (17.7 GB) exceed the 126 MB L2",
                        "collective": "all_gather of disparities per step" if world > 1 else "none",
+                       "host_affinity": f"GPU-local NUMA cores ({len(numa_cpus)})" if numa_cpus else "unchanged",
                        "overlap": "three-phase software pipeline across steps on three streams: front(k+1) = VPP + pad/gray/census/cost volume, main(k) = SGM sweeps + WTA, tail(k-1) = median..fills; two buffer sets; right-image branches on side streams",
                        "stage_ms_per_step_serial": {k: round(v, 3) for k, v in stage_ms.items()}, "vpp_ms_per_step": round(vpp_ms, 3),
                        "rsgm_fps": B / (rsgm_ms * 1e-3), "vpp_pairs_per_s": B / (vpp_ms * 1e-3), "check_mean_disp": check_val},

@@ -70,3 +70,29 @@ def run_sharded(n_frames, make_inputs, process, chunk=16, group=None, gather=Tru
     if local is None:
         raise ValueError("a rank received no frames: use n_frames >= world_size")
     return gather_frames(local, n_frames, group=group) if gather else local
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process (and therefore the pinned host buffers it allocates next: first-touch placement) to the CPU cores
+    that are local to GPU `device_index` (NVML's ideal CPU affinity).  With one process per GPU the host<->device copies of
+    the end-to-end path then stay on the GPU's own socket instead of crossing the inter-socket link.  Returns the cores bound
+    to, or None when NVML / the cpuset does not allow it (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = device_index
+        if vis:
+            ent = vis.split(",")[device_index].strip()
+            phys = int(ent) if ent.isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(os.cpu_count() or 1, 1) + 63) // 64)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus = sorted(ideal & set(os.sched_getaffinity(0)))
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
