@@ -544,12 +544,25 @@ __device__ __forceinline__ int uf_find_compress(int *L, int i)
     while (i != r) { const int nx = L[i]; L[i] = r; i = nx; }   // only used when no union runs concurrently
     return r;
 }
+// find with path halving.  Parent pointers only ever decrease (the larger root is linked under the smaller one), so
+// L[i] = grandparent always stores a valid ancestor; racing with a concurrent union it can at worst undo a link that
+// union's own retry loop re-establishes (the scheme of ECL-CC).
+__device__ __forceinline__ int uf_find_halve(int *L, int i)
+{
+    int p = L[i];
+    while (p != i) {
+        const int gp = L[p];
+        if (gp != p) L[i] = gp;
+        i = p; p = gp;
+    }
+    return i;
+}
 __device__ __forceinline__ void uf_union(int *L, int a, int b)
 {
     bool done = false;
     while (!done) {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
+        a = uf_find_halve(L, a);
+        b = uf_find_halve(L, b);
         if (a < b) { int old = atomicMin(&L[b], a); done = (old == b); b = old; }
         else if (b < a) { int old = atomicMin(&L[a], b); done = (old == a); a = old; }
         else done = true;
