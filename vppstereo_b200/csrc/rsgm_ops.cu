@@ -17,51 +17,72 @@ __device__ __forceinline__ int reflect_idx(int p, int len)
     return p;
 }
 
-// gray[n][Hp][Wp]; OpenCV 4.13 RGB2GRAY = (R*9798 + G*19235 + B*3735 + 16384) >> 15
-__global__ void pad_gray_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ gray, RsgmDims d, long total)
+// gray[n][Hp][Wp]; OpenCV 4.13 RGB2GRAY = (R*9798 + G*19235 + B*3735 + 16384) >> 15.
+// One thread = 4 adjacent output pixels of one padded row (Wp % 16 == 0), one 4-byte store; grid.y = frame * Hp + row.
+__global__ void __launch_bounds__(128) pad_gray_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ gray, RsgmDims d)
 {
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    int x, y;
-    long f;
-    split_fyx(t, d.Wp, d.Hp, x, y, f);
-    const int sy = reflect_idx(y - d.pt, d.H), sx = reflect_idx(x - d.pl, d.W);
-    const uint8_t *p = src + ((f * d.H + sy) * d.W + sx) * d.C;
-    uint32_t v;
-    if (d.C == 3) v = (p[0] * 9798u + p[1] * 19235u + p[2] * 3735u + 16384u) >> 15;
-    else v = p[0];
-    gray[t] = (uint8_t)v;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 >= d.Wp) return;
+    const long frow = blockIdx.y;                                  // f * Hp + y
+    const int y = (int)(frow % d.Hp);
+    const long f = frow / d.Hp;
+    const int sy = reflect_idx(y - d.pt, d.H);
+    const uint8_t *row = src + ((f * d.H + sy) * (long)d.W) * d.C;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int sx = reflect_idx(q * 4 + i - d.pl, d.W);
+        const uint8_t *p = row + (long)sx * d.C;
+        uint32_t v;
+        if (d.C == 3) v = (p[0] * 9798u + p[1] * 19235u + p[2] * 3735u + 16384u) >> 15;
+        else v = p[0];
+        out |= (v & 255u) << (8 * i);
+    }
+    reinterpret_cast<uint32_t *>(gray + frow * d.Wp)[q] = out;
 }
 
 // guide[n][Hp*Wp] = the first Hp*Wp BYTES of the padded interleaved image (RSGM/pyrSGM.cpp:586-588 reads a colour
-// buffer as if it were gray).
-__global__ void pad_flatbytes_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ guide, RsgmDims d, long total)
+// buffer as if it were gray).  One thread = 4 adjacent bytes (Hp*Wp % 4 == 0); grid.y = frame.
+__global__ void __launch_bounds__(128) pad_flatbytes_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ guide, RsgmDims d)
 {
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    int bx, by;                                // byte index inside the padded interleaved buffer = by * Wp + bx
-    long f;
-    split_fyx(t, d.Wp, d.Hp, bx, by, f);
-    const unsigned b = (unsigned)by * (unsigned)d.Wp + (unsigned)bx;
-    const unsigned px = b / (unsigned)d.C;
-    const int ch = (int)(b - px * (unsigned)d.C);
-    const int y = (int)(px / (unsigned)d.Wp), x = (int)(px - (unsigned)y * (unsigned)d.Wp);
-    const int sy = reflect_idx(y - d.pt, d.H), sx = reflect_idx(x - d.pl, d.W);
-    guide[t] = src[((f * d.H + sy) * d.W + sx) * d.C + ch];
+    const unsigned np = (unsigned)d.Wp * (unsigned)d.Hp;
+    const unsigned b0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;   // byte index inside the padded interleaved buffer
+    if (b0 >= np) return;
+    const long f = blockIdx.y;
+    const uint8_t *img = src + f * (long)d.H * d.W * d.C;
+    uint32_t out = 0;
+    unsigned px = b0 / (unsigned)d.C, ch = b0 - px * (unsigned)d.C;
+    unsigned y = px / (unsigned)d.Wp, x = px - y * (unsigned)d.Wp;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int sy = reflect_idx((int)y - d.pt, d.H), sx = reflect_idx((int)x - d.pl, d.W);
+        out |= (uint32_t)img[((long)sy * d.W + sx) * d.C + ch] << (8 * i);
+        if (++ch == (unsigned)d.C) { ch = 0; if (++x == (unsigned)d.Wp) { x = 0; y++; } }
+    }
+    reinterpret_cast<uint32_t *>(guide + f * (long)np)[b0 >> 2] = out;
 }
 
 int launch_pad_gray(const uint8_t *src, uint8_t *gray, const RsgmDims &d, int n, cudaStream_t st)
 {
-    long total = (long)n * d.Hp * d.Wp;
-    pad_gray_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, gray, d, total);
-    VPP_LAUNCH_CHECK("pad_gray_kernel");
+    const long rows = (long)n * d.Hp;
+    if (d.Hp > 65535) return VPPB200_ERR_ARG;
+    // grid.y is limited to 65535 rows: whole frames per launch
+    for (long r0 = 0; r0 < rows; r0 += 65535 / d.Hp * (long)d.Hp) {      // whole frames per launch
+        const long fr = r0 / d.Hp, nf = std::min((long)(65535 / d.Hp), n - fr);
+        pad_gray_kernel<<<dim3(cdiv(d.Wp / 4, 128), (unsigned)(nf * d.Hp)), 128, 0, st>>>(src + fr * (long)d.H * d.W * d.C,
+                                                                                      gray + fr * (long)d.Hp * d.Wp, d);
+        VPP_LAUNCH_CHECK("pad_gray_kernel");
+    }
     return VPPB200_OK;
 }
 int launch_pad_flatbytes(const uint8_t *src, uint8_t *guide, const RsgmDims &d, int n, cudaStream_t st)
 {
-    long total = (long)n * d.Hp * d.Wp;
-    pad_flatbytes_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, guide, d, total);
-    VPP_LAUNCH_CHECK("pad_flatbytes_kernel");
+    const long np = (long)d.Hp * d.Wp;
+    for (int f0 = 0; f0 < n; f0 += 65535) {
+        const int nf = std::min(65535, n - f0);
+        pad_flatbytes_kernel<<<dim3(cdiv(np / 4, 128), nf), 128, 0, st>>>(src + f0 * (long)d.H * d.W * d.C, guide + f0 * np, d);
+        VPP_LAUNCH_CHECK("pad_flatbytes_kernel");
+    }
     return VPPB200_OK;
 }
 
