@@ -406,19 +406,8 @@ int launch_subpixel(const uint16_t *S, float *disp, int W, int H, int D, int met
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cswap(float &a, float &b) { float t = fminf(a, b); b = fmaxf(a, b); a = t; }
 
-__global__ void median3x3_kernel(const float *__restrict__ src, float *__restrict__ dst, int W, int H, long total)
+__device__ __forceinline__ float median9(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, float v8)
 {
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const long n = (long)W * H;
-    int cx, cy;
-    long cf;
-    split_fyx(t, W, H, cx, cy, cf);
-    const long c = (long)cy * W + cx;
-    const float *s = src + (t - c);
-    if (c < W + 1 || c > n - W - 5) { dst[t] = s[c]; return; }
-    float v0 = s[c - W - 1], v1 = s[c - W], v2 = s[c - W + 1], v3 = s[c - 1], v4 = s[c], v5 = s[c + 1], v6 = s[c + W - 1],
-          v7 = s[c + W], v8 = s[c + W + 1];
     cswap(v1, v2); cswap(v4, v5); cswap(v7, v8);
     cswap(v0, v1); cswap(v3, v4); cswap(v6, v7);
     cswap(v1, v2); cswap(v4, v5); cswap(v7, v8);
@@ -426,13 +415,48 @@ __global__ void median3x3_kernel(const float *__restrict__ src, float *__restric
     cswap(v3, v6); cswap(v1, v4); cswap(v2, v5);
     cswap(v4, v7); cswap(v4, v2); cswap(v6, v4);
     cswap(v4, v2);
-    dst[t] = v4;
+    return v4;
+}
+
+// one thread = 4 adjacent flat positions (W % 16 == 0, so W*H % 4 == 0): three 6-float windows, one float4 store; grid.y = frame
+__global__ void __launch_bounds__(256) median3x3_kernel(const float *__restrict__ src, float *__restrict__ dst, int W, int H)
+{
+    const long n = (long)W * H;
+    const long c0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c0 >= n) return;
+    const float *s = src + (long)blockIdx.y * n;
+    const float4 mid = *reinterpret_cast<const float4 *>(s + c0);
+    float4 out = mid;
+    if (c0 + 3 >= W + 1 && c0 <= n - W - 5) {
+        // rows above / below exist for every position of the quad that is filtered (positions outside [W+1, n-W-5] keep
+        // `mid`); the two flat neighbours beside the quad may lie outside the frame only for quads that are not filtered there
+        const long up = c0 - W, dn = c0 + W;
+        const bool has_up = up >= 0, has_dn = dn + 3 < n;
+        float a[6], b[6], c[6];
+        const float4 u4 = has_up ? *reinterpret_cast<const float4 *>(s + up) : make_float4(0, 0, 0, 0);
+        const float4 d4 = has_dn ? *reinterpret_cast<const float4 *>(s + dn) : make_float4(0, 0, 0, 0);
+        a[0] = (has_up && up >= 1) ? s[up - 1] : 0.0f; a[1] = u4.x; a[2] = u4.y; a[3] = u4.z; a[4] = u4.w; a[5] = has_up ? s[up + 4] : 0.0f;
+        b[0] = c0 >= 1 ? s[c0 - 1] : 0.0f; b[1] = mid.x; b[2] = mid.y; b[3] = mid.z; b[4] = mid.w; b[5] = c0 + 4 < n ? s[c0 + 4] : 0.0f;
+        c[0] = has_dn ? s[dn - 1] : 0.0f; c[1] = d4.x; c[2] = d4.y; c[3] = d4.z; c[4] = d4.w; c[5] = (has_dn && dn + 4 < n) ? s[dn + 4] : 0.0f;
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const long cc = c0 + i;
+            r[i] = (cc < W + 1 || cc > n - W - 5) ? b[i + 1]
+                                                  : median9(a[i], a[i + 1], a[i + 2], b[i], b[i + 1], b[i + 2], c[i], c[i + 1], c[i + 2]);
+        }
+        out = make_float4(r[0], r[1], r[2], r[3]);
+    }
+    *reinterpret_cast<float4 *>(dst + (long)blockIdx.y * n + c0) = out;
 }
 int launch_median(const float *src, float *dst, int W, int H, int n, cudaStream_t st)
 {
-    long total = (long)n * W * H;
-    median3x3_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, dst, W, H, total);
-    VPP_LAUNCH_CHECK("median3x3_kernel");
+    if (W % 4) return VPPB200_ERR_WIDTH;                       // (the operator requires W % 16 == 0 anyway)
+    for (int f0 = 0; f0 < n; f0 += 65535) {
+        const int nf = std::min(65535, n - f0);
+        median3x3_kernel<<<dim3(cdiv((long)W * H / 4, 256), nf), 256, 0, st>>>(src + f0 * (long)W * H, dst + f0 * (long)W * H, W, H);
+        VPP_LAUNCH_CHECK("median3x3_kernel");
+    }
     return VPPB200_OK;
 }
 
