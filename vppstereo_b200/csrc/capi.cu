@@ -142,7 +142,7 @@ static size_t rsgm_ws_layout(const RsgmDims &d, int n, int sets, int set, void *
     size_t off = 0;
     char *b = (char *)base;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? b + o : (char *)nullptr; };
-    const size_t np = (size_t)n * d.Hp * d.Wp, nc = (size_t)n * d.H * d.W;
+    const size_t np = (size_t)n * d.Hp * d.Wp, nc = (size_t)n * d.H * tail_stride(d.W);
     RsgmWs w;
     w.gray_l = (uint8_t *)take(np); w.gray_r = (uint8_t *)take(np);
     w.census_l = (uint32_t *)take(np * 4); w.census_r = (uint32_t *)take(np * 4);

@@ -77,7 +77,8 @@ int launch_wta_right(const uint16_t *S, float *disp, int W, int H, int D, int n,
 int launch_subpixel(const uint16_t *S, float *disp, int W, int H, int D, int method, const float *lut, int n, cudaStream_t st);
 int launch_median(const float *src, float *dst, int W, int H, int n, cudaStream_t st);
 int launch_interp_clip(float *disp, int W, int H, int n, cudaStream_t st);   // _linear_interpolate(.,15,3) + clip>=0
-struct TailBufs { uint8_t *u8; int *label; int *count; };
+struct TailBufs { uint8_t *u8; int *label; int *count; };       // rows of tail_stride(W) elements
+static inline int tail_stride(int W) { return (W + 3) & ~3; }
 int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d, int subpixel, TailBufs tb, int n, cudaStream_t st);
 const float *device_rcp_lut(cudaStream_t st);   // library-owned table for this host CPU (lazy, per device)
 

@@ -518,8 +518,9 @@ int launch_interp_clip(float *disp, int W, int H, int n, cudaStream_t st)
 // tail of compute_rsgm on the cropped H x W frame (models/rsgm/rsgm.py:275-292)
 // ------------------------------------------------------------------------------------------------------------
 // crop + _left_right_check(th=1) + zero mask==128 + astype(uint8)
+// (u8, label and count rows have the stride Ws = W rounded up to 4, pad bytes 0, so that the speckle kernels can read words)
 __global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__restrict__ dr, uint8_t *__restrict__ u8,
-                                  RsgmDims d, long total)
+                                  RsgmDims d, int Ws, long total)
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
@@ -539,7 +540,9 @@ __global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__r
             v = 0.0f;
         }
     }
-    u8[t] = (uint8_t)v;
+    u8[(f * d.H + y) * Ws + x] = (uint8_t)v;
+    if (x == d.W - 1)
+        for (int xp = d.W; xp < Ws; xp++) u8[(f * d.H + y) * Ws + xp] = 0;
 }
 
 // cv2.filterSpeckles(img, 0, 200, 10) (rsgm.py:285): 4-connected components under |a-b| <= 10 among non-zero pixels,
@@ -551,12 +554,12 @@ __global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__r
 __device__ __forceinline__ bool spk_conn(int a, int b) { return a && b && abs(a - b) <= 10; }
 
 __global__ void __launch_bounds__(128) speckle_rows_kernel(const uint8_t *__restrict__ u8, int *__restrict__ label,
-                                                           int *__restrict__ count, int W, long total_rows)
+                                                           int *__restrict__ count, int W, int Ws, long total_rows)
 {
     const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= total_rows) return;
     const int lane = threadIdx.x & 31;
-    const long base = row * W;
+    const long base = row * Ws;
     int carry = 0;                                   // run start of the last pixel of the previous chunk
     for (int x0 = 0; x0 < W; x0 += 32) {
         const int x = x0 + lane;
@@ -613,60 +616,81 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b)
         else done = true;
     }
 }
-__global__ void speckle_merge_kernel(const uint8_t *__restrict__ u8, int *label, int W, int H, long total)
+// one thread = 4 adjacent pixels of a row: the row's word, the word below and the two bytes to their left
+__global__ void __launch_bounds__(256) speckle_merge_kernel(const uint8_t *__restrict__ u8, int *label, int W, int Ws, int H, long total_quads)
 {
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int v = u8[t];
-    if (!v) return;
-    int x, y;
-    long f_unused;
-    split_fyx(t, W, H, x, y, f_unused);
-    if (y + 1 >= H) return;
-    const int q = u8[t + W];
-    if (!spk_conn(v, q)) return;
-    if (x > 0) {
-        // the same pair of runs is already linked through the column to the left
-        const int vl = u8[t - 1], ql = u8[t + W - 1];
-        if (spk_conn(vl, v) && spk_conn(ql, q) && spk_conn(vl, ql)) return;
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total_quads) return;
+    const unsigned qpr = (unsigned)Ws >> 2;                    // (the launcher guarantees total_quads < 2^31)
+    const long row = (long)((unsigned)q / qpr);
+    const int x0 = (int)((unsigned)q - (unsigned)row * qpr) * 4;
+    if ((int)(row % H) + 1 >= H) return;
+    const long t0 = row * Ws + x0;
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(u8 + t0);
+    if (!w0) return;
+    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(u8 + t0 + Ws);
+    if (!w1) return;
+    int vl = x0 > 0 ? u8[t0 - 1] : 0, ql = x0 > 0 ? u8[t0 + Ws - 1] : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int v = (w0 >> (8 * i)) & 255, qv = (w1 >> (8 * i)) & 255;
+        // (x > 0: the same pair of runs is already linked through the column to the left)
+        if (spk_conn(v, qv) && !(x0 + i > 0 && spk_conn(vl, v) && spk_conn(ql, qv) && spk_conn(vl, ql)))
+            uf_union(label, label[t0 + i], label[t0 + Ws + i]);
+        vl = v; ql = qv;
     }
-    uf_union(label, label[t], label[t + W]);
 }
-__global__ void speckle_count_kernel(const uint8_t *__restrict__ u8, int *label, int *count, int W, long total)
+__global__ void __launch_bounds__(256) speckle_count_kernel(const uint8_t *__restrict__ u8, int *label, int *count, int W, int Ws, long total_quads)
 {
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int v = u8[t];
-    if (!v) return;
-    const int x = mod_w(t, W);
-    const bool run_end = (x == W - 1) || !spk_conn(v, u8[t + 1]);
-    if (!run_end) return;
-    // first pixel of this run: a non-start pixel still holds it (row kernel); a start pixel's own label may already
-    // point at another run's root, so a one-pixel run must not read its length from it
-    const bool is_start = (x == 0) || !spk_conn(u8[t - 1], v);
-    const int start = is_start ? (int)t : label[t];
-    const int root = uf_find_compress(label, start);
-    atomicAdd(&count[root], (int)(t - start) + 1);
+    const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total_quads) return;
+    const unsigned qpr = (unsigned)Ws >> 2;                    // (the launcher guarantees total_quads < 2^31)
+    const long row = (long)((unsigned)q / qpr);
+    const int x0 = (int)((unsigned)q - (unsigned)row * qpr) * 4;
+    const long t0 = row * Ws + x0;
+    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(u8 + t0);
+    if (!w0) return;
+    int prev = x0 > 0 ? u8[t0 - 1] : 0;
+    const int after = x0 + 4 < W ? u8[t0 + 4] : 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = x0 + i;
+        const int v = (w0 >> (8 * i)) & 255;
+        const int next = i < 3 ? (int)((w0 >> (8 * i + 8)) & 255) : after;
+        if (v && x < W) {
+            const bool run_end = (x == W - 1) || !spk_conn(v, next);
+            if (run_end) {
+                // first pixel of this run: a non-start pixel still holds it (row kernel); a start pixel's own label may
+                // already point at another run's root, so a one-pixel run must not read its length from it
+                const bool is_start = (x == 0) || !spk_conn(prev, v);
+                const long t = t0 + i;
+                const int start = is_start ? (int)t : label[t];
+                const int root = uf_find_compress(label, start);
+                atomicAdd(&count[root], (int)(t - start) + 1);
+            }
+        }
+        prev = v;
+    }
 }
 // apply the speckle verdict, restore sub-pixel values (rsgm.py:286-290) and write the float frame
 __global__ void speckle_apply_kernel(const uint8_t *__restrict__ u8, const int *__restrict__ label, const int *__restrict__ count,
-                                     const float *__restrict__ dl, float *__restrict__ out, RsgmDims d, int subpixel, long total)
+                                     const float *__restrict__ dl, float *__restrict__ out, RsgmDims d, int Ws, int subpixel,
+                                     long total)
 {
     long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    int b = u8[t];
+    int x, y;
+    long f;
+    split_fyx(t, d.W, d.H, x, y, f);
+    const long ts = (f * d.H + y) * Ws + x;
+    int b = u8[ts];
     if (b) {
-        const int start = label[t];                   // a non-start pixel still holds its run start
+        const int start = label[ts];                  // a non-start pixel still holds its run start
         const int root = uf_find(label, start);
         if (count[root] <= 200) b = 0;
     }
     float v = (float)b;
-    if (subpixel && b) {
-        int x, y;
-        long f;
-        split_fyx(t, d.W, d.H, x, y, f);
-        v = dl[(f * d.Hp + y + d.pt) * d.Wp + d.pl + x];
-    }
+    if (subpixel && b) v = dl[(f * d.Hp + y + d.pt) * d.Wp + d.pl + x];
     out[t] = v;
 }
 
@@ -730,20 +754,22 @@ __global__ void bg_cols_kernel(float *__restrict__ img, int W, int H, long total
 int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d, int subpixel, TailBufs tb, int n, cudaStream_t st)
 {
     const long total = (long)n * d.H * d.W;
-    if (total >= (1L << 31)) return VPPB200_ERR_ARG;
+    if ((long)n * d.H * tail_stride(d.W) >= (1L << 31)) return VPPB200_ERR_ARG;
     const int blocks = cdiv(total, 256);
-    lrcheck_u8_kernel<<<blocks, 256, 0, st>>>(dl, dr, tb.u8, d, total);
+    const int Ws = tail_stride(d.W);
+    const long quads = (long)n * d.H * (Ws >> 2);
+    lrcheck_u8_kernel<<<blocks, 256, 0, st>>>(dl, dr, tb.u8, d, Ws, total);
     VPP_LAUNCH_CHECK("lrcheck_u8_kernel");
     {
         const long nrows = (long)n * d.H;
-        speckle_rows_kernel<<<cdiv(nrows * 32, 128), 128, 0, st>>>(tb.u8, tb.label, tb.count, d.W, nrows);
+        speckle_rows_kernel<<<cdiv(nrows * 32, 128), 128, 0, st>>>(tb.u8, tb.label, tb.count, d.W, Ws, nrows);
         VPP_LAUNCH_CHECK("speckle_rows_kernel");
     }
-    speckle_merge_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, d.W, d.H, total);
+    speckle_merge_kernel<<<cdiv(quads, 256), 256, 0, st>>>(tb.u8, tb.label, d.W, Ws, d.H, quads);
     VPP_LAUNCH_CHECK("speckle_merge_kernel");
-    speckle_count_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, d.W, total);
+    speckle_count_kernel<<<cdiv(quads, 256), 256, 0, st>>>(tb.u8, tb.label, tb.count, d.W, Ws, quads);
     VPP_LAUNCH_CHECK("speckle_count_kernel");
-    speckle_apply_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, dl, out, d, subpixel, total);
+    speckle_apply_kernel<<<blocks, 256, 0, st>>>(tb.u8, tb.label, tb.count, dl, out, d, Ws, subpixel, total);
     VPP_LAUNCH_CHECK("speckle_apply_kernel");
     const long rows = (long)n * d.H;
     const int wpb = 4;
