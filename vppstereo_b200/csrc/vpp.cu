@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
 // Rows it cannot take (an occluded hint that is not discarded: its left blend reads the right image; more hints or
 // records than the shared-memory bins hold; patches wider than 15) are flagged and left to vpp_rnd_replay_kernel.
 struct RowsCfg { int cap_rec, cap_hint; };
-static constexpr int VR_NT = 256;
+static constexpr int VR_NT = 512;
 
 // the write records of one (hint, xw): calls emit(target, type) with target in [0, W) = left pixel, [W, 2W) = right pixel;
 // type 0 / 1 = interpolated right blend at x0 / x1, 2 = plain blend
@@ -476,8 +476,10 @@ __global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict
     __shared__ double lut_c[256], lut_o[256];
     {
         const double pv = (double)tid;
-        if (a.arith == 0) { lut_c[tid] = (double)__fmul_rn((float)pv, a.c32); lut_o[tid] = __dmul_rn(pv, __dsub_rn(1.0, (double)a.c32)); }
-        else { lut_c[tid] = __dmul_rn(pv, a.c64); lut_o[tid] = __dmul_rn(pv, __dsub_rn(1.0, a.c64)); }
+        if (tid < 256) {
+            if (a.arith == 0) { lut_c[tid] = (double)__fmul_rn((float)pv, a.c32); lut_o[tid] = __dmul_rn(pv, __dsub_rn(1.0, (double)a.c32)); }
+            else { lut_c[tid] = __dmul_rn(pv, a.c64); lut_o[tid] = __dmul_rn(pv, __dsub_rn(1.0, a.c64)); }
+        }
     }
     __syncthreads();
     // (4) replay: one thread per (active target pixel, channel)
