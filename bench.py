@@ -340,19 +340,20 @@ def main():
 
     # ---- timed region 2: end to end through the host-buffer API
     # (submit_host / collect: every step copies its inputs from pinned host memory and its disparities back to the host;
-    #  the copies of neighbouring steps overlap this step's kernels on separate streams, two batches in flight)
+    #  the copies of neighbouring steps overlap this step's kernels on separate streams, up to three batches in flight:
+    #  exactly args.steps batches are submitted and collected inside the timed region)
     for _ in range(2):
         pipe.collect(pipe.submit_host(left_h, right_h, hints_h))
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    prev = None
+    pending = []
     for k in range(args.steps):
-        tk = pipe.submit_host(left_h, right_h, hints_h)
-        if prev is not None:
-            res = pipe.collect(prev)
-        prev = tk
-    res = pipe.collect(prev)
+        pending.append(pipe.submit_host(left_h, right_h, hints_h))
+        if len(pending) == pipe.host_depth:
+            res = pipe.collect(pending.pop(0))
+    while pending:
+        res = pipe.collect(pending.pop(0))
     e1.record()
     sync_all()
     e2e_ms = e0.elapsed_time(e1)

@@ -271,30 +271,36 @@ def test_middlebury_shape_vs_oracle(mods, orc):
 
 
 def test_pipeline_streaming_matches_synchronous(mods):
-    """VppRsgmPipeline.submit_host/collect (copies overlapped on their own streams, two batches in flight) returns what the
-    synchronous run_host returns for the same batches and pattern seeds."""
+    """VppRsgmPipeline.submit_host/collect (copies overlapped on their own streams, up to host_depth = 3 batches in flight)
+    returns what the synchronous run_host returns for the same batches and pattern seeds."""
     import torch
     from vppstereo_b200.pipeline import VppRsgmPipeline
     synth = mods[2]
-    frames = [synth.make_pair(40 + f, shape=(60, 140), hints="lidar") for f in range(6)]
+    frames = [synth.make_pair(40 + f, shape=(60, 140), hints="lidar") for f in range(10)]
     batches = []
-    for b in range(3):
+    for b in range(5):
         fr = frames[2 * b:2 * b + 2]
         batches.append(tuple(torch.from_numpy(np.stack([p[k] for p in fr])).pin_memory() for k in ("left", "right", "hints")))
     sync_pipe = VppRsgmPipeline(60, 140, 3, batch=2, dmax=64, seed=5)
     want = [sync_pipe.run_host(*b).clone().numpy() for b in batches]
     pipe = VppRsgmPipeline(60, 140, 3, batch=2, dmax=64, seed=5)
-    got, prev = [], None
+    got, pending = [], []
     for b in batches:
-        tk = pipe.submit_host(*b)
-        if prev is not None:
-            got.append(pipe.collect(prev).clone().numpy())
-        prev = tk
-    got.append(pipe.collect(prev).clone().numpy())
-    for k in range(3):
+        pending.append(pipe.submit_host(*b))
+        if len(pending) == pipe.host_depth:
+            got.append(pipe.collect(pending.pop(0)).clone().numpy())
+    with pytest.raises(RuntimeError):
+        pipe.collect(pending[0] - 1 if pending[0] > 0 else pipe.host_depth - 1)       # already collected
+    while pending:
+        got.append(pipe.collect(pending.pop(0)).clone().numpy())
+    for k in range(5):
         assert_same(got[k], want[k], f"streamed batch {k}")
     with pytest.raises(RuntimeError):
         pipe.collect(0)
+    for _ in range(pipe.host_depth):
+        pipe.submit_host(*batches[0])
+    with pytest.raises(RuntimeError):
+        pipe.submit_host(*batches[0])                  # a fourth batch needs a collect first
 
 
 def test_pipeline_phases_overlapped_match_serial_and_oracle(mods, orc):

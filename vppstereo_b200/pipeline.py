@@ -59,6 +59,7 @@ class VppRsgmPipeline:
             self.d_hints = torch.empty((self.N, self.H, self.W), dtype=torch.float32, device=self.device)
             self.h_disp = torch.empty((self.N, self.H, self.W), dtype=torch.float32).pin_memory()
             self._stream_sets = None                  # created by the first submit_host
+            self.host_depth = 3                       # staging sets of the streaming host API
 
     def workspace_bytes(self):
         return self.ws_rsgm.numel() + self.ws_vpp.numel()
@@ -169,7 +170,7 @@ class VppRsgmPipeline:
         if self._stream_sets is None:
             with torch.cuda.device(self.device):
                 sets = []
-                for _ in range(2):
+                for _ in range(self.host_depth):
                     sets.append(dict(left=torch.empty_like(self.lv), right=torch.empty_like(self.lv),
                                      hints=torch.empty_like(self.d_hints), disp=torch.empty_like(self.disp),
                                      h_disp=torch.empty((self.N, self.H, self.W), dtype=torch.float32).pin_memory(),
@@ -179,14 +180,15 @@ class VppRsgmPipeline:
         return self._stream_sets
 
     def submit_host(self, left, right, hints):
-        """Queue one batch of host tensors (pinned for real overlap); returns a ticket for collect().  At most two
-        batches are in flight: submitting a third one first requires collecting the oldest."""
+        """Queue one batch of host tensors (pinned for real overlap); returns a ticket for collect().  At most `host_depth`
+        (3) batches are in flight: submitting one more first requires collecting the oldest.  Keeping two batches queued
+        behind the running one lets the next batch's inputs arrive, and its front phase start, while the current sweeps run."""
         torch = self.torch
         ss = self._streaming()
-        slot = ss["turn"] & 1
+        slot = ss["turn"] % self.host_depth
         st = ss["sets"][slot]
         if st["busy"]:
-            raise RuntimeError("submit_host: collect() the batch submitted two calls ago first")
+            raise RuntimeError(f"submit_host: collect() the batch submitted {self.host_depth} calls ago first")
         N = left.shape[0]
         compute = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
@@ -209,7 +211,7 @@ class VppRsgmPipeline:
 
     def collect(self, ticket):
         """Wait for a submitted batch; returns its pinned host float32 [N,H,W] disparities (valid until that staging set is
-        reused by the second submit_host after this call)."""
+        reused by the `host_depth`-th submit_host after it was submitted)."""
         st = self._streaming()["sets"][ticket]
         if not st["busy"]:
             raise RuntimeError("collect: nothing in flight for this ticket")
