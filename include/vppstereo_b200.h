@@ -181,6 +181,16 @@ int vppb200_vpp_scan_rnd(uint8_t *l, uint8_t *r, const float *g, int W, int H, i
                          int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
                          uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream);
 
+/* Row-band form of the rnd scan (an oversized frame split across GPUs): only the image rows
+ * [row_begin, row_end) of l and r are produced, every other row is left untouched.  Exact: a blend that writes image row yy
+ * only reads row yy of the same channel, and the stream position of every draw is a closed form of the full hint map g (which
+ * every band reads whole), so the union of disjoint bands equals the full scan bit for bit. */
+int vppb200_vpp_scan_rnd_rows(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                              int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                              int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                              uint64_t rng_seed, int row_begin, int row_end, int32_t *n_hints_out, void *workspace,
+                              size_t workspace_bytes, int n, void *stream);
+
 /* virtual_projection_scan_max_dist(l, r, g, width, height, channels, uniform_color, wsize, wsize_agg_x, wsize_agg_y,
  *                                  direction, c, c_occ, g_occ, discard_occluded, interpolate) -> #hints  pyx:133-341
  * Workspace: vppb200_vpp_max_dist_workspace_bytes (adds the per-hint dependency table of the row-wavefront kernel);

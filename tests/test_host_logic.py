@@ -140,3 +140,15 @@ def test_patch_threshold_tabulation():
             assert 1 + int((d >= thr).sum()) == vs._patch_size(d, dmin, dmax, wsize, gamma), (d, dmin, dmax, wsize, gamma)
     with pytest.raises(ZeroDivisionError):
         vs._patch_thresholds(np.float32(4.0), np.float32(4.0), 5, 0.3)
+
+
+def test_band_with_halo():
+    from vppstereo_b200 import dist as vd
+    for H, world, halo in [(2000, 8, 3), (375, 4, 1), (10, 3, 5)]:
+        covered = []
+        for r in range(world):
+            (lo, hi), (rlo, rhi) = vd.band_with_halo(H, r, world, halo)
+            assert 0 <= rlo <= lo <= hi <= rhi <= H and lo - rlo <= halo and rhi - hi <= halo
+            assert rlo == max(lo - halo, 0) and rhi == min(hi + halo, H)
+            covered += list(range(lo, hi))
+        assert covered == list(range(H))

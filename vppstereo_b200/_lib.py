@@ -23,7 +23,7 @@ SYMBOLS = [
     "vppb200_match_wta_right", "vppb200_subpixel_refine", "vppb200_median3x3",
     "vppb200_rsgm_workspace_bytes", "vppb200_compute_rsgm", "vppb200_compute_rsgm_tapped",
     "vppb200_rsgm_workspace_bytes_sets", "vppb200_compute_rsgm_phases",
-    "vppb200_vpp_workspace_bytes", "vppb200_vpp_max_dist_workspace_bytes", "vppb200_vpp_scan_rnd", "vppb200_vpp_scan_max_dist", "vppb200_vpp_scan_rnd_adaptive",
+    "vppb200_vpp_workspace_bytes", "vppb200_vpp_max_dist_workspace_bytes", "vppb200_vpp_scan_rnd", "vppb200_vpp_scan_max_dist", "vppb200_vpp_scan_rnd_adaptive", "vppb200_vpp_scan_rnd_rows",
     "vppb200_vpp_scan_max_dist_adaptive", "vppb200_bilateral_filling", "vppb200_f32chw_to_u8hwc", "vppb200_gt_reshape",
     "vppb200_u8hwc_to_f32chw", "vppb200_set_tuning",
     "vppb200_occlusion_workspace_bytes", "vppb200_occlusion_heuristic",

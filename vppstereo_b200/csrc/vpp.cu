@@ -27,6 +27,7 @@ struct VppArgs {
     const float *filled;   // [frames][H][W] bilateral-filled hints: a patch pixel is kept iff |g - filled| < 0.1 (float64)
     const float *thr;      // [frames][nthr] ascending disparity thresholds: patch size = 1 + #{k : g >= thr[k]}
     int nthr;
+    int y0, y1;            // rnd only: image rows [y0, y1) are produced (row-band split of an oversized frame), others left untouched
 };
 
 // per-hint patch radius and per-pixel keep test of the adaptive modes
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(128) vpp_rnd_replay_kernel(uint8_t *__restrict
     const int yy = (int)((t / a.C) % a.H);
     const long f = t / ((long)a.C * a.H);
     const int W = a.W, H = a.H, n = a.n;
+    if (yy < a.y0 || yy >= a.y1) return;                        // outside this call's row band
     if (only_flagged && !ws.rowflag[f * H + yy]) return;        // this row was done by vpp_rnd_rows_kernel
     Splat s{a, l + ((f * H + yy) * W) * a.C + j, r + ((f * H + yy) * W) * a.C + j};
     const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict
     const long fr = blockIdx.x;                           // f * H + yy
     const int yy = (int)(fr % H);
     const long f = fr / H;
+    if (yy < a.y0 || yy >= a.y1) return;                  // outside this call's row band (the replay kernel skips it too)
     const int ylo_row = max(0, yy - n), yhi_row = min(H - 1, yy + n);
     const int nrows = yhi_row - ylo_row + 1;
     __shared__ int rowstart[17];
@@ -591,6 +594,7 @@ __global__ void __launch_bounds__(128) vpp_rnd_adaptive_kernel(uint8_t *__restri
     const int yy = (int)((t / a.C) % a.H);
     const long f = t / ((long)a.C * a.H);
     const int W = a.W, H = a.H, n = a.n;
+    if (yy < a.y0 || yy >= a.y1) return;                        // outside this call's row band
     Splat s{a, l + ((f * H + yy) * W) * a.C + j, r + ((f * H + yy) * W) * a.C + j};
     const uint8_t *pat = pattern ? pattern + pattern_offsets[f] : nullptr;
     const long long pat_len = pattern ? pattern_offsets[f + 1] - pattern_offsets[f] : 0;
@@ -1103,6 +1107,7 @@ static VppArgs make_args(int W, int H, int C, int uniform, int wsize, int wax, i
     a.direction = direction; a.discard = discard != 0; a.interpolate = interpolate != 0; a.arith = arith;
     a.c32 = (float)c; a.cocc32 = (float)c_occ; a.c64 = c; a.cocc64 = c_occ;
     a.filled = nullptr; a.thr = nullptr; a.nthr = 0;
+    a.y0 = 0; a.y1 = H;
     return a;
 }
 
@@ -1121,16 +1126,18 @@ static int scan_rnd_impl(uint8_t *l, uint8_t *r, const float *g, int W, int H, i
                          int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
                          int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
                          uint64_t rng_seed, int32_t *n_hints_out, void *workspace, size_t workspace_bytes, int n, void *stream,
-                         const float *filled_g, const float *thresholds, int n_thresholds)
+                         const float *filled_g, const float *thresholds, int n_thresholds, int row_begin = 0, int row_end = -1)
 {
+    if (row_end < 0) row_end = H;
     if (!l || !r || !g || !g_occ || (pattern && !pattern_offsets) || W <= 0 || H <= 0 || C <= 0 || n <= 0 || wsize < 1 || W > 65535 ||
-        (arith != 0 && arith != 1) || (thresholds && n_thresholds != wsize - 1))
+        (arith != 0 && arith != 1) || (thresholds && n_thresholds != wsize - 1) || row_begin < 0 || row_end > H || row_begin > row_end)
         return VPPB200_ERR_ARG;
     if (!workspace || workspace_bytes < vpp_ws_layout(H, W, n, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     VppWs ws;
     vpp_ws_layout(H, W, n, workspace, &ws);
     VppArgs a = make_args(W, H, C, uniform_color, wsize, 1, 1, direction, c, c_occ, discard_occluded, interpolate, arith);
+    a.y0 = row_begin; a.y1 = row_end;
     if (filled_g || thresholds) {
         // adaptive patches: recounted stream positions, ordered per-row replay with per-hint radius and keep test
         a.filled = filled_g; a.thr = thresholds; a.nthr = thresholds ? n_thresholds : 0;
@@ -1183,6 +1190,17 @@ extern "C" int vppb200_vpp_scan_rnd_adaptive(uint8_t *l, uint8_t *r, const float
     return scan_rnd_impl(l, r, g, W, H, C, uniform_color, wsize, direction, c, c_occ, g_occ, discard_occluded, interpolate, arith,
                          pattern, pattern_offsets, rng_seed, n_hints_out, workspace, workspace_bytes, n, stream, filled_g,
                          patch_thresholds, n_thresholds);
+}
+
+extern "C" int vppb200_vpp_scan_rnd_rows(uint8_t *l, uint8_t *r, const float *g, int W, int H, int C, int uniform_color, int wsize,
+                                         int direction, double c, double c_occ, const uint8_t *g_occ, int discard_occluded,
+                                         int interpolate, int arith, const uint8_t *pattern, const int64_t *pattern_offsets,
+                                         uint64_t rng_seed, int row_begin, int row_end, int32_t *n_hints_out, void *workspace,
+                                         size_t workspace_bytes, int n, void *stream)
+{
+    return scan_rnd_impl(l, r, g, W, H, C, uniform_color, wsize, direction, c, c_occ, g_occ, discard_occluded, interpolate, arith,
+                         pattern, pattern_offsets, rng_seed, n_hints_out, workspace, workspace_bytes, n, stream, nullptr, nullptr, 0,
+                         row_begin, row_end);
 }
 
 extern "C" int vppb200_bilateral_filling(const float *dmap, const uint8_t *gray, float *out, int W, int H, int n_patch,

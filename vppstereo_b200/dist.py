@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: the hot path shards by FRAME.  One process per GPU, contiguous frame
-ranges per rank, no communication while computing, one collective at the end to gather the disparities.
+ranges per rank, no communication while computing, one collective at the end to gather the disparities.  An oversized
+single frame splits by ROW BANDS where the stage allows it exactly (vpp_rnd_banded, band_with_halo).
 
-Only torch.distributed is used (NCCL on GPUs, gloo in the CPU tests of this host logic); nothing here launches kernels.
+Only torch.distributed is used for communication (NCCL on GPUs, gloo in the CPU tests of this host logic).
 """
 import numpy as np
 
@@ -70,6 +71,48 @@ def run_sharded(n_frames, make_inputs, process, chunk=16, group=None, gather=Tru
     if local is None:
         raise ValueError("a rank received no frames: use n_frames >= world_size")
     return gather_frames(local, n_frames, group=group) if gather else local
+
+
+def band_with_halo(n_rows, rank, world_size, halo):
+    """Row band of `rank` for an oversized frame: (lo, hi) = the rows the rank owns, (rlo, rhi) = the rows it
+    has to read (owned rows plus `halo` rows on either side, clipped).  census needs halo 3, median 2, the rnd projection
+    reads hint rows within its patch radius."""
+    lo, hi = shard_range(n_rows, rank, world_size)
+    return (lo, hi), (max(lo - halo, 0), min(hi + halo, n_rows))
+
+
+def vpp_rnd_banded(left, right, hints, group=None, pattern=None, seed=0, **vpp_kwargs):
+    """Random-pattern VPP of ONE oversized frame split by row bands across the ranks of `group`: every
+    rank holds the full CUDA inputs, projects only its band of image rows (vppb200_vpp_scan_rnd_rows: exact, the stream
+    position of every draw is a closed form of the full hint map) and the bands are all-gathered.  Returns (lc, rc) uint8
+    [H,W,C] on every rank.  Keyword arguments are those of vpp() for method="rnd" without adaptive patches; all ranks must
+    pass the same `pattern` or `seed`."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from . import vpp_core_opt as core
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_available() and dist.is_initialized() else (0, 1)
+    kw = dict(wsize=3, left2right=True, blending=0.4, uniform_color=False, c_occ=0.0, g_occ=None, discard_occ=False, interpolate=True)
+    unknown = set(vpp_kwargs) - set(kw)
+    if unknown:
+        raise TypeError(f"vpp_rnd_banded: unsupported arguments {sorted(unknown)}")
+    kw.update(vpp_kwargs)
+    lc = _lib.as_device(left, torch.uint8).clone().contiguous()
+    rc = _lib.as_device(right, torch.uint8).clone().contiguous()
+    g = _lib.as_device(hints, torch.float32).contiguous()
+    if lc.dim() == 2:
+        lc, rc = lc.unsqueeze(-1).contiguous(), rc.unsqueeze(-1).contiguous()
+    H, W = g.shape
+    occ = torch.zeros((H, W), dtype=torch.uint8, device=g.device) if kw["g_occ"] is None else \
+        (_lib.as_device(kw["g_occ"], torch.float32) != 0).to(torch.uint8)
+    lo, hi = shard_range(H, rank, world)
+    rng_seed = None if pattern is not None else (int(seed) | (1 << 63))
+    core._scan("rnd", lc, rc, g, W, H, lc.shape[-1], kw["uniform_color"], kw["wsize"], None, 1 if kw["left2right"] else 0,
+               kw["blending"], kw["c_occ"], occ, kw["discard_occ"], kw["interpolate"], pattern, 1, device_rng_seed=rng_seed,
+               want_counts=False, rows=(lo, hi))
+    if world == 1:
+        return lc, rc
+    return gather_frames(lc[lo:hi].contiguous(), H, group=group), gather_frames(rc[lo:hi].contiguous(), H, group=group)
 
 
 def bind_to_gpu_numa(device_index):

@@ -86,7 +86,7 @@ def _check_views(l, r, g, g_occ, width, height, channels):
 
 
 def _scan(kind, l, r, g, width, height, channels, uniform_color, wsize, wagg, direction, c, c_occ, g_occ,
-          discard_occluded, interpolate, pattern, arith, device_rng_seed=None, want_counts=True, adaptive=None):
+          discard_occluded, interpolate, pattern, arith, device_rng_seed=None, want_counts=True, adaptive=None, rows=None):
     width, height, channels, wsize, direction = int(width), int(height), int(channels), int(wsize), int(direction)
     _check_views(l, r, g, g_occ, width, height, channels)
     torch = _lib.require_cuda()
@@ -132,7 +132,16 @@ def _scan(kind, l, r, g, width, height, channels, uniform_color, wsize, wagg, di
                 if pt.numel() == 0:
                     pt = torch.zeros(1, dtype=torch.uint8, device=dev)
                 ot_off = torch.from_numpy(offs).to(dev)
-            if adaptive_on:
+            if rows is not None:
+                if adaptive_on:
+                    raise ValueError("row bands are implemented for the fixed-patch rnd scan")
+                rc = L.vppb200_vpp_scan_rnd_rows(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
+                                                 int(bool(uniform_color)), wsize, direction, C.c_double(cc), C.c_double(co),
+                                                 _lib.ptr(ot), int(bool(discard_occluded)), int(bool(interpolate)), int(arith),
+                                                 _lib.ptr(pt), _lib.ptr(ot_off), C.c_uint64(int(device_rng_seed or 0) & (2**64 - 1)),
+                                                 int(rows[0]), int(rows[1]), _lib.ptr(counts), _lib.ptr(ws), C.c_size_t(ws.numel()),
+                                                 n, _lib.stream_ptr(dev))
+            elif adaptive_on:
                 rc = L.vppb200_vpp_scan_rnd_adaptive(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
                                                      int(bool(uniform_color)), wsize, direction, C.c_double(cc), C.c_double(co),
                                                      _lib.ptr(ot), int(bool(discard_occluded)), int(bool(interpolate)), int(arith),
@@ -151,6 +160,8 @@ def _scan(kind, l, r, g, width, height, channels, uniform_color, wsize, wagg, di
                                                       C.c_double(cc), C.c_double(co), _lib.ptr(ot), int(bool(discard_occluded)),
                                                       int(bool(interpolate)), int(arith), _lib.ptr(filled), _lib.ptr(thr), n_thr,
                                                       _lib.ptr(counts), _lib.ptr(ws), C.c_size_t(ws.numel()), n, _lib.stream_ptr(dev))
+        elif rows is not None:
+            raise ValueError("maxDistance does not split into independent row bands (SURVEY.md 8e): its windows read the current images")
         else:
             rc = L.vppb200_vpp_scan_max_dist(_lib.ptr(lt), _lib.ptr(rt), _lib.ptr(gt), width, height, channels,
                                              int(bool(uniform_color)), wsize, int(wagg[0]), int(wagg[1]), direction,
