@@ -922,6 +922,15 @@ __device__ __forceinline__ int md_ld_acquire(const int *p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// long dependency wait (the rows far ahead of the wavefront): bounded, so a protocol error traps instead of hanging the device
+__device__ __noinline__ void md_long_wait(const int *p, int need)
+{
+    for (unsigned spins = 0; spins < (1u << 26); spins++) {
+        if (!__any_sync(0xFFFFFFFFu, need != 0 && md_ld_acquire(p) < need)) return;
+        __nanosleep(1024u);
+    }
+    __trap();
+}
 __device__ __forceinline__ void md_st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -1003,7 +1012,11 @@ __global__ void __launch_bounds__(32) vpp_max_dist_wave_kernel(uint8_t *l, uint8
             // wait for the hints of the rows above that interact with this one
             {
                 unsigned ns = 32;
-                while (__any_sync(0xFFFFFFFFu, need != 0 && md_ld_acquire(mydep) < need)) { __nanosleep(ns); ns = min(ns * 2, 1024u); }
+                while (__any_sync(0xFFFFFFFFu, need != 0 && md_ld_acquire(mydep) < need)) {
+                    if (ns > 1024u) { md_long_wait(mydep, need); break; }      // (kept out of line: the short waits are the hot path)
+                    __nanosleep(ns);
+                    ns *= 2;
+                }
                 __syncwarp();                         // ... which orders every lane's loads below
             }
             if (k + 1 < cnt) fetch(k + 1, nx_x, nx_gv, nx_occ, nx_need);
