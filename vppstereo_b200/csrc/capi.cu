@@ -145,14 +145,15 @@ static size_t rsgm_ws_layout(const RsgmDims &d, int n, int sets, int set, void *
     const size_t np = (size_t)n * d.Hp * d.Wp, nc = (size_t)n * d.H * tail_stride(d.W);
     RsgmWs w;
     w.gray_l = (uint8_t *)take(np); w.gray_r = (uint8_t *)take(np);
-    w.census_l = (uint32_t *)take(np * 4); w.census_r = (uint32_t *)take(np * 4);
     const size_t tv = tile_volume_elems(d.Wp, d.Hp, d.D, n);  // layout T pads the width to 32-column groups
     const size_t vol = tv > np * d.D ? tv : np * d.D;
-    w.guide = nullptr; w.dsi = nullptr; w.dl = nullptr; w.dr = nullptr;
+    w.guide = nullptr; w.dsi = nullptr; w.dl = nullptr; w.dr = nullptr; w.census_l = nullptr; w.census_r = nullptr;
     for (int k = 0; k < sets; k++) {
         uint8_t *guide = (uint8_t *)take(np), *dsi = (uint8_t *)take(vol);
         float *dl = (float *)take(np * 4), *dr = (float *)take(np * 4);
-        if (k == set) { w.guide = guide; w.dsi = dsi; w.dl = dl; w.dr = dr; }
+        // (the census images cross the front -> main boundary too: the forward sweep turns them into the cost volume)
+        uint32_t *cl = (uint32_t *)take(np * 4), *cr = (uint32_t *)take(np * 4);
+        if (k == set) { w.guide = guide; w.dsi = dsi; w.dl = dl; w.dr = dr; w.census_l = cl; w.census_r = cr; }
     }
     w.S = (uint16_t *)take(vol * 3);                          // one uint16 S, or three uint8 partial-sum volumes
     w.S_xyd = (uint16_t *)take(np * d.D * 2);                 // the reference's xyd order (WTA input, test tap)
@@ -263,6 +264,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_VPP_ROWS: vpp_set_rows_kernel(value); return VPPB200_OK;
         case VPPB200_TUNE_VPP_MD_WAVE: vpp_set_md_wave(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_BYTE_SUMS: sweep_set_byte_sums(value); return VPPB200_OK;
+        case VPPB200_TUNE_SGM_FUSE_COST: sweep_set_fuse_cost(value); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }
 }
@@ -387,6 +389,8 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
     if (phases == 7) tm.begin(st);                           // per-stage timing covers whole-pipeline calls only
     const bool tiled = aggregate_tile_supported(d.Wp, d.Hp, D, n);
     const bool want_volume = taps && taps->dsi_agg;          // only the test tap needs the aggregated volume itself
+    // unguided frames: the Hamming volume is produced by the forward sweep itself (no stand-alone cost kernel)
+    const bool fuse_cost = tiled && !hints && sweep_fuses_cost(d.Wp, d.Hp, D, n, !want_volume);
     const uint16_t *S_final = w.S;
     if (front) {
         // rsgm.py:258-262  pad (BORDER_REFLECT) + RGB2GRAY; the P2 guide is the raw byte stream of the padded `left`
@@ -403,7 +407,7 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
         tm.done(VPPB200_STAGE_CENSUS);
         // rsgm.py:263-268  Hamming volume (+ optional guided modulation)
         if (tiled) {
-            if ((rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
+            if (!fuse_cost && (rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
             if (hints && (rc = launch_guided_tile(w.dsi, hints, validhints, d, n, st))) return rc;
         } else {
             if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
@@ -418,10 +422,12 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
             const StageHook hook = {StageMarks::hook, &tm};
             if (!want_volume) {
                 // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
-                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, hints == nullptr, &hook, st)))
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, hints == nullptr, &hook, st,
+                                                fuse_cost ? w.census_l : nullptr, fuse_cost ? w.census_r : nullptr)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
             } else {
-                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, false, &hook, st)))
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, false, &hook, st,
+                                                fuse_cost ? w.census_l : nullptr, fuse_cost ? w.census_r : nullptr)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
                 if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
                 S_final = w.S_xyd;

@@ -276,13 +276,20 @@ __device__ __forceinline__ uint32_t &u4c(uint4 &v, int i) { return i == 0 ? v.x 
 // the sweeps do not read-modify-write a uint16 S; each writes its own uint8 volume in the cost volume's layout (MODE 0 -> a0,
 // the v-sweeps -> a1, a2) and MODE 2 adds the three to its own path on the fly.  Same integers, 37 % less DRAM traffic.
 // FULLK: K2 == NW * 32, every lane's NW pairs are real disparities (no validity selects)
-template <int NW, int MODE, int DIR, bool S8, bool FULLK>
+// GEN (forward sweep only): the Hamming costs are not read but PRODUCED here from the two census rows
+// (RSGM/StereoBMHelper.cpp:29-140: popc(L[x] ^ R[x-d]) for d <= x on rows 2..H-3, 12 elsewhere) and written to the cost
+// volume for the three sweeps that follow: the stand-alone cost kernel and one read of the volume disappear, the popcounts
+// ride the forward sweep's idle issue slots.
+template <int NW, int MODE, int DIR, bool S8, bool FULLK, bool GEN>
 __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__restrict__ img, const uint16_t *__restrict__ cost,
                                                             uint32_t *__restrict__ S, TL t, long total_rows,
                                                             float *__restrict__ disp_l, float *__restrict__ disp_r,
                                                             const float *__restrict__ lut, uint16_t *__restrict__ a0,
-                                                            const uint16_t *__restrict__ a1, const uint16_t *__restrict__ a2)
+                                                            const uint16_t *__restrict__ a1, const uint16_t *__restrict__ a2,
+                                                            const uint32_t *__restrict__ cen_l, const uint32_t *__restrict__ cen_r,
+                                                            uint16_t *__restrict__ cost_out)
 {
+    static_assert(!GEN || (MODE == 0 && !S8 && DIR > 0), "costs are generated by the forward uint16 sweep");
     constexpr bool STORE = MODE == 0, WTA = MODE == 2;
     static_assert(!WTA || DIR < 0, "the fused WTA rides the backward sweep");
     static_assert(!S8 || MODE != 1, "byte partial sums: forward store or fused WTA only");
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             const int xc = DIR > 0 ? q : nchunks - 1 - q;
             const int toff = ((xc >> 2) * K2) * 32 + (xc & 3) * 8;       // tile start + first column of the chunk
             uint8_t *sb = base + (q & 1) * stage_b;
-            {
+            if (!GEN) {
                 const uint16_t *src = crow + toff + lane * 32;
                 const uint32_t dst = smem_u32(sb) + lane * HCROW;
                 for (int r0 = 0; r0 < K2; r0 += 32)
@@ -355,6 +362,14 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     uint32_t bucket[2 * NW];                        // WTA right: best (cost << 16 | d) of the in-flight target pixels
 #pragma unroll
     for (int k = 0; k < 2 * NW; k++) bucket[k] = 0xFFFFFFFFu;
+    // GEN: this lane's window of the right census row, R[xlo - d0 - (2NW-1) + j], j = 0 .. 2NW+6 (slides by 8 per chunk)
+    constexpr int RWN = 2 * NW + 7;
+    uint32_t rw[RWN];
+#pragma unroll
+    for (int j = 0; j < RWN; j++) rw[j] = 0;
+    const uint32_t *clrow = GEN ? cen_l + row * W : nullptr, *crrow = GEN ? cen_r + row * W : nullptr;
+    const int yrow = (int)(row % t.H);
+    const bool row_ok = yrow >= 2 && yrow < t.H - 2;
     int step = 0, ring = 0;
     for (int q = 0; q < nchunks; q++) {
         cp_async_wait<1>();
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
 #pragma unroll
             for (int v = 0; v < (NA > 0 ? NA : 1); v++) av[v][j] = cv[j];
             if (wv[j]) {
-                cv[j] = *reinterpret_cast<const uint4 *>(sb + (NW * lane + j) * HCROW);
+                if (!GEN) cv[j] = *reinterpret_cast<const uint4 *>(sb + (NW * lane + j) * HCROW);
 #pragma unroll
                 for (int v = 0; v < NA; v++)
                     av[v][j] = *reinterpret_cast<const uint4 *>(sb + (v + 1) * K2 * HCROW + (NW * lane + j) * HCROW);
@@ -379,6 +394,37 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                     s0[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW);
                     s1[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW + 16);
                 }
+            }
+        }
+        if (GEN) {
+            uint32_t Lc[8];
+            {
+                const uint4 la = *reinterpret_cast<const uint4 *>(clrow + xlo), lb = *reinterpret_cast<const uint4 *>(clrow + xlo + 4);
+                Lc[0] = la.x; Lc[1] = la.y; Lc[2] = la.z; Lc[3] = la.w; Lc[4] = lb.x; Lc[5] = lb.y; Lc[6] = lb.z; Lc[7] = lb.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 2 * NW - 1; j++) rw[j] = rw[j + 8];
+#pragma unroll
+            for (int j = 2 * NW - 1; j < RWN; j++) {
+                const int idx = xlo - d0 - (2 * NW - 1) + j;
+                rw[j] = idx >= 0 ? crrow[idx] : 0u;
+            }
+            const bool chk = xlo < d0 + 2 * NW;          // some (pixel, disparity) of this lane's block has d > x
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                uint32_t comp[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int pp = 0; pp < 8; pp++) {
+                    uint32_t lo = (uint32_t)__popc(Lc[pp] ^ rw[pp - 2 * j + (2 * NW - 1)]);
+                    uint32_t hi = (uint32_t)__popc(Lc[pp] ^ rw[pp - 2 * j - 1 + (2 * NW - 1)]);
+                    if (chk) {
+                        if (d0 + 2 * j > xlo + pp) lo = 12u;
+                        if (d0 + 2 * j + 1 > xlo + pp) hi = 12u;
+                    }
+                    if (!row_ok) { lo = 12u; hi = 12u; }
+                    comp[pp >> 1] |= (lo | (hi << 8)) << (16 * (pp & 1));
+                }
+                cv[j] = make_uint4(comp[0], comp[1], comp[2], comp[3]);
             }
         }
         float out_l = 0.0f, out_r = 0.0f;            // lane p keeps the results of the chunk's pixel p
@@ -491,6 +537,13 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             for (int j = 0; j < NW; j++)
                 if (wv[j]) *reinterpret_cast<uint4 *>(dst + (NW * lane + j) * 32) = av[0][j];
         } else {
+            if (GEN) {
+                // the generated cost rows of the chunk: one 16-byte piece (8 columns x 2 disparities) per tile row
+                uint16_t *dst = cost_out + row * (long)t.G * K2 * 32 + ((xlo >> 5) * K2) * 32 + (xlo & 31);
+#pragma unroll
+                for (int j = 0; j < NW; j++)
+                    if (wv[j]) *reinterpret_cast<uint4 *>(dst + (NW * lane + j) * 32) = cv[j];
+            }
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 if (wv[j]) {
@@ -515,17 +568,22 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
 
 struct ByteVols { uint16_t *a0, *a1, *a2; };       // S8: the three byte partial-sum volumes (layout T, uint16 words)
 
+struct CostGen { const uint32_t *cl, *cr; uint16_t *out; };     // forward sweep that produces the cost volume (cl == NULL: reads it)
+
 template <int NW, int MODE, int DIR, bool S8>
 static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int n, float *dl, float *dr,
-                   const float *lut, const ByteVols &bv, cudaStream_t st)
+                   const float *lut, const ByteVols &bv, cudaStream_t st, const CostGen &cg = CostGen{nullptr, nullptr, nullptr})
 {
     const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
     const size_t stage = S8 ? (size_t)t.K2 * HCROW * (MODE == 2 ? 4 : 1) : h_stage_bytes(t.K2);
     const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * 3 * t.K2 * 4 : 0);
-    auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, S8, true> : sgm_h_kernel<NW, MODE, DIR, S8, false>;
+    auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, S8, true, false> : sgm_h_kernel<NW, MODE, DIR, S8, false, false>;
+    if constexpr (MODE == 0 && !S8 && DIR > 0) {
+        if (cg.cl) kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, 0, 1, false, true, true> : sgm_h_kernel<NW, 0, 1, false, false, true>;
+    }
     if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows, dl, dr, lut, bv.a0, bv.a1, bv.a2);
+    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows, dl, dr, lut, bv.a0, bv.a1, bv.a2, cg.cl, cg.cr, cg.out);
     VPP_LAUNCH_CHECK("sgm_h_kernel");
     return VPPB200_OK;
 }
@@ -533,13 +591,13 @@ static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const 
 // mode 0: forward sweep, S = L;  mode 1: backward sweep, S += L;  mode 2: backward sweep fused with WTA (dl, dr, lut)
 // s8: byte partial sums (modes 0 and 2 only)
 static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int mode, int n, float *dl, float *dr,
-                 const float *lut, bool s8, const ByteVols &bv, cudaStream_t st)
+                 const float *lut, bool s8, const ByteVols &bv, cudaStream_t st, const CostGen &cg = CostGen{nullptr, nullptr, nullptr})
 {
 #define VPP_RUN_H(NW)                                                                                                  \
     if (s8)                                                                                                            \
         return mode == 0 ? run_h_t<NW, 0, 1, true>(img, cost, S, t, n, nullptr, nullptr, nullptr, bv, st)              \
                          : run_h_t<NW, 2, -1, true>(img, cost, S, t, n, dl, dr, lut, bv, st);                          \
-    return mode == 0 ? run_h_t<NW, 0, 1, false>(img, cost, S, t, n, nullptr, nullptr, nullptr, bv, st)                 \
+    return mode == 0 ? run_h_t<NW, 0, 1, false>(img, cost, S, t, n, nullptr, nullptr, nullptr, bv, st, cg)             \
          : mode == 1 ? run_h_t<NW, 1, -1, false>(img, cost, S, t, n, nullptr, nullptr, nullptr, bv, st)                \
                      : run_h_t<NW, 2, -1, false>(img, cost, S, t, n, dl, dr, lut, bv, st)
     switch ((t.K2 + 31) / 32) {
@@ -1051,8 +1109,21 @@ bool aggregate_tile_supported(int W, int H, int D, int n)
 // pipe and by synchronisation, not by HBM.  Kept as an option (VPPB200_TUNE_SGM_BYTE_SUMS), off by default.
 static int g_byte_sums_off = 1;
 void sweep_set_byte_sums(int on) { g_byte_sums_off = !on; }
+// cen_l / cen_r != NULL: the cost volume cost8 is not an input but is produced by the forward sweep from the census images
+// (sweep_fuses_cost tells the caller when that is available and selected).
+// Measured on B200 (batch 64 @K): the stand-alone cost kernel (1.47 ms) disappears and the forward sweep grows from 3.56 to
+// 5.27 ms -- POPC issues on the same integer pipe the sweep saturates, so the popcounts do not hide in its idle issue slots;
+// step 25.87 vs 25.75 ms.  Bit-identical, kept as an option (VPPB200_TUNE_SGM_FUSE_COST), off by default.
+static int g_fuse_cost_off = 1;
+void sweep_set_fuse_cost(int on) { g_fuse_cost_off = !on; }
+bool sweep_fuses_cost(int W, int H, int D, int n, bool byte_sums)
+{
+    (void)H; (void)D; (void)n;
+    return !g_fuse_cost_off && W % 32 == 0 && (!byte_sums || g_byte_sums_off);
+}
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, void *halo_ws, int W, int H, int D, int n,
-                          float *dl, float *dr, const float *lut, bool byte_sums, const StageHook *hook, cudaStream_t st)
+                          float *dl, float *dr, const float *lut, bool byte_sums, const StageHook *hook, cudaStream_t st,
+                          const uint32_t *cen_l, const uint32_t *cen_r)
 {
     const TL t = make_tl(W, H, D);
     VPlan plan;
@@ -1064,7 +1135,12 @@ int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S1
     ByteVols bv{nullptr, nullptr, nullptr};
     if (s8) { bv.a0 = S16; bv.a1 = S16 + (size_t)n * t.frame; bv.a2 = S16 + (size_t)2 * n * t.frame; }
     auto done = [&](int stage) { if (hook) hook->fn(hook->ctx, stage); };
-    if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, s8, bv, st))) return rc;
+    CostGen cg{nullptr, nullptr, nullptr};
+    if (cen_l && cen_r) {
+        if (s8 || W % 32 != 0) return VPPB200_ERR_ARG;
+        cg = CostGen{cen_l, cen_r, reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(cost8))};
+    }
+    if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, s8, bv, st, cg))) return rc;
     done(VPPB200_STAGE_SGM_H_FWD);
     uint32_t *halo = static_cast<uint32_t *>(halo_ws);
     if ((rc = run_v(img, cost, s8 ? reinterpret_cast<uint32_t *>(bv.a1) : S, halo, t, 0, n, plan, s8, st))) return rc;
