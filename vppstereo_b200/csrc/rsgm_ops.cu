@@ -88,24 +88,9 @@ int launch_pad_flatbytes(const uint8_t *src, uint8_t *guide, const RsgmDims &d, 
 
 // ------------------------------------------------------------------------------------------------------------
 // census5x5  (RSGM/FastFilters.cpp:181-442).  The image is a flat byte stream: neighbours of the first/last two
-// columns wrap into the adjacent rows.  One thread produces 4 adjacent codes from 5 x 8 staged bytes.
+// columns wrap into the adjacent rows.  One thread produces 4 adjacent codes from 5 x 8 staged bytes; the four centres are compared
+// against each neighbour offset with ONE byte-wise SIMD compare (__vsetltu4: 5 integer instructions for 4 comparisons).
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t census_sse_order(const uint8_t (&win)[5][8], int o)
-{
-    // neighbours k = 0..23 in raster order, bit position 8*(k/8) + (7 - k%8)   (:273-281,:320-328,:352-359)
-    const uint32_t c = win[2][o + 2];
-    uint32_t v = 0;
-    int k = 0;
-#pragma unroll
-    for (int dy = 0; dy < 5; dy++)
-#pragma unroll
-        for (int dx = 0; dx < 5; dx++) {
-            if (dy == 2 && dx == 2) continue;
-            v |= (uint32_t)(win[dy][o + dx] < c) << (8 * (k / 8) + (7 - k % 8));
-            k++;
-        }
-    return v;
-}
 __device__ __forceinline__ uint32_t census_tail_order(const uint8_t (&win)[5][8], int o)
 {
     // scalar tail (:424-441): value = sum bit_k * 2^(23-k)
@@ -140,7 +125,7 @@ __global__ void __launch_bounds__(256) census5x5_kernel(const uint8_t *__restric
     if (any_body || tail_row) {
         // flat neighbours c0 + (dy-2)*W + (dx-2), dx = 0..7 (may wrap across row ends; outside the frame: 0), fetched as the
         // three aligned words that cover them (c0, W and n are multiples of 4: a word is entirely inside or outside)
-        uint8_t win[5][8];
+        uint32_t wlo[5], whi[5];                       // window bytes 0..3 and 4..7 of each row = flat c0-2 .. c0+5
 #pragma unroll
         for (int dy = 0; dy < 5; dy++) {
             const long a0 = c0 + (long)(dy - 2) * W - 4;
@@ -150,18 +135,42 @@ __global__ void __launch_bounds__(256) census5x5_kernel(const uint8_t *__restric
                 const long a = a0 + 4 * i;
                 wd[i] = (a >= 0 && a < n) ? *reinterpret_cast<const uint32_t *>(img + a) : 0u;
             }
-            win[dy][0] = (uint8_t)(wd[0] >> 16); win[dy][1] = (uint8_t)(wd[0] >> 24);
-            win[dy][2] = (uint8_t)wd[1]; win[dy][3] = (uint8_t)(wd[1] >> 8); win[dy][4] = (uint8_t)(wd[1] >> 16);
-            win[dy][5] = (uint8_t)(wd[1] >> 24); win[dy][6] = (uint8_t)wd[2]; win[dy][7] = (uint8_t)(wd[2] >> 8);
+            wlo[dy] = __byte_perm(wd[0], wd[1], 0x5432); whi[dy] = __byte_perm(wd[1], wd[2], 0x5432);
+        }
+        // body pixels: the four centres are compared byte-wise in one register (neighbour < centre per byte), the 24 result
+        // bits per pixel are shifted into three byte-sliced accumulators (neighbours 0-7, 8-15, 16-23: first neighbour = MSB,
+        // the order of FastFilters.cpp:273-281) and transposed into the four codes at the end
+        const uint32_t cw = __byte_perm(wlo[2], whi[2], 0x5432);
+        uint32_t acc[3] = {0u, 0u, 0u};
+        {
+            int k = 0;
+#pragma unroll
+            for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+                for (int dx = 0; dx < 5; dx++) {
+                    if (dy == 2 && dx == 2) continue;
+                    const uint32_t nb = __byte_perm(wlo[dy], whi[dy], 0x3210u + 0x1111u * dx);
+                    acc[k / 8] = acc[k / 8] * 2u + __vsetltu4(nb, cw);
+                    k++;
+                }
         }
         uint32_t r[4];
 #pragma unroll
         for (int o = 0; o < 4; o++) {
             const long c = c0 + o;
             const int cc = col + o;
-            if (c >= lo && c <= hi) r[o] = census_sse_order(win, o);
-            else if (row == H - 3 && cc >= W - 14 && cc <= W - 3) r[o] = census_tail_order(win, o);
-            else r[o] = 0;
+            if (c >= lo && c <= hi) {
+                r[o] = ((acc[0] >> (8 * o)) & 255u) | (((acc[1] >> (8 * o)) & 255u) << 8) | (((acc[2] >> (8 * o)) & 255u) << 16);
+            } else if (row == H - 3 && cc >= W - 14 && cc <= W - 3) {
+                uint8_t win[5][8];                     // (rare: the reference's scalar tail has its own bit order)
+#pragma unroll
+                for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) win[dy][i] = (uint8_t)((i < 4 ? wlo[dy] : whi[dy]) >> (8 * (i & 3)));
+                r[o] = census_tail_order(win, o);
+            } else {
+                r[o] = 0;
+            }
         }
         out = make_uint4(r[0], r[1], r[2], r[3]);
     }
