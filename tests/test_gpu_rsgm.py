@@ -234,6 +234,26 @@ def test_cost_volume_from_the_forward_sweep(mods, orc, tuning, shape, D, channel
     tuning(_lib.TUNE_SGM_FUSE_COST, 0)
 
 
+def test_compute_rsgm_random_shapes(mods, orc):
+    """Seeded random sweep over frame shapes (any H >= 5, W >= 17: padded to multiples of 16, often not of 32), disparity ranges
+    (multiples of 8 up to 256), gray / colour, guided or not, sub-pixel on / off, batches of 1-3: bit-exact against the oracle."""
+    rsgm, synth = mods[1], mods[2]
+    rng = np.random.default_rng(4242)
+    for case in range(48):
+        H, W = int(rng.integers(5, 80)), int(rng.integers(17, 300))
+        D = int(rng.integers(1, 33)) * 8
+        ch = int(rng.choice([1, 3])); sub = bool(rng.integers(2)); guided = rng.integers(4) == 0; nb = int(rng.integers(1, 4))
+        frames = [synth.make_pair(int(rng.integers(10000)), shape=(H, W), hints="random", channels=ch, density=0.1) for _ in range(nb)]
+        left = np.stack([p["left"] for p in frames]); right = np.stack([p["right"] for p in frames])
+        hints = np.stack([p["hints"] for p in frames]) if guided else None
+        valid = (hints > 0).astype(np.float32) if guided else None
+        got = rsgm.compute_rsgm(left, left, right, hints=hints, validhints=valid, dmax=D, subpixel=sub)
+        for f, p in enumerate(frames):
+            want = orc.compute_rsgm(p["left"], p["left"], p["right"], hints=None if not guided else p["hints"],
+                                    validhints=None if not guided else (p["hints"] > 0).astype(np.float32), dmax=D, subpixel=sub)
+            assert_same(got[f], want, f"case {case}: {H}x{W} D={D} C={ch} sub={sub} guided={guided} frame {f}/{nb}")
+
+
 def test_compute_rsgm_guided_and_batch(mods, orc):
     rsgm, synth = mods[1], mods[2]
     frames = [synth.make_pair(f, shape=(45, 100), hints="random") for f in range(3)]
