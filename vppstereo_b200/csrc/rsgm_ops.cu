@@ -527,32 +527,8 @@ int launch_interp_clip(float *disp, int W, int H, int n, cudaStream_t st)
 // tail of compute_rsgm on the cropped H x W frame (models/rsgm/rsgm.py:275-292)
 // ------------------------------------------------------------------------------------------------------------
 // crop + _left_right_check(th=1) + zero mask==128 + astype(uint8)
-// (u8, label and count rows have the stride Ws = W rounded up to 4, pad bytes 0, so that the speckle kernels can read words)
-__global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__restrict__ dr, uint8_t *__restrict__ u8,
-                                  RsgmDims d, int Ws, long total)
-{
-    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    int x, y;
-    long f;
-    split_fyx(t, d.W, d.H, x, y, f);
-    const float *lrow = dl + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
-    const float *rrow = dr + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
-    float v = lrow[x];
-    if (v > 0) {
-        const int dd = __float2int_rn(v);            // numba round(): half to even (rsgm.py:237)
-        const int xd = x - dd;
-        if (xd >= 0 && xd <= d.W - 1) {
-            const float r = rrow[xd];
-            if (r > 0 && fabsf(__fsub_rn(v, r)) > 1.0f) v = 0.0f;
-        } else {
-            v = 0.0f;
-        }
-    }
-    u8[(f * d.H + y) * Ws + x] = (uint8_t)v;
-    if (x == d.W - 1)
-        for (int xp = d.W; xp < Ws; xp++) u8[(f * d.H + y) * Ws + xp] = 0;
-}
+// (u8, label and count rows have the stride Ws = W rounded up to 4, pad bytes 0, so that the speckle kernels can read words;
+// the left-right check itself lives in speckle_rows_kernel)
 
 // cv2.filterSpeckles(img, 0, 200, 10) (rsgm.py:285): 4-connected components under |a-b| <= 10 among non-zero pixels,
 // components with <= 200 pixels are zeroed.  The relation is symmetric, so the labelling is order independent.
@@ -562,18 +538,43 @@ __global__ void lrcheck_u8_kernel(const float *__restrict__ dl, const float *__r
 //   count  : one atomicAdd per run (its length) on the root
 __device__ __forceinline__ bool spk_conn(int a, int b) { return a && b && abs(a - b) <= 10; }
 
-__global__ void __launch_bounds__(128) speckle_rows_kernel(const uint8_t *__restrict__ u8, int *__restrict__ label,
-                                                           int *__restrict__ count, int W, int Ws, long total_rows)
+// rows: crop + _left_right_check(th=1) + zero mask==128 + astype(uint8) (rsgm.py:229-248,:275-284) fused with the run labelling: the warp that labels a row
+// produces the row's uint8 map itself (one pass over the two disparity rows instead of a kernel and a round trip of the map)
+__global__ void __launch_bounds__(128) speckle_rows_kernel(const float *__restrict__ dl, const float *__restrict__ dr,
+                                                           uint8_t *__restrict__ u8, int *__restrict__ label,
+                                                           int *__restrict__ count, RsgmDims d, int Ws, long total_rows)
 {
     const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= total_rows) return;
     const int lane = threadIdx.x & 31;
+    const int W = d.W;
     const long base = row * Ws;
+    const int y = (int)(row % d.H);
+    const long f = row / d.H;
+    const float *lrow = dl + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
+    const float *rrow = dr + ((f * d.Hp + y + d.pt) * d.Wp + d.pl);
     int carry = 0;                                   // run start of the last pixel of the previous chunk
-    for (int x0 = 0; x0 < W; x0 += 32) {
+    int prev_last = 0;                               // uint8 value of the last pixel of the previous chunk
+    for (int x0 = 0; x0 < Ws; x0 += 32) {
         const int x = x0 + lane;
-        const int v = x < W ? u8[base + x] : 0;
-        const int left = (x > 0 && x < W) ? u8[base + x - 1] : 0;
+        int v = 0;
+        if (x < W) {
+            float fv = lrow[x];
+            if (fv > 0) {
+                const int dd = __float2int_rn(fv);   // numba round(): half to even (rsgm.py:237)
+                const int xd = x - dd;
+                if (xd >= 0 && xd <= W - 1) {
+                    const float r = rrow[xd];
+                    if (r > 0 && fabsf(__fsub_rn(fv, r)) > 1.0f) fv = 0.0f;
+                } else {
+                    fv = 0.0f;
+                }
+            }
+            v = (int)(uint8_t)fv;
+        }
+        int left = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        if (lane == 0) left = prev_last;
+        prev_last = __shfl_sync(0xFFFFFFFFu, v, 31);
         int s = spk_conn(v, left) ? -1 : x;          // -1: continues the run of the pixel to the left
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(128) speckle_rows_kernel(const uint8_t *__rest
         }
         if (s < 0) s = carry;
         carry = __shfl_sync(0xFFFFFFFFu, s, 31);
+        if (x < Ws) u8[base + x] = (uint8_t)v;       // (pad bytes of the row stride: 0)
         if (x < W) {
             label[base + x] = v ? (int)(base + s) : -1;
             count[base + x] = 0;
@@ -767,11 +769,9 @@ int launch_tail(const float *dl, const float *dr, float *out, const RsgmDims &d,
     const int blocks = cdiv(total, 256);
     const int Ws = tail_stride(d.W);
     const long quads = (long)n * d.H * (Ws >> 2);
-    lrcheck_u8_kernel<<<blocks, 256, 0, st>>>(dl, dr, tb.u8, d, Ws, total);
-    VPP_LAUNCH_CHECK("lrcheck_u8_kernel");
     {
         const long nrows = (long)n * d.H;
-        speckle_rows_kernel<<<cdiv(nrows * 32, 128), 128, 0, st>>>(tb.u8, tb.label, tb.count, d.W, Ws, nrows);
+        speckle_rows_kernel<<<cdiv(nrows * 32, 128), 128, 0, st>>>(dl, dr, tb.u8, tb.label, tb.count, d, Ws, nrows);
         VPP_LAUNCH_CHECK("speckle_rows_kernel");
     }
     speckle_merge_kernel<<<cdiv(quads, 256), 256, 0, st>>>(tb.u8, tb.label, d.W, Ws, d.H, quads);
