@@ -341,10 +341,12 @@ def test_pipeline_streaming_matches_synchronous(mods):
         assert_same(got[k], want[k], f"streamed batch {k}")
     with pytest.raises(RuntimeError):
         pipe.collect(0)
-    for _ in range(pipe.host_depth):
-        pipe.submit_host(*batches[0])
+    tickets = [pipe.submit_host(*batches[0]) for _ in range(pipe.host_depth)]
     with pytest.raises(RuntimeError):
         pipe.submit_host(*batches[0])                  # a fourth batch needs a collect first
+    for tk in tickets:                                 # nothing stays in flight when the pipeline is dropped
+        assert pipe.collect(tk).shape == (2, 60, 140)
+    pipe.close()
 
 
 def test_pipeline_phases_overlapped_match_serial_and_oracle(mods, orc):
@@ -364,6 +366,9 @@ def test_pipeline_phases_overlapped_match_serial_and_oracle(mods, orc):
     for b in batches:
         want.append(serial.run_device_serial(*b).clone())
         proj.append((serial.lv.clone(), serial.rv.clone()))
+    # (dirty the allocator's free blocks first: the pipeline's zero-initialised occlusion mask must be complete before its own
+    # streams run the first front phase -- regression test for a constructor / first-call ordering bug)
+    junk = torch.full((96 << 20,), 255, dtype=torch.uint8, device="cuda"); torch.cuda.synchronize(); del junk
     pipe = VppRsgmPipeline(72, 160, 3, batch=2, dmax=64, seed=9)
     outs = [torch.empty((2, 72, 160), dtype=torch.float32, device="cuda") for _ in batches]
     for b, o in zip(batches, outs):                    # back to back: phases of neighbouring calls overlap

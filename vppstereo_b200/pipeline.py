@@ -60,6 +60,25 @@ class VppRsgmPipeline:
             self.h_disp = torch.empty((self.N, self.H, self.W), dtype=torch.float32).pin_memory()
             self._stream_sets = None                  # created by the first submit_host
             self.host_depth = 3                       # staging sets of the streaming host API
+            # the zero-filled occlusion mask above was queued on the constructing stream, while the first call's front phase
+            # runs on this object's own streams (which do not wait for it when inputs_ready=True): finish it here
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        """Wait for everything queued on the pipeline's own streams.  The buffers belong to this object while the kernels that
+        use them run on private streams the caching allocator does not track: they must not be released (and handed to another
+        tensor) before that work has finished.  Called by __del__; call it yourself before dropping a pipeline with batches
+        still in flight."""
+        try:
+            for s in (self.vpp_stream, self.main_stream, self.tail_stream):
+                s.synchronize()
+            if self._stream_sets is not None:
+                self._stream_sets["h2d"].synchronize(); self._stream_sets["d2h"].synchronize()
+        except Exception:
+            pass
+
+    def __del__(self):
+        self.close()
 
     def workspace_bytes(self):
         return self.ws_rsgm.numel() + self.ws_vpp.numel()
