@@ -427,10 +427,13 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                 cv[j] = make_uint4(comp[0], comp[1], comp[2], comp[3]);
             }
         }
-        float out_l = 0.0f, out_r = 0.0f;            // lane p keeps the results of the chunk's pixel p
+
         // per-warp scratch behind the stages: final S of the current and of the previous pixel (sub-pixel lookups); a ring
         // of three buffers, so the buffer written at step s+1 is not one a slower lane still reads at step s
         uint32_t *scr = reinterpret_cast<uint32_t *>(hsm + (size_t)HWARPS * 2 * stage_b) + warp * 3 * K2;
+        // the chunk's 8 + 8 results (uniform across the warp) are parked in shared memory by lane 0: two LSU stores per pixel
+        // instead of two compare + select pairs on the integer pipe
+        float *wout = reinterpret_cast<float *>(hsm + (size_t)HWARPS * 2 * stage_b + (size_t)HWARPS * 3 * K2 * 4) + warp * 16;
         const bool nomask = xlo >= D - 1;             // every d <= x in this chunk: the left arg-min needs no range mask
 #pragma unroll
         for (int pp = 0; pp < 8; pp++, step++) {
@@ -512,12 +515,12 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                         o = -10.0f;
                     }
                 }
-                if (lane == p) out_l = o;
+                if (lane == 0) wout[p] = o;
                 // right: every in-flight target absorbs its disparity slot, slot 0 retires to disp_r[x]
 #pragma unroll
                 for (int k = 0; k < 2 * NW; k++) bucket[k] = min(bucket[k], key[k]);
                 const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bucket[0], 0);
-                if (lane == p) out_r = (float)(b0 & 0xFFFFu);
+                if (lane == 0) wout[8 + p] = (float)(b0 & 0xFFFFu);
                 uint32_t from_up = __shfl_down_sync(0xFFFFFFFFu, bucket[0], 1);
                 if (lane == 31) from_up = 0xFFFFFFFFu;
 #pragma unroll
@@ -526,9 +529,10 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             }
         }
         if (WTA) {
+            __syncwarp();
             if (lane < 8) {
-                disp_l[row * W + xlo + lane] = out_l;
-                disp_r[row * W + xlo + lane] = out_r;
+                disp_l[row * W + xlo + lane] = wout[lane];
+                disp_r[row * W + xlo + lane] = wout[8 + lane];
             }
         } else if (S8) {
             // the chunk's byte rows leave from registers: one 16-byte piece (8 columns x 2 disparities) per tile row
@@ -577,7 +581,7 @@ static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const 
     const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
     const size_t stage = S8 ? (size_t)t.K2 * HCROW * (MODE == 2 ? 4 : 1) : h_stage_bytes(t.K2);
-    const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * 3 * t.K2 * 4 : 0);
+    const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * (3 * t.K2 + 16) * 4 : 0);
     auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, S8, true, false> : sgm_h_kernel<NW, MODE, DIR, S8, false, false>;
     if constexpr (MODE == 0 && !S8 && DIR > 0) {
         if (cg.cl) kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, 0, 1, false, true, true> : sgm_h_kernel<NW, 0, 1, false, false, true>;
