@@ -224,6 +224,78 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------- parity probe
+PROBE_STEP = 1 << 20          # call number (pattern seed) of the probe batch: fixed, whatever was timed before it
+PROBE_FRAMES = (0, 63)
+BENCH_CHECK = os.path.join(ROOT, "tests", "golden", "bench_check.json")
+
+
+def bench_inputs(rank, B):
+    """The benchmark's synthetic batch of one rank: 8 distinct K-shape frames tiled to B (generation is host work, not part of
+    the path).  Returns numpy arrays left, right [B,H,W,3] uint8 and hints [B,H,W] float32."""
+    import numpy as np
+    from vppstereo_b200 import synth
+    uniq = min(B, 8)
+    frames = [synth.make_pair(rank * 1000 + f, shape="K", hints="lidar") for f in range(uniq)]
+    idx = [i % uniq for i in range(B)]
+    return (np.stack([frames[i]["left"] for i in idx]), np.stack([frames[i]["right"] for i in idx]),
+            np.stack([frames[i]["hints"] for i in idx]))
+
+
+def probe_digest(lv, rv, disp):
+    """sha256 over the projected pair (uint8) and the disparity bit patterns (float32) of one frame"""
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()
+    for a in (lv, rv, disp):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def parity_probe(batch=64, pipe=None, tensors=None):
+    """One extra batch of rank 0's benchmark inputs through the very pipeline object and code path that was timed
+    (VppRsgmPipeline.run_device: device-generated pattern, three streams, the planner's v-sweep shape for this batch), with a
+    fixed pattern seed; sha256 of the projected pair and of the disparity bits of frames 0 and batch-1.  bench.py asserts them
+    against tests/golden/bench_check.json, which tests/golden/make_bench_check.py derives with the CPU oracle."""
+    import torch
+    from vppstereo_b200 import _lib
+    from vppstereo_b200.pipeline import VppRsgmPipeline
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if tensors is None:
+        tensors = tuple(torch.from_numpy(a).to(dev) for a in bench_inputs(0, batch))
+    own = pipe is None
+    if own:
+        pipe = VppRsgmPipeline(H, W, C, batch=batch, dmax=D, device=dev)
+    was = _lib.get_tuning(_lib.TUNE_RCP_HOST, 0)
+    _lib.set_tuning(_lib.TUNE_RCP_HOST, 0)           # the committed hashes are for the library's default (fixed) RCPSS table
+    try:
+        out = pipe.run_device(*tensors, inputs_ready=True, step=PROBE_STEP)
+        torch.cuda.synchronize(dev)
+        frames = [f if f < batch else batch - 1 for f in PROBE_FRAMES]
+        digests = [probe_digest(pipe.lv[f].cpu().numpy(), pipe.rv[f].cpu().numpy(), out[f].cpu().numpy()) for f in frames]
+    finally:
+        _lib.set_tuning(_lib.TUNE_RCP_HOST, was)
+        if own:
+            pipe.close()
+    return {"frames": frames, "step": PROBE_STEP, "sha256": digests}
+
+
+def assert_parity_probe(probe, batch):
+    """Compare with the committed oracle-derived digests; a mismatch is fatal (no JSON line is printed)."""
+    if batch != 64:
+        probe["expected"] = None
+        probe["ok"] = None            # the committed digests are for the configured batch of 64
+        return probe
+    with open(BENCH_CHECK) as f:
+        want = json.load(f)
+    probe["expected"] = want["sha256"]
+    probe["ok"] = probe["sha256"] == want["sha256"]
+    if not probe["ok"]:
+        raise SystemExit(f"bench.py: PARITY PROBE FAILED: disparities of the timed path differ from the oracle-derived digests "
+                         f"in {BENCH_CHECK}: got {probe['sha256']}, want {want['sha256']}")
+    return probe
+
+
 # ---------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -261,12 +333,7 @@ def main():
     warmup = max(args.warmup, 3)
 
     # synthetic inputs: a few distinct frames tiled to the batch (generation is host work, not part of the path)
-    uniq = min(B, 8)
-    frames = [synth.make_pair(rank * 1000 + f, shape="K", hints="lidar") for f in range(uniq)]
-    idx = [i % uniq for i in range(B)]
-    left_h = torch.from_numpy(np.stack([frames[i]["left"] for i in idx])).pin_memory()
-    right_h = torch.from_numpy(np.stack([frames[i]["right"] for i in idx])).pin_memory()
-    hints_h = torch.from_numpy(np.stack([frames[i]["hints"] for i in idx])).pin_memory()
+    left_h, right_h, hints_h = (torch.from_numpy(a).pin_memory() for a in bench_inputs(rank, B))
     left, right, hints = left_h.to(dev), right_h.to(dev), hints_h.to(dev)
     n_hints = float((hints_h > 0).sum()) / B
     pipe = VppRsgmPipeline(H, W, C, batch=B, dmax=D, device=dev)
@@ -359,6 +426,11 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
     check_val = float(res[0].mean())
 
+    # ---- parity probe: the timed pipeline object on rank 0's inputs with a fixed pattern seed, against oracle-derived digests
+    probe = None
+    if rank == 0:
+        probe = assert_parity_probe(parity_probe(B, pipe=pipe, tensors=(left, right, hints)), B)
+
     # max over ranks
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -408,6 +480,7 @@ def main():
                     "h2d_bytes_per_step": int(left_h.numel() + right_h.numel() + hints_h.numel() * 4),
                     "d2h_bytes_per_step": int(B * H * W * 4)},
             "gpu_launches": int(launches),
+            "parity_probe": probe,
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,
         }

@@ -44,8 +44,9 @@ const char *vppb200_version(void);
 const char *vppb200_last_cuda_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t vppb200_launch_count(void);
-/* 65536-entry table lut[k] = rcp_nz_ss(-2k) evaluated with the HOST CPU's RCPSS instruction
- * (RSGM/StereoBMHelper.cpp:752-756, used by subPixelRefine :1088-1096).  Host pointer. */
+/* 65536-entry table lut[k] = rcp_nz_ss(-2k) (RSGM/StereoBMHelper.cpp:752-756, used by subPixelRefine :1088-1096) as the
+ * library currently uses it when a call passes rcp_lut = NULL: by default the FIXED table of Intel's RCPSS approximation
+ * (same numbers on every host); with VPPB200_TUNE_RCP_HOST = 1 the table of the HOST CPU's own RCPSS instruction.  Host pointer. */
 int vppb200_rcp_lut_host(float *lut_host);
 
 /* Host-side restatement of glibc srand()/rand() (TYPE_3 additive feedback generator, r[i] = r[i-3] + r[i-31]) so that
@@ -88,6 +89,7 @@ int vppb200_stage_times(float *ms_out, int *calls_out);
 #define VPPB200_TUNE_SGM_CLUSTERS 2   /* upper bound on frames in flight in the v-sweep (0 = all SMs); experiments only */
 #define VPPB200_TUNE_VPP_MD_WAVE 5    /* 0 = VPP maxDistance by the serial one-warp-per-(frame, channel) kernel, 1 = row wavefront (default) */
 #define VPPB200_TUNE_SGM_FUSE_COST 6  /* 1 = the forward h-sweep produces the Hamming cost volume from the census images (W % 32 == 0, unguided; measured: not faster), 0 = stand-alone cost kernel (default) */
+#define VPPB200_TUNE_RCP_HOST 7       /* 0 = sub-pixel reciprocal from the fixed Intel RCPSS table (default), 1 = from the host CPU's RCPSS instruction */
 #define VPPB200_TUNE_SGM_BYTE_SUMS 4  /* 0 = sweeps read-modify-write one uint16 S (default), 1 = uint8 partial-sum volumes where exact */
 int vppb200_set_tuning(int key, int value);
 
@@ -113,7 +115,7 @@ int vppb200_match_wta(const uint16_t *dsi_agg, float *disp, int W, int H, int D,
 int vppb200_match_wta_right(const uint16_t *dsi_agg, float *disp, int W, int H, int D, float uniqueness, int n, void *stream);
 
 /* subPixelRefine(dsi, disp, W, H, D, method)                             RSGM/pyrSGM.cpp:639, StereoBMHelper.cpp:1065-1135.
- * rcp_lut: DEVICE copy of the vppb200_rcp_lut_host table (method 0); NULL = the library's own table for this host. */
+ * rcp_lut: DEVICE copy of the vppb200_rcp_lut_host table (method 0); NULL = the library's table (see vppb200_rcp_lut_host). */
 int vppb200_subpixel_refine(const uint16_t *dsi, float *disp, int W, int H, int D, int method, const float *rcp_lut,
                             int n, void *stream);
 

@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _host_rcpss_for_oracle_parity():
+    """The oracle follows the reference and evaluates the sub-pixel reciprocal with the HOST CPU's RCPSS instruction; the library
+    defaults to the fixed Intel table (same numbers on every host).  The GPU parity tests compare against the oracle on whatever
+    host the box has, so they switch the library to the host's RCPSS; tests of the default table switch back themselves."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from vppstereo_b200 import _lib
+            _lib.set_tuning(_lib.TUNE_RCP_HOST, 1)
+    except Exception:
+        pass
+    yield
+
+
 @pytest.fixture(scope="session")
 def orc():
     """The CPU oracle (oracle/*.c through ctypes).  Test infrastructure only."""

@@ -152,3 +152,63 @@ def test_band_with_halo():
             assert rlo == max(lo - halo, 0) and rhi == min(hi + halo, H)
             covered += list(range(lo, hi))
         assert covered == list(range(H))
+
+
+def test_default_rcp_table_is_the_recorded_intel_table(orc, golden_lut):
+    """subPixelRefine's reciprocal (RSGM/StereoBMHelper.cpp:752-756): the library's default is the FIXED Intel table (2048
+    mantissas, csrc/rcp_intel_table.inc) = the table recorded with the golden vectors; VPPB200_TUNE_RCP_HOST selects the host
+    CPU's own RCPSS, which is what the oracle (like the reference) evaluates."""
+    from vppstereo_b200 import _lib
+    L = _lib.lib()
+    lut = np.empty(65536, np.float32)
+    try:
+        _lib.set_tuning(_lib.TUNE_RCP_HOST, 0)
+        assert L.vppb200_rcp_lut_host(lut.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(lut.view(np.uint32), golden_lut.view(np.uint32))
+        _lib.set_tuning(_lib.TUNE_RCP_HOST, 1)
+        assert L.vppb200_rcp_lut_host(lut.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(lut.view(np.uint32), orc.rcp_lut().view(np.uint32))
+    finally:
+        _lib.set_tuning(_lib.TUNE_RCP_HOST, 0)
+
+
+def test_device_pattern_is_a_pure_counter_hash():
+    """vpp_core_opt.device_pattern restates csrc/vpp.cu::counter_pattern: prefix-stable, frame- and seed-dependent, uniform bytes"""
+    from vppstereo_b200 import vpp_core_opt as core
+    a = core.device_pattern(12345, 3, 4096)
+    assert a.dtype == np.uint8 and np.array_equal(a[:100], core.device_pattern(12345, 3, 100))
+    assert not np.array_equal(a, core.device_pattern(12345, 4, 4096)) and not np.array_equal(a, core.device_pattern(12346, 3, 4096))
+    assert 100 < a.mean() < 155 and len(np.unique(a)) == 256
+    # scalar restatement of the same hash
+    def one(seed, f, i):
+        k = (seed ^ (f * 0x9E3779B97F4A7C15)) & (2**64 - 1)
+        key = (k & 0xFFFFFFFF) ^ (((k >> 32) * 0x85EBCA6B) & 0xFFFFFFFF)
+        h = ((i * 0x9E3779B1) & 0xFFFFFFFF) ^ key
+        h ^= h >> 16; h = (h * 0x85EBCA6B) & 0xFFFFFFFF
+        h ^= h >> 13; h = (h * 0xC2B2AE35) & 0xFFFFFFFF
+        h ^= h >> 16
+        return h >> 24
+    assert [one(2**63 + 5, 63, i) for i in (0, 1, 77, 4095)] == [int(core.device_pattern(2**63 + 5, 63, 4096)[i]) for i in (0, 1, 77, 4095)]
+
+
+def test_pipeline_rejects_bad_operands_without_gpu():
+    """VppRsgmPipeline._check validates before any pointer reaches a kernel (exercised here on a stand-in object: no GPU needed)"""
+    import torch
+    from vppstereo_b200.pipeline import VppRsgmPipeline
+    p = VppRsgmPipeline.__new__(VppRsgmPipeline)
+    p.torch, p.H, p.W, p.C, p.N, p.device = torch, 8, 16, 3, 4, torch.device("cuda", 0)
+    p.vpp_stream = p.main_stream = p.tail_stream = None; p._stream_sets = None
+    l = torch.zeros((2, 8, 16, 3), dtype=torch.uint8); g = torch.zeros((2, 8, 16), dtype=torch.float32)
+    assert p._check(l, l, g, host=True) == 2
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        p._check(l, l, g)                                               # host tensors on the device path
+    with pytest.raises(TypeError, match="float32"):
+        p._check(l, l, g.double(), host=True)
+    with pytest.raises(ValueError, match="shape"):
+        p._check(l, l[:1], g, host=True)
+    with pytest.raises(ValueError, match="contiguous"):
+        p._check(l, l, torch.zeros((2, 16, 8), dtype=torch.float32).transpose(1, 2), host=True)
+    with pytest.raises(ValueError, match="does not fit"):
+        p._check(torch.zeros((5, 8, 16, 3), dtype=torch.uint8), l, g, host=True)
+    with pytest.raises(TypeError, match="torch tensor"):
+        p._check(l.numpy(), l, g, host=True)

@@ -56,12 +56,21 @@ def lib():
     return _lib
 
 
-TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS, TUNE_VPP_ROWS, TUNE_SGM_BYTE_SUMS, TUNE_VPP_MD_WAVE, TUNE_SGM_FUSE_COST = 0, 1, 2, 3, 4, 5, 6
+TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS, TUNE_VPP_ROWS, TUNE_SGM_BYTE_SUMS, TUNE_VPP_MD_WAVE, TUNE_SGM_FUSE_COST, TUNE_RCP_HOST = 0, 1, 2, 3, 4, 5, 6, 7
+
+
+_tuning = {}
 
 
 def set_tuning(key, value):
     """Process-wide tuning / test hook (include/vppstereo_b200.h: vppb200_set_tuning)."""
     check(lib().vppb200_set_tuning(int(key), int(value)), "set_tuning")
+    _tuning[int(key)] = int(value)
+
+
+def get_tuning(key, default=0):
+    """The value last set through set_tuning in this process (`default` = the library's initial value)."""
+    return _tuning.get(int(key), default)
 
 
 def launch_count():

@@ -23,33 +23,53 @@ int cuda_fail(const char *what, cudaError_t e)
     return VPPB200_ERR_CUDA;
 }
 
-// rcp_nz_ss(-2k) on this host's CPU (RSGM/StereoBMHelper.cpp:752-756): RCPSS is a vendor-specific table instruction, so the
-// table is produced by the instruction itself and uploaded once per device.
-static void fill_rcp_lut(float *lut)
+// rcp_nz_ss(-2k) (RSGM/StereoBMHelper.cpp:752-756): RCPSS is a vendor-specific table instruction, so the reference's sub-pixel
+// disparities depend on the CPU it runs on.  Default here: the fixed table of Intel's approximation (a function of the
+// operand's exponent and top 11 mantissa bits, tools/make_rcp_table.py), so that every host and every rank of a sharded run
+// produce the same numbers.  VPPB200_TUNE_RCP_HOST = 1 selects the RCPSS of the host CPU instead (parity tests against a
+// reference compiled on that host).
+static const uint32_t kRcpIntelMant[2048] = {
+#include "rcp_intel_table.inc"
+};
+static void fill_rcp_lut_host(float *lut)
 {
     lut[0] = 0.0f;
     for (int k = 1; k < 65536; k++) lut[k] = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(2.0f * (float)(-k))));
 }
+static void fill_rcp_lut_fixed(float *lut)
+{
+    lut[0] = 0.0f;
+    for (int k = 1; k < 65536; k++) {
+        const float x = 2.0f * (float)(-k);
+        uint32_t b;
+        memcpy(&b, &x, 4);
+        const uint32_t r = 0x80000000u | ((253u - ((b >> 23) & 0xFFu)) << 23) | kRcpIntelMant[(b >> 12) & 0x7FFu];
+        memcpy(&lut[k], &r, 4);
+    }
+}
+static std::atomic<int> g_rcp_host{0};
+static void fill_rcp_lut(float *lut) { g_rcp_host.load() ? fill_rcp_lut_host(lut) : fill_rcp_lut_fixed(lut); }
 
 static std::mutex g_lut_mutex;
-static float *g_dev_lut[64] = {nullptr};
+static float *g_dev_lut[2][64] = {{nullptr}, {nullptr}};   // [fixed | host][device]
 
 const float *device_rcp_lut(cudaStream_t st)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lock(g_lut_mutex);
-    if (!g_dev_lut[dev]) {
+    const int which = g_rcp_host.load() ? 1 : 0;
+    if (!g_dev_lut[which][dev]) {
         static float host[65536];
-        fill_rcp_lut(host);
+        which ? fill_rcp_lut_host(host) : fill_rcp_lut_fixed(host);
         float *d = nullptr;
         if (cudaMalloc(&d, sizeof host) != cudaSuccess) return nullptr;
         // synchronous one-time upload: the host table is static and the copy must be complete before first use
         if (cudaMemcpy(d, host, sizeof host, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
-        g_dev_lut[dev] = d;
+        g_dev_lut[which][dev] = d;
     }
     (void)st;
-    return g_dev_lut[dev];
+    return g_dev_lut[which][dev];
 }
 
 // ---- optional per-stage timing of compute_rsgm (bench.py's live roofline measurement) ----------------------------
@@ -265,6 +285,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_VPP_MD_WAVE: vpp_set_md_wave(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_BYTE_SUMS: sweep_set_byte_sums(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_FUSE_COST: sweep_set_fuse_cost(value); return VPPB200_OK;
+        case VPPB200_TUNE_RCP_HOST: g_rcp_host.store(value != 0); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }
 }

@@ -30,8 +30,13 @@ class VppRsgmPipeline:
         self.direction = 1 if left2right else 0
         self.interpolate, self.subpixel = bool(interpolate), bool(subpixel)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("VppRsgmPipeline needs a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.seed = int(seed)
-        self.step = 0
+        self.step = 0                                 # pattern-seed counter
+        self.calls = 0                                # buffer-set parity
         L = _lib.lib()
         self.lib = L
         with torch.cuda.device(self.device):
@@ -83,6 +88,51 @@ class VppRsgmPipeline:
     def workspace_bytes(self):
         return self.ws_rsgm.numel() + self.ws_vpp.numel()
 
+    def _check(self, left, right, hints, out=None, host=False):
+        """Operand validation shared by every entry point: the kernels receive raw pointers, so a wrong dtype, shape, device
+        or a non-contiguous view would be read as garbage or out of bounds.  Returns the batch size."""
+        torch = self.torch
+        for name, t in (("left", left), ("right", right), ("hints", hints)):
+            if not isinstance(t, torch.Tensor):
+                raise TypeError(f"{name}: expected a torch tensor, got {type(t).__name__}")
+        if left.dim() != 4 or tuple(left.shape[1:]) != (self.H, self.W, self.C):
+            raise ValueError(f"left: expected [N,{self.H},{self.W},{self.C}], got {tuple(left.shape)}")
+        N = int(left.shape[0])
+        if not 1 <= N <= self.N:
+            raise ValueError(f"batch of {N} frames does not fit this pipeline (batch={self.N})")
+        want = (("left", left, torch.uint8, (N, self.H, self.W, self.C)), ("right", right, torch.uint8, (N, self.H, self.W, self.C)),
+                ("hints", hints, torch.float32, (N, self.H, self.W)))
+        if out is not None:
+            if not isinstance(out, torch.Tensor):
+                raise TypeError("out: expected a torch tensor")
+            want += (("out", out, torch.float32, (N, self.H, self.W)),)
+        for name, t, dt, shape in want:
+            if t.dtype != dt:
+                raise TypeError(f"{name}: expected {dt}, got {t.dtype}")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+            if not t.is_contiguous():
+                raise ValueError(f"{name}: must be contiguous")
+            on_host = host and name != "out"
+            if on_host:
+                if t.is_cuda:
+                    raise ValueError(f"{name}: expected a host tensor (use run_device for CUDA tensors)")
+            elif not t.is_cuda or t.device != self.device:
+                raise ValueError(f"{name}: expected a CUDA tensor on {self.device}, got {t.device}")
+        return N
+
+    def _next_seed(self, step):
+        """Pattern seed of one call: a function of the pipeline's seed and the call counter (or of an explicit `step`)."""
+        if step is None:
+            self.step += 1
+            step = self.step
+        return (self.seed * 0x9E3779B97F4A7C15 + int(step)) & (2**64 - 1)
+
+    def pattern_seed(self, step):
+        """The rng_seed the VPP kernels receive on call number `step` (1-based) -- with vpp_core_opt.device_pattern this
+        replays the projected pattern of any frame on the host."""
+        return (self.seed * 0x9E3779B97F4A7C15 + int(step)) & (2**64 - 1)
+
     def _phase(self, phases, b, left, lv, rv, out, N, stream):
         L = self.lib
         rc = L.vppb200_compute_rsgm_phases(_lib.ptr(left), _lib.ptr(lv), _lib.ptr(rv), None, None, _lib.ptr(out), self.H, self.W,
@@ -90,7 +140,7 @@ class VppRsgmPipeline:
                                            C.c_size_t(self.ws_rsgm.numel()), N, C.c_void_p(stream.cuda_stream), phases, 2, b)
         _lib.check(rc, "compute_rsgm_phases")
 
-    def run_device(self, left, right, hints, out=None, inputs_ready=None):
+    def run_device(self, left, right, hints, out=None, inputs_ready=None, step=None):
         """VPP (in copies) + compute_rsgm; all operands CUDA tensors [N,H,W,C] uint8 / [N,H,W] float32.
 
         The work is queued on the pipeline's three streams (front / main / tail, see the module docstring) and the caller's
@@ -99,17 +149,22 @@ class VppRsgmPipeline:
         `inputs_ready`: None = the inputs were produced on the current stream (the front phase waits for everything queued
         on it so far, which includes the previous result: no overlap between calls); True = the inputs are complete; a
         torch.cuda.Event = wait for that event.  The inputs must stay untouched until the front phase has read them
-        (`self.front_done[k & 1]` of call k)."""
+        (`self.front_done[k & 1]` of call k).
+        `step`: explicit call number for the pattern seed (default: the pipeline's own counter, 1, 2, ...)."""
+        torch = self.torch
+        N = self._check(left, right, hints, out)
+        with torch.cuda.device(self.device):
+            return self._run_device(left, right, hints, out, inputs_ready, step, N)
+
+    def _run_device(self, left, right, hints, out, inputs_ready, step, N):
         torch, L = self.torch, self.lib
-        N = left.shape[0]
-        assert N <= self.N and left.shape[1:] == (self.H, self.W, self.C)
         out = self.disp[:N] if out is None else out
         caller = torch.cuda.current_stream(self.device)
         front, main, tail = self.vpp_stream, self.main_stream, self.tail_stream
-        b = self.step & 1
+        b = self.calls & 1
+        self.calls += 1
         lv, rv = self.lv2[b][:N], self.rv2[b][:N]
-        self.step += 1
-        seed = (self.seed * 0x9E3779B97F4A7C15 + self.step) & (2**64 - 1)
+        seed = self._next_seed(step)
         # ---- front: VPP into projected-image set b, then the matcher's front phase into buffer set b
         if inputs_ready is None:
             front.wait_stream(caller)
@@ -145,19 +200,24 @@ class VppRsgmPipeline:
         self.lv, self.rv = self.lv2[b], self.rv2[b]     # the projected pair of the latest call
         return out
 
-    def run_device_serial(self, left, right, hints, out=None):
+    def run_device_serial(self, left, right, hints, out=None, step=None):
         """The same computation, everything in order on the current stream (no overlap between calls, no internal streams
         except the right-image branches): what bench.py times stage by stage."""
+        torch = self.torch
+        N = self._check(left, right, hints, out)
+        with torch.cuda.device(self.device):
+            return self._run_device_serial(left, right, hints, out, step, N)
+
+    def _run_device_serial(self, left, right, hints, out, step, N):
         torch, L = self.torch, self.lib
-        N = left.shape[0]
         out = self.disp[:N] if out is None else out
         st = torch.cuda.current_stream(self.device)
         for s in (self.vpp_stream, self.main_stream, self.tail_stream):
             st.wait_stream(s)
-        b = self.step & 1
+        b = self.calls & 1
+        self.calls += 1
         lv, rv = self.lv2[b][:N], self.rv2[b][:N]
-        self.step += 1
-        seed = (self.seed * 0x9E3779B97F4A7C15 + self.step) & (2**64 - 1)
+        seed = self._next_seed(step)
         lv.copy_(left); rv.copy_(right)
         rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), self.W, self.H, self.C, 0, self.wsize,
                                     self.direction, C.c_double(self.blending), C.c_double(self.c_occ), _lib.ptr(self.occ),
@@ -173,7 +233,7 @@ class VppRsgmPipeline:
     def run_host(self, left, right, hints):
         """Host tensors (ideally pinned) in, pinned host float32 [N,H,W] out; the copies are part of the call."""
         torch = self.torch
-        N = left.shape[0]
+        N = self._check(left, right, hints, host=True)
         with torch.cuda.device(self.device):
             self.d_left[:N].copy_(left, non_blocking=True)
             self.d_right[:N].copy_(right, non_blocking=True)
@@ -208,7 +268,7 @@ class VppRsgmPipeline:
         st = ss["sets"][slot]
         if st["busy"]:
             raise RuntimeError(f"submit_host: collect() the batch submitted {self.host_depth} calls ago first")
-        N = left.shape[0]
+        N = self._check(left, right, hints, host=True)
         compute = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
             with torch.cuda.stream(ss["h2d"]):

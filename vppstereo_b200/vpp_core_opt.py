@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["get_seed", "init_rand", "virtual_projection_scan_rnd", "virtual_projection_scan_max_dist", "gt_reshape",
-           "draws_per_frame", "draw_pattern"]
+           "draws_per_frame", "draw_pattern", "device_pattern"]
 
 _state = None
 
@@ -41,6 +41,22 @@ def draw_pattern(n):
     out = np.empty(int(n), np.uint8)
     _lib.check(_lib.lib().vppb200_glibc_rand_fill(_state, out.ctypes.data_as(C.c_void_p), C.c_int64(int(n))), "draw_pattern")
     return out
+
+
+def device_pattern(rng_seed, frame, n):
+    """The first n values of the on-device pattern stream of `frame` (index inside the batch of one call) for `rng_seed`:
+    host restatement of csrc/vpp.cu::counter_pattern, the generator the scans use when no pattern is passed
+    (vppb200_vpp_scan_rnd with pattern = NULL).  Pure integer arithmetic; lets a caller (and the parity tests) replay on the
+    host exactly what the device drew."""
+    M32 = np.uint64(0xFFFFFFFF)
+    k = np.uint64(int(rng_seed) & (2**64 - 1)) ^ np.uint64((int(frame) * 0x9E3779B97F4A7C15) & (2**64 - 1))
+    key = np.uint32(int(k & M32) ^ ((int(k >> np.uint64(32)) * 0x85EBCA6B) & 0xFFFFFFFF))
+    idx = np.arange(int(n), dtype=np.uint64)
+    h = ((idx * np.uint64(0x9E3779B1)) & M32) ^ np.uint64(key)
+    h ^= h >> np.uint64(16); h = (h * np.uint64(0x85EBCA6B)) & M32
+    h ^= h >> np.uint64(13); h = (h * np.uint64(0xC2B2AE35)) & M32
+    h ^= h >> np.uint64(16)
+    return (h >> np.uint64(24)).astype(np.uint8)
 
 
 def draws_per_frame(g, wsize, channels, uniform_color):
