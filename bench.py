@@ -340,7 +340,7 @@ def main():
     gather_buf = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
     L = _lib.lib()
     for key, env in ((_lib.TUNE_SGM_BYTE_SUMS, "VPPB200_BYTE_SUMS"), (_lib.TUNE_SGM_CLUSTERS, "VPPB200_TEAMS"),
-                     (_lib.TUNE_SGM_MAX_STRIP, "VPPB200_MAX_STRIP")):           # A/B experiments only
+                     (_lib.TUNE_SGM_MAX_STRIP, "VPPB200_MAX_STRIP"), (_lib.TUNE_SGM_V_RED, "VPPB200_V_RED")):   # A/B experiments only
         if env in os.environ:
             _lib.set_tuning(key, int(os.environ[env]))
 

@@ -177,7 +177,7 @@ static size_t rsgm_ws_layout(const RsgmDims &d, int n, int sets, int set, void *
     }
     w.S = (uint16_t *)take(vol * 3);                          // one uint16 S, or three uint8 partial-sum volumes
     w.S_xyd = (uint16_t *)take(np * d.D * 2);                 // the reference's xyd order (WTA input, test tap)
-    w.halo = (void *)take(sweep_halo_bytes(d.D));
+    w.halo = (void *)take(sweep_halo_bytes(d.Wp, d.Hp, d.D, n));
     w.dlf = (float *)take(np * 4); w.drf = (float *)take(np * 4);
     w.tail.u8 = (uint8_t *)take(nc); w.tail.label = (int *)take(nc * 4); w.tail.count = (int *)take(nc * 4);
     if (ws) *ws = w;
@@ -285,6 +285,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_VPP_MD_WAVE: vpp_set_md_wave(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_BYTE_SUMS: sweep_set_byte_sums(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_FUSE_COST: sweep_set_fuse_cost(value); return VPPB200_OK;
+        case VPPB200_TUNE_SGM_V_RED: sweep_set_v_red(value); return VPPB200_OK;
         case VPPB200_TUNE_RCP_HOST: g_rcp_host.store(value != 0); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }
@@ -447,7 +448,7 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
                                                 fuse_cost ? w.census_l : nullptr, fuse_cost ? w.census_r : nullptr)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
             } else {
-                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, false, &hook, st,
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, hints == nullptr, &hook, st,
                                                 fuse_cost ? w.census_l : nullptr, fuse_cost ? w.census_r : nullptr)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
                 if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;

@@ -59,14 +59,16 @@ size_t tile_volume_elems(int W, int H, int D, int n);
 int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st);
 int launch_guided_tile(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st);
 struct StageHook { void (*fn)(void *, int); void *ctx; };   // called with VPPB200_STAGE_* when that stage has been queued
-size_t sweep_halo_bytes(int D);                            // workspace of the v-sweep's inter-CTA halo lines
-// byte_sums: costs are plain Hamming distances (<= 24), so each sweep's partial sum fits a byte; S must hold 3 bytes per element
+size_t sweep_halo_bytes(int W, int H, int D, int n);       // workspace of the v-sweep: inter-CTA halo lines, abort flag, P2 table
+// plain_costs: the costs are plain Hamming distances (<= 24, no guided modulation): un-normalised path state, and (option) each
+// sweep's partial sum fits a byte; S must hold 3 bytes per element
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost, uint16_t *S, void *halo_ws, int W, int H, int D, int n, float *dl,
-                          float *dr, const float *lut, bool byte_sums, const StageHook *hook, cudaStream_t st,
+                          float *dr, const float *lut, bool plain_costs, const StageHook *hook, cudaStream_t st,
                           const uint32_t *cen_l = nullptr, const uint32_t *cen_r = nullptr);
 bool sweep_fuses_cost(int W, int H, int D, int n, bool byte_sums);   // the forward sweep can produce the cost volume itself
 void sweep_set_fuse_cost(int on);
 void sweep_set_byte_sums(int on);
+void sweep_set_v_red(int on);
 int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, int n, cudaStream_t st);
 void sweep_set_max_strip(int cols);
 void sweep_set_enabled(int on);
