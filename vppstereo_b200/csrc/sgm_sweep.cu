@@ -624,8 +624,14 @@ struct VArgs {
     int GC;            // 32-column groups per CTA, ceil(G / csize)
 };
 
-static constexpr int VPARTS = 3;   // warps per column group (each owns a third of the disparity pairs)
-static constexpr int VU = 8;       // disparity pairs per operand block (software pipelined)
+#ifndef VPP_VPARTS
+#define VPP_VPARTS 3
+#endif
+#ifndef VPP_VU
+#define VPP_VU 8
+#endif
+static constexpr int VPARTS = VPP_VPARTS;   // warps per column group (each owns a share of the disparity pairs)
+static constexpr int VU = VPP_VU;           // disparity pairs per operand block (software pipelined)
 
 __device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -795,8 +801,11 @@ __device__ __forceinline__ void v2_block(const uint32_t (&cb)[VU], const uint32_
 // S8: the sweep's own sum L1+L2+L3 goes out as a uint8 volume (layout of the cost volume) instead of S += (see sgm_h_kernel).
 // NORM: see above.
 // halo: [CTA][r1 | r3][row parity][K2 state words + VPARTS part minima] inbound buffers, then one abort word at the end
+// Register cap: 96 where the S update is a reduction (no operand registers for S; no spills): the one-CTA-per-SM grid then
+// leaves a quarter of the register file and ~30 KB of shared memory per SM to the front / tail kernels of the neighbouring
+// batches, which run beside the sweep (measured: the sweep alone 6.09 -> 6.39 ms, the pipelined step 23.7 -> 23.3 ms)
 template <int NS, bool FULL, bool S8, bool NORM, bool RED>
-__global__ void __launch_bounds__(((NS - 1) / 32) * VPARTS * 32, 1) sgm_v2_kernel(const uint32_t *__restrict__ p2q_all,
+__global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_t *__restrict__ p2q_all,
                                                                                  const uint16_t *__restrict__ cost_all,
                                                                                  uint32_t *__restrict__ S_all, uint32_t *halo,
                                                                                  uint32_t *abort_flag, VArgs a)
@@ -874,13 +883,20 @@ __global__ void __launch_bounds__(((NS - 1) / 32) * VPARTS * 32, 1) sgm_v2_kerne
             asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(mb_base + (uint32_t)(2 * gl + (int)(tt & 1u)) * 8u)
                          : "memory");
     };
-    auto wait_row = [&](int gq, unsigned tt) {       // every warp of group gq has completed row tt
+    auto try_row = [&](int gq, unsigned tt) -> uint32_t {
         const uint32_t addr = mb_base + (uint32_t)(2 * gq + (int)(tt & 1u)) * 8u, parity = (tt >> 1) & 1u;
         uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        return ok;
+    };
+    auto wait_rows = [&](unsigned tt) {              // every warp of this group and of its ring neighbours has completed row tt
+        uint32_t a0 = 0, a1 = 0, a2 = 0;             // the three waits are issued back to back
         do {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        } while (!ok);
+            if (!a0) a0 = try_row(g_prev, tt);
+            if (!a1) a1 = try_row(g_next, tt);
+            if (!a2) a2 = try_row(gl, tt);
+        } while (!(a0 & a1 & a2));
     };
 
     unsigned t = 0;                                 // rows processed by this team so far, over all its frames
@@ -911,9 +927,7 @@ __global__ void __launch_bounds__(((NS - 1) / 32) * VPARTS * 32, 1) sgm_v2_kerne
             const int d1 = dj > 0 ? slotA : slotB, d2 = lc, d3 = dj > 0 ? slotB : slotA;
             if (t > 0) {
                 // ---- rows t-1 of the groups this row depends on
-                wait_row(gl, t - 1u);
-                wait_row(g_prev, t - 1u);
-                wait_row(g_next, t - 1u);
+                wait_rows(t - 1u);
                 // ---- lines entering from the neighbour CTAs: row t-1 of their edge column, into the ring slot of the entering lane
                 if (enter1 | enter3) {
                     const unsigned pp = (t - 1u) & 1u, tag = ((t - 1u) >> 1) & 7u;
@@ -1142,14 +1156,14 @@ static int plan_v(const TL &t, int n, VPlan *plan)
 }
 
 // the v-sweep's scratch behind the inbound halo lines: [abort flag (256 B)] [P2 table: n * H * G * 32 words]
-static constexpr size_t HALO_LINES_BYTES = (size_t)1024 * 2 * 2 * (128 + VPARTS) * 4;     // generously 1024 CTAs, D <= 256
+static constexpr size_t HALO_LINES_BYTES = (size_t)1024 * 2 * 2 * (128 + 8) * 4;     // generously 1024 CTAs, D <= 256
 size_t sweep_halo_bytes(int W, int H, int D, int n)
 {
     (void)D;
     return HALO_LINES_BYTES + 256 + (size_t)n * H * ((W + 31) / 32) * 32 * 4;
 }
 
-static int g_v_red = 0;             // experiment: S += by red.global.add instead of load + add + store
+static int g_v_red = 1;             // S += by red.global.add (default) instead of load + add + store
 void sweep_set_v_red(int on) { g_v_red = on != 0; }
 
 template <int GC>
@@ -1164,6 +1178,7 @@ static int run_v_t(const uint32_t *p2q, const uint16_t *cost, uint32_t *S, uint3
     void *args[] = {(void *)&p2q, (void *)&cost, (void *)&S, (void *)&halo, (void *)&abort_flag, (void *)&a};
     const void *kern;
     if (s8) kern = full ? (const void *)sgm_v2_kernel<NS, true, true, false, false> : (const void *)sgm_v2_kernel<NS, false, true, false, false>;
+    else if (norm && g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, true, true> : (const void *)sgm_v2_kernel<NS, false, false, true, true>;
     else if (norm) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, true, false> : (const void *)sgm_v2_kernel<NS, false, false, true, false>;
     else if (g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, false, true> : (const void *)sgm_v2_kernel<NS, false, false, false, true>;
     else kern = full ? (const void *)sgm_v2_kernel<NS, true, false, false, false> : (const void *)sgm_v2_kernel<NS, false, false, false, false>;
