@@ -31,7 +31,6 @@ H, W, C, D = 375, 1242, 3, 192
 HP, WP = 384, 1248
 ALG_BYTES_AGG = 4 * WP * HP * D + WP * HP            # aggregate, per frame (368.5 MB)
 ALG_BYTES_VSWEEP = 5 * WP * HP * D + WP * HP         # one v-sweep launch, per frame: uint8 costs in, uint16 S in and out (460 MB)
-NCU_TRAFFIC_VSWEEP = 29.395e9                        # dram read+write per launch, profiles/r01_summary_v4.md (ncu --set full, batch 64)
 ALG_BYTES_VPP = 4 * H * W * C + 4 * H * W + H * W    # + C * in-image patch pixels of the hints (added at run time)
 STAGES = ["pad_gray", "census", "cost_volume", "sgm_h_fwd", "sgm_v_down", "sgm_v_up", "sgm_h_bwd_wta", "wta_unfused", "median_interp",
           "tail"]
@@ -297,13 +296,40 @@ def assert_parity_probe(probe, batch):
 
 
 # ---------------------------------------------------------------------------------------- GPU arm
+def ncu_traffic():
+    """dram read + write bytes of one v-sweep launch from the committed ncu capture of this build (tools/ncu_traffic.py writes
+    profiles/vsweep_traffic.json from the .ncu-rep); None when the file is missing"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "vsweep_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d.get("source")
+    except Exception:
+        return None, None
+
+
+def time_steps(step, n, sync_all, torch):
+    """n calls of step() between two CUDA events on the current stream, barrier + synchronize on both sides -> ms"""
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for k in range(n):
+        step(k)
+    ev1.record()
+    sync_all()
+    return ev0.elapsed_time(ev1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (configs[1]: 64)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="K", choices=["K", "M", "nets"],
+                    help="K = configs[1] (default, the metric's configuration); M = configs[2] (Middlebury frame, maxDistance + occlusion "
+                         "mask, row bands across the GPUs); nets = configs[3] (VPP -> RAFT-Stereo / PSMNet as device tensors)")
+    ap.add_argument("--sustained-steps", type=int, default=200, help="steps of the additional >= 5 s measurement (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (default: one per core)")
     ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
@@ -312,11 +338,19 @@ def main():
         return cpu_worker_main(args.cpu_worker)
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "M":
+        import bench_m
+        return bench_m.main(args)
+    if args.workload == "nets":
+        import bench_nets
+        return bench_nets.main(args)
 
+    import ctypes
     import numpy as np
     import torch
     import torch.distributed as dist
-    from vppstereo_b200 import _lib, synth
+    from vppstereo_b200 import _lib
+    from vppstereo_b200.dist import PeerGather
     from vppstereo_b200.pipeline import VppRsgmPipeline
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,17 +371,31 @@ def main():
     left, right, hints = left_h.to(dev), right_h.to(dev), hints_h.to(dev)
     n_hints = float((hints_h > 0).sum()) / B
     pipe = VppRsgmPipeline(H, W, C, batch=B, dmax=D, device=dev)
-    gather_buf = torch.empty((world * B, H, W), dtype=torch.float32, device=dev) if world > 1 else None
     L = _lib.lib()
     for key, env in ((_lib.TUNE_SGM_BYTE_SUMS, "VPPB200_BYTE_SUMS"), (_lib.TUNE_SGM_CLUSTERS, "VPPB200_TEAMS"),
                      (_lib.TUNE_SGM_MAX_STRIP, "VPPB200_MAX_STRIP"), (_lib.TUNE_SGM_V_RED, "VPPB200_V_RED")):   # A/B experiments only
         if env in os.environ:
             _lib.set_tuning(key, int(os.environ[env]))
 
-    def step_device():
+    # ---- the path's only exchange: every rank's disparities to every rank, once per step, on the copy engines
+    # (dist.PeerGather: peer-mapped buffers, DMA over NVLink, stream memory operations; nothing on the SMs or on the compute
+    # streams).  A consumer stream takes each gathered step and releases its buffer.
+    pg = PeerGather((B, H, W), torch.float32, dev, depth=2) if world > 1 else None
+    consumer = torch.cuda.Stream(dev) if world > 1 else None
+    gstep = [0]
+
+    def gather(out):
+        k = gstep[0]
+        gstep[0] += 1
+        pg.push(k, out)
+        with torch.cuda.stream(consumer):
+            pg.wait(k)
+            pg.release(k)
+
+    def step_device(_k=0):
         out = pipe.run_device(left, right, hints, inputs_ready=True)     # the inputs are resident in HBM (definition of `value`)
-        if world > 1:                                   # the path's only collective: final disparity gather
-            dist.all_gather_into_tensor(gather_buf, out)
+        if world > 1:
+            gather(out)
         return out
 
     def sync_all():
@@ -360,26 +408,20 @@ def main():
         step_device()
     sync_all()
 
-    # ---- timed region 1: device-resident inputs
+    # ---- timed region 1: device-resident inputs, exactly --steps steps
     sampler = ClockSampler(local_rank); sampler.start()
     launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    vpp_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
-    ev0.record()
-    for k in range(args.steps):
-        step_device()
-    ev1.record()
-    sync_all()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = time_steps(step_device, args.steps, sync_all, torch)
     launches = _lib.launch_count() - launches0
-    L.vppb200_stage_timing(0)
+    # the same, sustained over >= 5 s (power and clocks settle): reported beside the --steps figure
+    sus_n = args.sustained_steps if args.sustained_steps > args.steps else 0
+    ms_sus = time_steps(step_device, sus_n, sync_all, torch) if sus_n else None
     clocks = sampler.summary()
-    # per-stage / per-kernel launch durations: a few more steps WITHOUT the cross-step overlap (VPP of step k+1 otherwise
+
+    # ---- per-stage / per-kernel launch durations: a few more steps WITHOUT the cross-step overlap (VPP of step k+1 otherwise
     # shares the SMs with the sweeps of step k and stretches them), CUDA events at the stage boundaries of the stream
-    import ctypes
     L.vppb200_stage_timing(1)
-    for k in range(max(3, min(args.steps, 5))):
+    for k in range(5):
         pipe.run_device_serial(left, right, hints)
     sync_all()
     st_ms = (ctypes.c_float * len(STAGES))(); calls = ctypes.c_int(0)
@@ -390,41 +432,53 @@ def main():
 
     # ---- VPP alone (same stream, CUDA events) for its own roofline line
     lv, rv = pipe.lv, pipe.rv
-    import ctypes as C_
-    def vpp_only():
+
+    def vpp_only(_k=0):
         lv.copy_(left); rv.copy_(right)
-        rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), W, H, C, 0, 3, 1, C_.c_double(0.4), C_.c_double(0.0),
-                                    _lib.ptr(pipe.occ), 0, 1, 1, None, None, C_.c_uint64(7), None, _lib.ptr(pipe.ws_vpp),
-                                    C_.c_size_t(pipe.ws_vpp.numel()), B, _lib.stream_ptr(dev))
+        rc = L.vppb200_vpp_scan_rnd(_lib.ptr(lv), _lib.ptr(rv), _lib.ptr(hints), W, H, C, 0, 3, 1, ctypes.c_double(0.4), ctypes.c_double(0.0),
+                                    _lib.ptr(pipe.occ), 0, 1, 1, None, None, ctypes.c_uint64(7), None, _lib.ptr(pipe.ws_vpp),
+                                    ctypes.c_size_t(pipe.ws_vpp.numel()), B, _lib.stream_ptr(dev))
         _lib.check(rc, "vpp")
     vpp_only(); torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(max(args.steps, 3)):
-        vpp_only()
-    e1.record(); torch.cuda.synchronize(dev)
-    vpp_ms = e0.elapsed_time(e1) / max(args.steps, 3)
+    vpp_ms = time_steps(vpp_only, 10, lambda: torch.cuda.synchronize(dev), torch) / 10
 
     # ---- timed region 2: end to end through the host-buffer API
-    # (submit_host / collect: every step copies its inputs from pinned host memory and its disparities back to the host;
-    #  the copies of neighbouring steps overlap this step's kernels on separate streams, up to three batches in flight:
-    #  exactly args.steps batches are submitted and collected inside the timed region)
-    for _ in range(2):
-        pipe.collect(pipe.submit_host(left_h, right_h, hints_h))
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    pending = []
-    for k in range(args.steps):
-        pending.append(pipe.submit_host(left_h, right_h, hints_h))
-        if len(pending) == pipe.host_depth:
+    # (submit_host / collect: every step copies its inputs from pinned host memory and its disparities back to the host; the
+    #  copies of neighbouring steps overlap this step's kernels on separate streams, up to three batches in flight; at N > 1
+    #  the same per-step gather as above rides along: exactly n batches are submitted, gathered and collected in the region)
+    hook = gather if world > 1 else None
+
+    def e2e_run(n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        pending, res = [], None
+        for k in range(n):
+            pending.append(pipe.submit_host(left_h, right_h, hints_h, on_computed=hook))
+            if len(pending) == pipe.host_depth:
+                res = pipe.collect(pending.pop(0))
+        while pending:
             res = pipe.collect(pending.pop(0))
-    while pending:
-        res = pipe.collect(pending.pop(0))
-    e1.record()
-    sync_all()
-    e2e_ms = e0.elapsed_time(e1)
+        ev1.record()
+        sync_all()
+        return ev0.elapsed_time(ev1), res
+    e2e_run(3)
+    e2e_ms, res = e2e_run(args.steps)
+    e2e_sus_ms = e2e_run(sus_n)[0] if sus_n else None
     check_val = float(res[0].mean())
+
+    # ---- single-frame latency (test.py runs batch 1): host frame in -> host disparity out, one frame at a time
+    lat_ms = None
+    if rank == 0:
+        p1 = VppRsgmPipeline(H, W, C, batch=1, dmax=D, device=dev)
+        l1, r1, g1 = left_h[:1].clone().pin_memory(), right_h[:1].clone().pin_memory(), hints_h[:1].clone().pin_memory()
+        for _ in range(3):
+            p1.run_host(l1, r1, g1)
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter(); p1.run_host(l1, r1, g1); ts.append((time.perf_counter() - t0) * 1e3)
+        lat_ms = sorted(ts)[len(ts) // 2]
+        p1.close()
 
     # ---- parity probe: the timed pipeline object on rank 0's inputs with a fixed pattern seed, against oracle-derived digests
     probe = None
@@ -432,10 +486,11 @@ def main():
         probe = assert_parity_probe(parity_probe(B, pipe=pipe, tensors=(left, right, hints)), B)
 
     # max over ranks
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    vals = [ms_total, e2e_ms, ms_sus or 0.0, e2e_sus_ms or 0.0]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, ms_sus_m, e2e_sus_m = (float(x) for x in t)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -451,31 +506,46 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         frames_total = world * B * args.steps
-        v_s = 0.5 * (stage_ms["sgm_v_down"] + stage_ms["sgm_v_up"]) * 1e-3          # average launch of the dominant kernel
+        v_s = 0.5 * (stage_ms["sgm_v_down"] + stage_ms["sgm_v_up"]) * 1e-3          # average launch of the dominant kernel (+ its P2 table kernel)
         achieved = ALG_BYTES_VSWEEP * B / v_s / 1e9
         agg_s = sum(stage_ms[k] for k in ("sgm_h_fwd", "sgm_v_down", "sgm_v_up", "sgm_h_bwd_wta")) * 1e-3
         agg_achieved = ALG_BYTES_AGG * B / agg_s / 1e9
         vpp_bytes = (ALG_BYTES_VPP + C * 9 * n_hints) * B
+        traffic, traffic_src = ncu_traffic()
+        gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
+
+        def roof(nbytes, ms, what):
+            return {"what": what, "achieved": gbs(nbytes, ms), "peak": peak, "unit": "GB/s", "frac": gbs(nbytes, ms) / peak, "ms": ms,
+                    "algorithmic_bytes": nbytes}
         line = {
             "metric": METRIC, "value": frames_total / (ms_total * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": "configs[1]: KITTI-shape 1242x375x3 pairs, LiDAR-like 5% hints, VPP rnd 3x3 blending 0.4 + rSGM D=192, batch 64 per GPU",
                        "batch_per_gpu": B, "frames_per_step": world * B, "l2": "inputs per step (298 MB) and cost volumes (17.7 GB) exceed the 126 MB L2",
-                       "collective": "all_gather of disparities per step" if world > 1 else "none",
+                       "collective": (f"per step, every rank's disparities to every rank ({B * H * W * 4 * (world - 1)} B out per rank): "
+                                      f"{'copy engines over peer-mapped memory (dist.PeerGather), off the SMs and off the compute streams' if pg.available else 'NCCL all_gather (peer mapping unavailable: ' + pg.why + ')'}; "
+                                      "inside both timed regions; configs[4]'s 1024-frame sequence = 16/N such steps per rank") if world > 1 else "none",
                        "host_affinity": f"GPU-local NUMA cores ({len(numa_cpus)})" if numa_cpus else "unchanged",
                        "overlap": "three-phase software pipeline across steps on three streams: front(k+1) = VPP + pad/gray/census/cost volume, main(k) = SGM sweeps + WTA, tail(k-1) = median..fills; two buffer sets; right-image branches on side streams",
                        "stage_ms_per_step_serial": {k: round(v, 3) for k, v in stage_ms.items()}, "vpp_ms_per_step": round(vpp_ms, 3),
-                       "rsgm_fps": B / (rsgm_ms * 1e-3), "vpp_pairs_per_s": B / (vpp_ms * 1e-3), "check_mean_disp": check_val},
-            "roofline": {"bound": "hbm", "kernel": "sgm_v_kernel (v-sweep: paths r1+r2+r3 of one pass, 2 launches per step)",
+                       "rsgm_fps": B / (rsgm_ms * 1e-3), "vpp_pairs_per_s": B / (vpp_ms * 1e-3), "check_mean_disp": check_val,
+                       "latency_batch1_ms": lat_ms,
+                       "latency_note": "one K-shape frame, pinned host in -> host out through VppRsgmPipeline(batch=1).run_host, median of 20; the reference needs cpu_baseline.single_frame_latency_s per frame on one core"},
+            "sustained": None if not sus_n else {"steps": sus_n, "value": world * B * sus_n / (ms_sus_m * 1e-3), "ms_per_step": ms_sus_m / sus_n,
+                                                 "e2e_value": world * B * sus_n / (e2e_sus_m * 1e-3), "seconds": ms_sus_m * 1e-3,
+                                                 "what": "the same two timed regions run for --sustained-steps steps (>= 5 s each)"},
+            "roofline": {"bound": "hbm", "kernel": "sgm_v2_kernel (v-sweep: paths r1+r2+r3 of one pass, 2 launches per step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_VSWEEP if B == 64 else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ALG_BYTES_VSWEEP * B, "launch_ms": v_s * 1e3,
-                         "aggregate_8_paths": {"what": "h_fwd + v_down + v_up + h_bwd(+WTA) vs SURVEY 8d aggregate bytes (4WHD+WH)",
-                                               "achieved": agg_achieved, "frac": agg_achieved / peak, "ms": agg_s * 1e3,
-                                               "algorithmic_bytes": ALG_BYTES_AGG * B},
-                         "vpp": {"achieved": vpp_bytes / (vpp_ms * 1e-3) / 1e9, "frac": vpp_bytes / (vpp_ms * 1e-3) / 1e9 / peak,
-                                 "algorithmic_bytes": vpp_bytes}},
+                         "traffic": traffic if B == 64 else None, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_VSWEEP * B, "launch_ms": v_s * 1e3},
+            # the other kernels of the step against the same peak, each on SURVEY.md 8(d)'s bytes for its row
+            "roofline_aggregate_8_paths": roof(ALG_BYTES_AGG * B, agg_s * 1e3, "h_fwd + v_down + v_up + h_bwd(+WTA) vs SURVEY 8d aggregate bytes (4WHD+WH)"),
+            "roofline_vpp": roof(vpp_bytes, vpp_ms, "VPP rnd: images in/out + hints + mask + pattern draws (SURVEY 8d)"),
+            "roofline_census": roof(2 * 5 * WP * HP * B, stage_ms["census"], "census 5x5 of both images: 1 byte in, 4 bytes out per pixel (SURVEY 8d)"),
+            "roofline_cost_volume": roof((8 * WP * HP + WP * HP * D) * B, stage_ms["cost_volume"], "Hamming volume: two census images in, uint8 volume out"),
+            "roofline_h_fwd": roof(3 * WP * HP * D * B, stage_ms["sgm_h_fwd"], "h-sweep fwd: uint8 costs in, uint16 S out"),
+            "roofline_h_bwd_wta": roof((3 * WP * HP * D + 8 * WP * HP) * B, stage_ms["sgm_h_bwd_wta"], "h-sweep bwd + WTA: costs + S in, two disparity maps out"),
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(left_h.numel() + right_h.numel() + hints_h.numel() * 4),
                     "d2h_bytes_per_step": int(B * H * W * 4)},
@@ -486,6 +556,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        pg.close()
         dist.destroy_process_group()
 
 

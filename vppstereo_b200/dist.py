@@ -59,6 +59,144 @@ def gather_frames(local, n_frames, group=None, dst=None):
     return torch.cat([bufs[r][: sizes[r]] for r in range(world)], 0)
 
 
+class PeerGather:
+    """All-gather of per-step results between the ranks of ONE node on the COPY ENGINES: no SM kernel, nothing on the compute
+    streams.  The frame-sharded path needs exactly one exchange -- every rank's disparities to every rank -- and the sweeps that
+    produce them are cooperative launches that want every SM, so an SM-resident collective kernel on the same device either
+    waits for them or makes them wait.  Here every rank owns `depth` gather buffers [world, *shape]; after step k rank r copies
+    its shard into slot r of every peer's buffer (cudaMemcpyAsync onto peer-mapped memory: DMA over NVLink), then a 4-byte step
+    counter into the peer's flag word r; a consumer stream waits on its own flag words with stream memory operations
+    (cuStreamWaitValue32, again no kernel).  Peer memory is mapped once with CUDA IPC handles exchanged through the process
+    group (torch.distributed carries only that hand-shake and the barriers).
+
+        pg = PeerGather((B, H, W), torch.float32, device)            # collective: all ranks
+        pg.push(k, disp)              # after step k (disp produced on the current stream)
+        full = pg.wait(k)             # [world, B, H, W] of step k, valid on the current stream
+        pg.release(k)                 # when the reads of `full` have been queued on the current stream
+
+    `available` is False (and push / wait fall back to one NCCL all_gather per step) when peer mapping is not possible."""
+
+    MAX_STEPS = 1 << 20
+
+    def __init__(self, shape, dtype, device, group=None, depth=2):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.device = torch.device(device)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.depth = int(depth)
+        self.shape = tuple(shape)
+        with torch.cuda.device(self.device):
+            self.bufs = torch.empty((self.depth, self.world) + self.shape, dtype=dtype, device=self.device)
+            # [0]: flags[r] = steps rank r has pushed here; [1]: credits[p] = steps peer p has released (consumed) of MY pushes
+            self.words = torch.zeros((2, max(self.world, 1)), dtype=torch.int32, device=self.device)
+            self.ticks = torch.arange(self.MAX_STEPS, dtype=torch.int32, device=self.device)
+            self.copy_stream = torch.cuda.Stream(self.device)
+            torch.cuda.current_stream(self.device).synchronize()
+        self.available, self.why = False, "single rank"
+        self.peer_bufs, self.peer_words = [self.bufs], [self.words]
+        if self.world > 1:
+            self._map_peers()
+
+    def _map_peers(self):
+        torch, dist = self.torch, self.dist
+        ok, why, mine = True, "", None
+        try:
+            from cuda.bindings import driver as cu
+            from torch.multiprocessing.reductions import reduce_tensor
+            self._cu = cu
+            mine = (reduce_tensor(self.bufs), reduce_tensor(self.words))
+        except Exception as e:                          # no cuda-python / no IPC: every rank must take the same branch
+            ok, why = False, f"{type(e).__name__}: {e}"
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (ok, why, mine), group=self.group)
+        bad = [w for o, w, _ in everyone if not o]
+        if not bad:
+            try:
+                self.peer_bufs, self.peer_words = [], []
+                for r, (_, _, handles) in enumerate(everyone):
+                    if r == self.rank:
+                        self.peer_bufs.append(self.bufs); self.peer_words.append(self.words)
+                    else:
+                        (fb, ab), (fw, aw) = handles
+                        self.peer_bufs.append(fb(*ab)); self.peer_words.append(fw(*aw))
+            except Exception as e:
+                ok, why = False, f"{type(e).__name__}: {e}"
+        else:
+            ok, why = False, bad[0]
+        verdicts = [None] * self.world
+        dist.all_gather_object(verdicts, (ok, why), group=self.group)
+        bad = [w for o, w in verdicts if not o]
+        self.available, self.why = (not bad), (bad[0] if bad else "peer-mapped (CUDA IPC), copy engines")
+        if not self.available:
+            self.peer_bufs, self.peer_words = [self.bufs], [self.words]
+
+    def _wait_word(self, stream, tensor, index, value):
+        """stream waits until (int32)tensor[index] >= value (stream memory operation, no kernel)"""
+        cu = self._cu
+        err, = cu.cuStreamWaitValue32(cu.CUstream(stream.cuda_stream), cu.CUdeviceptr(tensor.data_ptr() + 4 * index), int(value),
+                                      cu.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ)
+        if int(err) != 0:
+            raise RuntimeError(f"cuStreamWaitValue32 failed: {err}")
+
+    def push(self, k, local):
+        """Step k's shard (produced on the current stream) goes to every rank's buffer k % depth, slot `rank`."""
+        torch = self.torch
+        if k + 1 >= self.MAX_STEPS:
+            raise ValueError("PeerGather: step counter exhausted")
+        cur = torch.cuda.current_stream(self.device)
+        if not self.available:
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self.bufs[k % self.depth], local.contiguous(), group=self.group)
+            else:
+                self.bufs[k % self.depth, 0].copy_(local, non_blocking=True)
+            return
+        cs = self.copy_stream
+        cs.wait_stream(cur)
+        with torch.cuda.device(self.device), torch.cuda.stream(cs):
+            for j in range(self.world):
+                p = (self.rank + j) % self.world                         # own slot first, then the peers in ring order
+                if k >= self.depth and p != self.rank:
+                    self._wait_word(cs, self.words[1], p, k - self.depth + 1)       # peer p has released step k - depth
+                self.peer_bufs[p][k % self.depth, self.rank].copy_(local, non_blocking=True)
+                self.peer_words[p][0, self.rank:self.rank + 1].copy_(self.ticks[k + 1:k + 2], non_blocking=True)
+
+    def wait(self, k):
+        """[world, *shape] of step k; the current stream waits (on the device) until every rank's shard has landed."""
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.device)
+        if self.available:
+            with torch.cuda.device(self.device):
+                for r in range(self.world):
+                    self._wait_word(cur, self.words[0], r, k + 1)
+        elif self.world == 1:
+            pass                                     # same stream as push
+        return self.bufs[k % self.depth]
+
+    def release(self, k):
+        """The reads of step k's gathered buffer have been queued on the current stream: tell every peer it may be overwritten."""
+        torch = self.torch
+        if not self.available:
+            return
+        cs = self.copy_stream
+        cs.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.device(self.device), torch.cuda.stream(cs):
+            for p in range(self.world):
+                if p != self.rank:
+                    self.peer_words[p][1, self.rank:self.rank + 1].copy_(self.ticks[k + 1:k + 2], non_blocking=True)
+
+    def close(self):
+        """Collective: nobody unmaps while a peer may still write."""
+        try:
+            self.torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                self.dist.barrier(group=self.group)
+        except Exception:
+            pass
+        self.peer_bufs, self.peer_words = [self.bufs], [self.words]
+
+
 def run_sharded(n_frames, make_inputs, process, chunk=16, group=None, gather=True):
     """Frame-sharded driver.  make_inputs(lo, hi) -> inputs of frames [lo, hi); process(inputs) -> tensor [hi-lo, ...].
     Returns the gathered [n_frames, ...] result (every rank) or the local shard when gather=False."""

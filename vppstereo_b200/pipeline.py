@@ -258,10 +258,12 @@ class VppRsgmPipeline:
                 self._stream_sets = dict(sets=sets, h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device), turn=0)
         return self._stream_sets
 
-    def submit_host(self, left, right, hints):
+    def submit_host(self, left, right, hints, on_computed=None):
         """Queue one batch of host tensors (pinned for real overlap); returns a ticket for collect().  At most `host_depth`
         (3) batches are in flight: submitting one more first requires collecting the oldest.  Keeping two batches queued
-        behind the running one lets the next batch's inputs arrive, and its front phase start, while the current sweeps run."""
+        behind the running one lets the next batch's inputs arrive, and its front phase start, while the current sweeps run.
+        `on_computed(disp)`: called with the batch's device result right after it has been queued (current stream = the stream
+        it becomes valid on), e.g. to hand it to dist.PeerGather.push beside the device->host copy."""
         torch = self.torch
         ss = self._streaming()
         slot = ss["turn"] % self.host_depth
@@ -280,6 +282,8 @@ class VppRsgmPipeline:
             compute.wait_event(st["copied_in"])
             self.run_device(st["left"][:N], st["right"][:N], st["hints"][:N], out=st["disp"][:N], inputs_ready=st["copied_in"])
             st["computed"].record(compute)
+            if on_computed is not None:
+                on_computed(st["disp"][:N])
             with torch.cuda.stream(ss["d2h"]):
                 ss["d2h"].wait_event(st["computed"])
                 st["h_disp"][:N].copy_(st["disp"][:N], non_blocking=True)
