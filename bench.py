@@ -25,6 +25,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The path keeps ~10 CUDA streams busy (three pipeline phases, two side branches, H2D / D2H, the peer gather's copy, credit and
+# consumer streams); with the default of 8 hardware connections two of them share a queue and a stream that is parked in a
+# wait (peer flag, event) holds up the one behind it.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "VPP pairs/s & rSGM fps @1242x375, 5% hints, D=192; % of HBM peak"
 H, W, C, D = 375, 1242, 3, 192
@@ -383,8 +387,13 @@ def main():
     pg = PeerGather((B, H, W), torch.float32, dev, depth=2) if world > 1 else None
     consumer = torch.cuda.Stream(dev) if world > 1 else None
     gstep = [0]
+    gmode = os.environ.get("VPPB200_GATHER", "p2p")           # experiments: none | nccl | p2p (default)
+    if pg is not None and gmode == "nccl":
+        pg.available, pg.why = False, "forced by VPPB200_GATHER=nccl"
 
     def gather(out):
+        if gmode == "none":
+            return
         k = gstep[0]
         gstep[0] += 1
         pg.push(k, out)

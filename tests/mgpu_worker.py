@@ -55,8 +55,8 @@ def main():
                     msgs.append(f"{mode}: step {k} shard {r}: {(a != b).sum()} of {a.size} values differ")
             solo.close()
         pipe.close()
-        pg.close()
         msgs.append(f"{mode}: available={pg.available} ({pg.why})")
+        pg.close()
     bad = [m for m in msgs if "differ" in m]
     with open(os.path.join(outdir, f"rank{rank}.txt"), "w") as f:
         f.write(("FAIL\n" if bad else "OK\n") + "\n".join(msgs) + "\n")

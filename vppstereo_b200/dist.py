@@ -87,40 +87,87 @@ class PeerGather:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.depth = int(depth)
         self.shape = tuple(shape)
+        self.dtype = dtype
+        self._raw, self._opened = [], []
+        self.available, self.why = False, "single rank"
         with torch.cuda.device(self.device):
-            self.bufs = torch.empty((self.depth, self.world) + self.shape, dtype=dtype, device=self.device)
-            # [0]: flags[r] = steps rank r has pushed here; [1]: credits[p] = steps peer p has released (consumed) of MY pushes
-            self.words = torch.zeros((2, max(self.world, 1)), dtype=torch.int32, device=self.device)
             self.ticks = torch.arange(self.MAX_STEPS, dtype=torch.int32, device=self.device)
             self.copy_stream = torch.cuda.Stream(self.device)
-            torch.cuda.current_stream(self.device).synchronize()
-        self.available, self.why = False, "single rank"
-        self.peer_bufs, self.peer_words = [self.bufs], [self.words]
+            self.credit_stream = torch.cuda.Stream(self.device)
         if self.world > 1:
             self._map_peers()
+        if not self.available:                        # plain torch buffers (NCCL fallback / single rank)
+            with torch.cuda.device(self.device):
+                self.bufs = torch.empty((self.depth, self.world) + self.shape, dtype=dtype, device=self.device)
+                self.words = torch.zeros((2, max(self.world, 1)), dtype=torch.int32, device=self.device)
+            self.peer_bufs, self.peer_words = [self.bufs], [self.words]
+        torch.cuda.current_stream(self.device).synchronize()
+
+    class _RawView:
+        """a raw device allocation as something torch.as_tensor understands"""
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+    def _views(self, ptr):
+        """(gather buffers, flag / credit words) over one raw allocation: [depth * world * shape | 2 * world int32]"""
+        torch = self.torch
+        nb = self.depth * self.world * int(np.prod(self.shape)) * torch.empty((), dtype=self.dtype).element_size()
+        nb_al = (nb + 255) & ~255
+        raw = torch.as_tensor(self._RawView(ptr, nb_al + 8 * self.world), device=self.device)
+        bufs = raw[:nb].view(self.dtype).view((self.depth, self.world) + self.shape)
+        words = raw[nb_al:nb_al + 8 * self.world].view(torch.int32).view(2, self.world)
+        return bufs, words, nb_al + 8 * self.world
 
     def _map_peers(self):
+        """Every rank cudaMallocs its buffers, exports them with cudaIpcGetMemHandle and opens the peers' handles IN THE CONTEXT
+        OF ITS OWN DEVICE (cudaIpcMemLazyEnablePeerAccess): the peer memory then is ordinary device-addressable memory for this
+        GPU's DMA engines and kernels, reached over NVLink -- the way NCCL maps its buffers.  (torch's own CUDA-IPC rebuild opens
+        the handle in a context on the PEER device instead; copies into it from here were staged through the host: 25 GB/s.)"""
         torch, dist = self.torch, self.dist
-        ok, why, mine = True, "", None
+        ok, why, handle = True, "", None
         try:
             from cuda.bindings import driver as cu
-            from torch.multiprocessing.reductions import reduce_tensor
-            self._cu = cu
-            mine = (reduce_tensor(self.bufs), reduce_tensor(self.words))
+            from cuda.bindings import runtime as rt
+            self._cu, self._rt = cu, rt
+            with torch.cuda.device(self.device):
+                elem = torch.empty((), dtype=self.dtype).element_size()
+                nb = self.depth * self.world * int(np.prod(self.shape)) * elem
+                total = ((nb + 255) & ~255) + 8 * self.world
+                err, ptr = rt.cudaMalloc(total)
+                if int(err) != 0:
+                    raise RuntimeError(f"cudaMalloc({total}): {err}")
+                self._raw.append(int(ptr))
+                err, = rt.cudaMemset(ptr, 0, total)
+                err2, h = rt.cudaIpcGetMemHandle(ptr)
+                if int(err) != 0 or int(err2) != 0:
+                    raise RuntimeError(f"cudaIpcGetMemHandle: {err} {err2}")
+                handle = (bytes(h.reserved), self.device.index)
+                rt.cudaDeviceSynchronize()
         except Exception as e:                          # no cuda-python / no IPC: every rank must take the same branch
             ok, why = False, f"{type(e).__name__}: {e}"
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, (ok, why, mine), group=self.group)
+        dist.all_gather_object(everyone, (ok, why, handle), group=self.group)
         bad = [w for o, w, _ in everyone if not o]
         if not bad:
             try:
+                rt = self._rt
                 self.peer_bufs, self.peer_words = [], []
-                for r, (_, _, handles) in enumerate(everyone):
-                    if r == self.rank:
-                        self.peer_bufs.append(self.bufs); self.peer_words.append(self.words)
-                    else:
-                        (fb, ab), (fw, aw) = handles
-                        self.peer_bufs.append(fb(*ab)); self.peer_words.append(fw(*aw))
+                with torch.cuda.device(self.device):
+                    for r, (_, _, (hb, pdev)) in enumerate(everyone):
+                        if r == self.rank:
+                            pptr = self._raw[0]
+                        else:
+                            if pdev != self.device.index and not torch.cuda.can_device_access_peer(self.device.index, pdev):
+                                raise RuntimeError(f"device {self.device.index} cannot access peer device {pdev}")
+                            h = rt.cudaIpcMemHandle_t()
+                            h.reserved = hb
+                            err, pptr = rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)
+                            if int(err) != 0:
+                                raise RuntimeError(f"cudaIpcOpenMemHandle(rank {r}): {err}")
+                            self._opened.append(int(pptr))
+                        b, w, _ = self._views(int(pptr))
+                        self.peer_bufs.append(b); self.peer_words.append(w)
+                self.bufs, self.words = self.peer_bufs[self.rank], self.peer_words[self.rank]
             except Exception as e:
                 ok, why = False, f"{type(e).__name__}: {e}"
         else:
@@ -130,7 +177,20 @@ class PeerGather:
         bad = [w for o, w in verdicts if not o]
         self.available, self.why = (not bad), (bad[0] if bad else "peer-mapped (CUDA IPC), copy engines")
         if not self.available:
-            self.peer_bufs, self.peer_words = [self.bufs], [self.words]
+            self._unmap()
+
+    def _unmap(self):
+        rt = getattr(self, "_rt", None)
+        if rt is None:
+            return
+        self.peer_bufs, self.peer_words = [], []
+        with self.torch.cuda.device(self.device):
+            for p in self._opened:
+                rt.cudaIpcCloseMemHandle(p)
+            self._opened = []
+            for p in self._raw:
+                rt.cudaFree(p)
+            self._raw = []
 
     def _wait_word(self, stream, tensor, index, value):
         """stream waits until (int32)tensor[index] >= value (stream memory operation, no kernel)"""
@@ -139,6 +199,18 @@ class PeerGather:
                                       cu.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ)
         if int(err) != 0:
             raise RuntimeError(f"cuStreamWaitValue32 failed: {err}")
+
+    def _copy(self, stream, dst, src):
+        """dst <- src (same byte size, both contiguous) as ONE asynchronous driver-level copy on `stream` of this rank's own
+        device.  dst may be peer-mapped memory: with unified addressing the DMA engine of this GPU writes it over NVLink.
+        (torch's own cross-device copy_ would also queue events on a stream of the PEER device in this process' context on
+        that GPU, and that second context then time-slices with the peer's kernels: measured 1.9 ms per step.)"""
+        cu = self._cu
+        nbytes = src.numel() * src.element_size()
+        assert dst.numel() * dst.element_size() == nbytes and src.is_contiguous() and dst.is_contiguous()
+        err, = cu.cuMemcpyAsync(cu.CUdeviceptr(dst.data_ptr()), cu.CUdeviceptr(src.data_ptr()), nbytes, cu.CUstream(stream.cuda_stream))
+        if int(err) != 0:
+            raise RuntimeError(f"cuMemcpyAsync failed: {err}")
 
     def push(self, k, local):
         """Step k's shard (produced on the current stream) goes to every rank's buffer k % depth, slot `rank`."""
@@ -152,15 +224,17 @@ class PeerGather:
             else:
                 self.bufs[k % self.depth, 0].copy_(local, non_blocking=True)
             return
+        local = local.contiguous()
         cs = self.copy_stream
         cs.wait_stream(cur)
-        with torch.cuda.device(self.device), torch.cuda.stream(cs):
+        local.record_stream(cs)
+        with torch.cuda.device(self.device):
             for j in range(self.world):
                 p = (self.rank + j) % self.world                         # own slot first, then the peers in ring order
                 if k >= self.depth and p != self.rank:
                     self._wait_word(cs, self.words[1], p, k - self.depth + 1)       # peer p has released step k - depth
-                self.peer_bufs[p][k % self.depth, self.rank].copy_(local, non_blocking=True)
-                self.peer_words[p][0, self.rank:self.rank + 1].copy_(self.ticks[k + 1:k + 2], non_blocking=True)
+                self._copy(cs, self.peer_bufs[p][k % self.depth, self.rank], local)
+                self._copy(cs, self.peer_words[p][0, self.rank:self.rank + 1], self.ticks[k + 1:k + 2])
 
     def wait(self, k):
         """[world, *shape] of step k; the current stream waits (on the device) until every rank's shard has landed."""
@@ -179,12 +253,12 @@ class PeerGather:
         torch = self.torch
         if not self.available:
             return
-        cs = self.copy_stream
+        cs = self.credit_stream                      # not the push stream: a late peer must not hold back this rank's next push
         cs.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.device(self.device), torch.cuda.stream(cs):
+        with torch.cuda.device(self.device):
             for p in range(self.world):
                 if p != self.rank:
-                    self.peer_words[p][1, self.rank:self.rank + 1].copy_(self.ticks[k + 1:k + 2], non_blocking=True)
+                    self._copy(cs, self.peer_words[p][1, self.rank:self.rank + 1], self.ticks[k + 1:k + 2])
 
     def close(self):
         """Collective: nobody unmaps while a peer may still write."""
@@ -194,7 +268,10 @@ class PeerGather:
                 self.dist.barrier(group=self.group)
         except Exception:
             pass
-        self.peer_bufs, self.peer_words = [self.bufs], [self.words]
+        if self._raw:                                # raw IPC-exported allocation and the peers' mappings
+            self.bufs = self.words = None
+            self._unmap()
+            self.available = False
 
 
 def run_sharded(n_frames, make_inputs, process, chunk=16, group=None, gather=True):
