@@ -13,6 +13,9 @@ copied into the repo. Outputs (oracle/_ref/):
                             no FMA contraction, matching the reference's own default distutils build)
   rsgm_ref.pycode, vpp_standalone_ref.pycode, filter_ref.pycode
                          <- byte-compiled models/rsgm/rsgm.py, vpp_standalone.py, filter.py (glue + numba kernels)
+  refmodels/{raft_stereo,psmnet}/*.pyc, losses_ref.pycode
+                         <- byte-compiled models/raft_stereo, models/psmnet (the CONSUMERS of the projected images, BASELINE
+                            configs[3]: random-initialised in the tests / bench, never rebuilt here) and losses.py (sample_hints)
 Run every process that calls pyrSGM with MALLOC_MMAP_THRESHOLD_=65536: the reference
 reads uninitialised malloc memory in census rows 0,1,H-2,H-1.
 """
@@ -62,6 +65,31 @@ def build(force=False):
         if force or not os.path.exists(d):
             py_compile.compile(os.path.join(REF, src), cfile=d, doraise=True)
             print("+ py_compile", src, "->", d)
+    d = os.path.join(OUT, "losses_ref.pycode")
+    if (force or not os.path.exists(d)) and os.path.exists(os.path.join(REF, "losses.py")):
+        py_compile.compile(os.path.join(REF, "losses.py"), cfile=d, doraise=True)
+    # the two networks as sourceless packages (relative imports keep working): refmodels/<pkg>/<module>.pyc
+    pk = os.path.join(OUT, "refmodels")
+    for sub in ("raft_stereo", "raft_stereo/utils", "psmnet"):
+        srcdir = os.path.join(REF, "models", sub)
+        dstdir = os.path.join(pk, sub)
+        os.makedirs(dstdir, exist_ok=True)
+        names = [f for f in os.listdir(srcdir) if f.endswith(".py")]
+        if "__init__.py" not in names:
+            names.append("__init__.py")
+        for f in names:
+            d = os.path.join(dstdir, f + "c")
+            if force or not os.path.exists(d):
+                src = os.path.join(srcdir, f)
+                if not os.path.exists(src):             # a directory without __init__.py (raft_stereo/utils): empty package marker
+                    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as t:
+                        src = t.name
+                py_compile.compile(src, cfile=d, doraise=True)
+    d = os.path.join(pk, "__init__.pyc")
+    if force or not os.path.exists(d):
+        with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as t:
+            pass
+        py_compile.compile(t.name, cfile=d, doraise=True)
     return True
 
 

@@ -53,6 +53,33 @@ def load():
     return ns
 
 
+def load_nets():
+    """(RAFTStereo, PSMNet): the reference's own network classes (models/raft_stereo/raft_stereo.py:23, models/psmnet/psmnet.py:86)
+    from the byte-compiled packages under oracle/_ref/refmodels.  They are the consumers of the projected images (BASELINE
+    configs[3]); tests and bench.py instantiate them with random weights.  `opt_einsum` (imported, never called, by
+    models/raft_stereo/update.py:4) is absent from this image: a stand-in module is registered."""
+    if not os.path.isdir(os.path.join(REF_DIR, "refmodels")):
+        raise RuntimeError("oracle/_ref/refmodels not built: run `python oracle/build_ref.py` where /root/reference exists")
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    if "opt_einsum" not in sys.modules:
+        try:
+            import opt_einsum  # noqa: F401
+        except ImportError:
+            import torch
+            stub = types.ModuleType("opt_einsum")
+            stub.contract = torch.einsum
+            sys.modules["opt_einsum"] = stub
+    raft = importlib.import_module("refmodels.raft_stereo.raft_stereo")
+    psm = importlib.import_module("refmodels.psmnet.psmnet")
+    return raft.RAFTStereo, psm.PSMNet
+
+
+def load_losses():
+    """the reference's losses.py (sample_hints, losses.py:5-10), byte-compiled"""
+    return _load_pyc("losses_ref", "losses_ref.pycode")
+
+
 def zero_unwritten_census(ct):
     """The reference never writes census rows 0,1,H-2,H-1 nor (H-3, {W-16,W-15,W-2,W-1}) (RSGM/FastFilters.cpp:181-442)
     and returns whatever malloc held there (non-deterministic, feeds the cost volume through row H-3).  Parity is

@@ -17,7 +17,7 @@ ERR_WIDTH, ERR_DISP, ERR_THREADS, ERR_UNIQUENESS, ERR_METHOD, ERR_WORKSPACE, ERR
 
 # every symbol include/vppstereo_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "vppb200_version", "vppb200_last_cuda_error", "vppb200_launch_count", "vppb200_rcp_lut_host",
+    "vppb200_version", "vppb200_last_cuda_error", "vppb200_launch_count", "vppb200_rcp_lut_host", "vppb200_async_error",
     "vppb200_glibc_srand", "vppb200_glibc_rand_fill", "vppb200_stage_timing", "vppb200_stage_times",
     "vppb200_census5x5", "vppb200_cost_census5x5_xyd", "vppb200_aggregate", "vppb200_match_wta",
     "vppb200_match_wta_right", "vppb200_subpixel_refine", "vppb200_median3x3",
@@ -71,6 +71,13 @@ def set_tuning(key, value):
 def get_tuning(key, default=0):
     """The value last set through set_tuning in this process (`default` = the library's initial value)."""
     return _tuning.get(int(key), default)
+
+
+def check_async(device=None):
+    """Raise if a cooperative sweep on `device` reported a timed-out hand-off since the last check (synchronises the device)."""
+    torch = torch_mod()
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        check(lib().vppb200_async_error(), "async_error")
 
 
 def launch_count():

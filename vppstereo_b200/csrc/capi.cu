@@ -275,6 +275,19 @@ extern "C" int vppb200_stage_times(float *ms_out, int *calls_out)
     return VPPB200_OK;
 }
 
+extern "C" int vppb200_async_error(void)
+{
+    int hit = 0;
+    int rc = sweep_take_abort_flag(&hit);
+    if (rc) return rc;
+    if (hit) {
+        snprintf(g_err, sizeof g_err, "sgm_v2_kernel: a hand-off wait between the CTAs of a team timed out (results of the affected "
+                                      "calls are undefined); were all CTAs of the cooperative grid resident?");
+        return VPPB200_ERR_CUDA;
+    }
+    return VPPB200_OK;
+}
+
 extern "C" int vppb200_set_tuning(int key, int value)
 {
     switch (key) {

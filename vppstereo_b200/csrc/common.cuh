@@ -69,6 +69,7 @@ bool sweep_fuses_cost(int W, int H, int D, int n, bool byte_sums);   // the forw
 void sweep_set_fuse_cost(int on);
 void sweep_set_byte_sums(int on);
 void sweep_set_v_red(int on);
+int sweep_take_abort_flag(int *out);
 int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, int n, cudaStream_t st);
 void sweep_set_max_strip(int cols);
 void sweep_set_enabled(int on);

@@ -714,6 +714,11 @@ __global__ void __launch_bounds__(256) sgm_p2_kernel(const uint8_t *__restrict__
     p2q[t] = out;
 }
 
+// Raised by a hand-off wait that timed out (a CTA of the team not resident / not progressing: the protocol needs all CTAs of the
+// cooperative grid on the device at once).  The grid then runs to completion with undefined results instead of trapping the
+// context; the host reads the flag with vppb200_async_error().
+__device__ unsigned int g_sweep_abort = 0;
+
 // bounded wait on a tagged halo word; on a timeout the abort flag is raised and every later wait returns at once
 __device__ __noinline__ uint32_t halo_wait2(const uint32_t *p, uint32_t tag, uint32_t *abort_flag)
 {
@@ -1196,7 +1201,8 @@ static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, void *ha
                  const VPlan &p, bool s8, bool norm, cudaStream_t st)
 {
     uint32_t *halo = static_cast<uint32_t *>(halo_ws);
-    uint32_t *abort_flag = reinterpret_cast<uint32_t *>(static_cast<char *>(halo_ws) + HALO_LINES_BYTES);
+    uint32_t *abort_flag = nullptr;
+    VPP_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void **>(&abort_flag), g_sweep_abort));
     uint32_t *p2q = reinterpret_cast<uint32_t *>(static_cast<char *>(halo_ws) + HALO_LINES_BYTES + 256);
     const int G32 = t.G * 32;
     const long total = (long)n * t.H * G32;
@@ -1209,6 +1215,16 @@ static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, void *ha
         case 4: return run_v_t<4>(p2q, cost, S, halo, abort_flag, t, pass, n, p, s8, norm, st);
         default: return run_v_t<5>(p2q, cost, S, halo, abort_flag, t, pass, n, p, s8, norm, st);
     }
+}
+
+// 0 = no hand-off wait has timed out since the last call on the current device; 1 = one has (flag cleared).  Blocking.
+int sweep_take_abort_flag(int *out)
+{
+    unsigned int v = 0, zero = 0;
+    VPP_CUDA_TRY(cudaMemcpyFromSymbol(&v, g_sweep_abort, sizeof v));
+    if (v) VPP_CUDA_TRY(cudaMemcpyToSymbol(g_sweep_abort, &zero, sizeof zero));
+    *out = v != 0;
+    return VPPB200_OK;
 }
 
 // does the sweep cover this shape on the current device?  (a team of resident CTAs must hold a frame's path state)

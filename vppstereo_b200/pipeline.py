@@ -77,13 +77,23 @@ class VppRsgmPipeline:
         try:
             for s in (self.vpp_stream, self.main_stream, self.tail_stream):
                 s.synchronize()
+            _lib.check_async(self.device)
             if self._stream_sets is not None:
                 self._stream_sets["h2d"].synchronize(); self._stream_sets["d2h"].synchronize()
+        except RuntimeError:
+            raise
         except Exception:
             pass
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self):
+        """Wait for the device and raise if a sweep reported a timed-out hand-off between its CTAs (vppb200_async_error)."""
+        _lib.check_async(self.device)
 
     def workspace_bytes(self):
         return self.ws_rsgm.numel() + self.ws_vpp.numel()
