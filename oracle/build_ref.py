@@ -13,7 +13,7 @@ copied into the repo. Outputs (oracle/_ref/):
                             no FMA contraction, matching the reference's own default distutils build)
   rsgm_ref.pycode, vpp_standalone_ref.pycode, filter_ref.pycode
                          <- byte-compiled models/rsgm/rsgm.py, vpp_standalone.py, filter.py (glue + numba kernels)
-  refmodels/{raft_stereo,psmnet}/*.pyc, losses_ref.pycode
+  refmodels/{raft_stereo,psmnet}/*.pycode, losses_ref.pycode
                          <- byte-compiled models/raft_stereo, models/psmnet (the CONSUMERS of the projected images, BASELINE
                             configs[3]: random-initialised in the tests / bench, never rebuilt here) and losses.py (sample_hints)
 Run every process that calls pyrSGM with MALLOC_MMAP_THRESHOLD_=65536: the reference
@@ -68,7 +68,7 @@ def build(force=False):
     d = os.path.join(OUT, "losses_ref.pycode")
     if (force or not os.path.exists(d)) and os.path.exists(os.path.join(REF, "losses.py")):
         py_compile.compile(os.path.join(REF, "losses.py"), cfile=d, doraise=True)
-    # the two networks as sourceless packages (relative imports keep working): refmodels/<pkg>/<module>.pyc
+    # the two networks as sourceless packages (relative imports keep working): refmodels/<pkg>/<module>.pycode (imported through oracle/ref.py's finder)
     pk = os.path.join(OUT, "refmodels")
     for sub in ("raft_stereo", "raft_stereo/utils", "psmnet"):
         srcdir = os.path.join(REF, "models", sub)
@@ -78,14 +78,14 @@ def build(force=False):
         if "__init__.py" not in names:
             names.append("__init__.py")
         for f in names:
-            d = os.path.join(dstdir, f + "c")
+            d = os.path.join(dstdir, f[:-3] + ".pycode")     # (.pyc files do not travel with gpurun)
             if force or not os.path.exists(d):
                 src = os.path.join(srcdir, f)
                 if not os.path.exists(src):             # a directory without __init__.py (raft_stereo/utils): empty package marker
                     with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as t:
                         src = t.name
                 py_compile.compile(src, cfile=d, doraise=True)
-    d = os.path.join(pk, "__init__.pyc")
+    d = os.path.join(pk, "__init__.pycode")
     if force or not os.path.exists(d):
         with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as t:
             pass

@@ -53,6 +53,24 @@ def load():
     return ns
 
 
+class _RefModelsFinder:
+    """meta-path finder: refmodels[.pkg[.module]] -> oracle/_ref/refmodels/.../*.pycode (sourceless, relative imports work)"""
+
+    @staticmethod
+    def find_spec(fullname, path=None, target=None):
+        if fullname != "refmodels" and not fullname.startswith("refmodels."):
+            return None
+        base = os.path.join(REF_DIR, *fullname.split("."))
+        if os.path.isdir(base):
+            init = os.path.join(base, "__init__.pycode")
+            loader = importlib.machinery.SourcelessFileLoader(fullname, init)
+            return importlib.util.spec_from_file_location(fullname, init, loader=loader, submodule_search_locations=[base])
+        if os.path.exists(base + ".pycode"):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, base + ".pycode")
+            return importlib.util.spec_from_file_location(fullname, base + ".pycode", loader=loader)
+        return None
+
+
 def load_nets():
     """(RAFTStereo, PSMNet): the reference's own network classes (models/raft_stereo/raft_stereo.py:23, models/psmnet/psmnet.py:86)
     from the byte-compiled packages under oracle/_ref/refmodels.  They are the consumers of the projected images (BASELINE
@@ -60,8 +78,8 @@ def load_nets():
     models/raft_stereo/update.py:4) is absent from this image: a stand-in module is registered."""
     if not os.path.isdir(os.path.join(REF_DIR, "refmodels")):
         raise RuntimeError("oracle/_ref/refmodels not built: run `python oracle/build_ref.py` where /root/reference exists")
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
+    if not any(f is _RefModelsFinder for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefModelsFinder)
     if "opt_einsum" not in sys.modules:
         try:
             import opt_einsum  # noqa: F401
