@@ -340,6 +340,12 @@ def main():
     args = ap.parse_args()
     if args.cpu_worker:
         return cpu_worker_main(args.cpu_worker)
+    if args.impl == "reference" and args.workload == "nets":
+        import bench_nets
+        return bench_nets.main(args, reference=True)
+    if args.impl == "reference" and args.workload == "M":
+        import bench_m
+        return bench_m.main(args, reference=True)
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.workload == "M":

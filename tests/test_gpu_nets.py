@@ -40,7 +40,7 @@ def _reference_feed(img_u8_hwc, ht, wt):
     return F.pad(t, _pad, mode="replicate"), _pad
 
 
-@pytest.mark.parametrize("shape", [(96, 200), (375, 1242)])
+@pytest.mark.parametrize("shape", [(256, 330), (375, 1242)])      # (PSMNet's 64x64 pooling branch needs >= 256 rows)
 def test_nets_device_handoff_vs_reference_flow(nets, orc, shape):
     import torch
     from vppstereo_b200 import synth, vpp_standalone, vpp_core_opt
@@ -64,12 +64,12 @@ def test_nets_device_handoff_vs_reference_flow(nets, orc, shape):
     for a, b, what in ((dev2, ref2, "im2_vpp"), (dev3, ref3, "im3_vpp"), (dev0, ref0, "im2")):
         assert_same(a.cpu().numpy(), b.cpu().numpy(), f"network input {what}")
     with torch.no_grad():
-        iters = 8 if H > 200 else 12
+        iters = 8 if H > 300 else 12
         _, d_dev = raft(dev0, dev2, dev3, test_mode=True, iters=iters)
         _, d_ref = raft(ref0, ref2, ref3, test_mode=True, iters=iters)
         assert torch.isfinite(d_dev).all()
         assert torch.allclose(d_dev, d_ref, rtol=1e-4, atol=1e-3), float((d_dev - d_ref).abs().max())
-        if H <= 200:                                  # PSMNet's 3-D cost volume at K size is a bench matter, not a parity one
+        if H <= 300:                                  # PSMNet's 3-D cost volume at K size is a bench matter, not a parity one
             o_dev = psm(im2=dev2, im3=dev3)[0]
             o_ref = psm(im2=ref2, im3=ref3)[0]
             assert torch.isfinite(o_dev).all()
