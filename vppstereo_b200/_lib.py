@@ -146,27 +146,50 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
+    """the current stream of `device` (default: of the current device) as the void* the C-ABI takes"""
     torch = torch_mod()
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def device_of(*tensors):
+    """the CUDA device of the first tensor operand: front-ends launch on ITS current stream, with it as the current device
+    (the library's per-device state -- reciprocal table, side streams, sweep plan -- follows the current device)"""
+    for t in tensors:
+        if t is not None and is_tensor(t) and t.is_cuda:
+            return t.device
+    torch = torch_mod()
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 _ws_cache = {}
 
 
 def workspace(nbytes, device, tag="ws"):
-    """Cached byte buffer on `device` (grown on demand, never shrunk); the C-ABI never allocates on the data path."""
+    """Cached scratch buffer for the drop-in front-ends (grown on demand, never shrunk); the C-ABI never allocates on the data
+    path.  One buffer per (tag, device, CURRENT STREAM): the kernels of a call run on the caller's current stream, so calls made
+    under different `torch.cuda.stream(...)` contexts (or from threads with their own streams) never share scratch memory, and
+    calls on one stream are ordered by the stream.  A buffer that is replaced by a larger one is handed back to the allocator
+    with `record_stream`, i.e. only reused once the work queued on that stream has finished."""
     torch = torch_mod()
-    key = (tag, torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device())
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(index)
+    key = (tag, index, int(stream.cuda_stream))
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = None
+        if buf is not None:
+            buf.record_stream(stream)
         _ws_cache.pop(key, None)
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        with torch.cuda.device(index), torch.cuda.stream(stream):
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", index))
         _ws_cache[key] = buf
     return buf
 
 
 def free_workspaces():
+    """Drop every cached scratch buffer (synchronises first: kernels on private streams may still be using them)."""
+    if _ws_cache:
+        torch_mod().cuda.synchronize()
     _ws_cache.clear()
 
 

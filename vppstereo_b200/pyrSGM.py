@@ -16,6 +16,25 @@ __all__ = ["census5x5_SSE", "median3x3_SSE", "costMeasureCensus5x5_xyd_SSE", "ma
            "aggregate_SSE", "subPixelRefine"]
 
 
+def _on_operand_device(fn):
+    """Run an operator with the device of its first CUDA-tensor operand as the current device (numpy operands: the current
+    device): outputs and staging buffers are allocated there, the launch goes to THAT device's current stream, and the library's
+    per-device state (reciprocal table, side streams) is the right one -- also when the caller's current device is another GPU."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = next((a.device for a in args if _lib.is_tensor(a) and a.is_cuda), None)
+        if dev is None:
+            return fn(*args, **kwargs)
+        others = [a.device for a in args if _lib.is_tensor(a) and a.is_cuda and a.device != dev]
+        if others:
+            raise ValueError(f"operands live on different devices ({dev} and {others[0]})")
+        with _lib.torch_mod().cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _frames(numel, per_frame):
     n = numel // per_frame
     if n < 1 or n * per_frame != numel:
@@ -49,6 +68,7 @@ def _out_operand(dst, np_dtype, copy_in):
     return torch.empty(dst.size, dtype=dt, device="cuda")
 
 
+@_on_operand_device
 def census5x5_SSE(src, dst, width, height):
     """census5x5_SSE(src u8[H,W], dst u32[H,W], W, H)  RSGM/pyrSGM.cpp:14-95 -> FastFilters.cpp:181-442"""
     width, height = int(width), int(height)
@@ -61,6 +81,7 @@ def census5x5_SSE(src, dst, width, height):
     _writeback(dst, d, np.uint32)
 
 
+@_on_operand_device
 def median3x3_SSE(src, dst, width, height):
     """median3x3_SSE(src f32, dst f32, W, H)  RSGM/pyrSGM.cpp:97-178 -> FastFilters.cpp:701-757"""
     width, height = int(width), int(height)
@@ -73,6 +94,7 @@ def median3x3_SSE(src, dst, width, height):
     _writeback(dst, d, np.float32)
 
 
+@_on_operand_device
 def costMeasureCensus5x5_xyd_SSE(leftCensus, rightCensus, dsi, width, height, dispCount, numThreads):
     """costMeasureCensus5x5_xyd_SSE(cl, cr, dsi u16[H,W,D], W, H, D, nthreads)  RSGM/pyrSGM.cpp:180-294"""
     width, height, dispCount, numThreads = int(width), int(height), int(dispCount), int(numThreads)
@@ -91,6 +113,7 @@ def costMeasureCensus5x5_xyd_SSE(leftCensus, rightCensus, dsi, width, height, di
     _writeback(dsi, d, np.uint16)
 
 
+@_on_operand_device
 def aggregate_SSE(img, dsi, dsiAgg, width, height, dispCount, P1, P2min, Alpha, Gamma, honor_params=False):
     """aggregate_SSE(img u8, dsi, dsiAgg, W, H, D, P1, P2min, Alpha, Gamma)  RSGM/pyrSGM.cpp:504-637.
     As upstream, P1/P2min/Alpha/Gamma are parsed and then ignored (effective 7/17/0.25/50, pyrSGM.cpp:519 vs :557-560)
@@ -138,16 +161,19 @@ def _wta(sym, name, dsiAgg, dispImg, width, height, dispCount, uniqueness):
     _writeback(dispImg, d, np.float32)
 
 
+@_on_operand_device
 def matchWTA_SSE(dsiAgg, dispImg, width, height, dispCount, uniqueness):
     """matchWTA_SSE(dsiAgg u16, disp f32[H,W], W, H, D, uniqueness)  RSGM/pyrSGM.cpp:296-397"""
     _wta("vppb200_match_wta", "matchWTA_SSE", dsiAgg, dispImg, width, height, dispCount, uniqueness)
 
 
+@_on_operand_device
 def matchWTARight_SSE(dsiAgg, dispImg, width, height, dispCount, uniqueness):
     """matchWTARight_SSE(dsiAgg u16, disp f32[H,W], W, H, D, uniqueness)  RSGM/pyrSGM.cpp:399-502"""
     _wta("vppb200_match_wta_right", "matchWTARight_SSE", dsiAgg, dispImg, width, height, dispCount, uniqueness)
 
 
+@_on_operand_device
 def subPixelRefine(dsi, dispImg, width, height, dispCount, method, rcp_lut=None):
     """subPixelRefine(dsi u16, disp f32 (read and written), W, H, D, method)  RSGM/pyrSGM.cpp:639-741.
     rcp_lut (extra, optional): 65536-entry RCPSS table recorded on another CPU (golden vectors); default = this host's."""
