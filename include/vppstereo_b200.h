@@ -93,10 +93,10 @@ int vppb200_stage_times(float *ms_out, int *calls_out);
 #define VPPB200_TUNE_VPP_ROWS 3       /* 0 = VPP rnd by the ordered per-row replay only, 1 = per-pixel replay where possible (default) */
 #define VPPB200_TUNE_SGM_CLUSTERS 2   /* upper bound on frames in flight in the v-sweep (0 = all SMs); experiments only */
 #define VPPB200_TUNE_VPP_MD_WAVE 5    /* 0 = VPP maxDistance by the serial one-warp-per-(frame, channel) kernel, 1 = row wavefront (default) */
-#define VPPB200_TUNE_SGM_FUSE_COST 6  /* 1 = the forward h-sweep produces the Hamming cost volume from the census images (W % 32 == 0, unguided; measured: not faster), 0 = stand-alone cost kernel (default) */
+#define VPPB200_TUNE_SGM_FUSE_COST 6  /* round-1 option (forward h-sweep producing the cost volume), measured slower and removed: accepted, no effect */
 #define VPPB200_TUNE_RCP_HOST 7       /* 0 = sub-pixel reciprocal from the fixed Intel RCPSS table (default), 1 = from the host CPU's RCPSS instruction */
 #define VPPB200_TUNE_SGM_V_RED 8      /* 1 = the v-sweeps add into S with red.global.add (no load of S; default), 0 = load + add + store */
-#define VPPB200_TUNE_SGM_BYTE_SUMS 4  /* 0 = sweeps read-modify-write one uint16 S (default), 1 = uint8 partial-sum volumes where exact */
+#define VPPB200_TUNE_SGM_BYTE_SUMS 4  /* round-1 option (uint8 partial-sum volumes), measured slower and removed: accepted, no effect */
 int vppb200_set_tuning(int key, int value);
 
 /* ---- pyrSGM operators ----------------------------------------------------------------------------------- */

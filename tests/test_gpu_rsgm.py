@@ -179,8 +179,7 @@ def tuning(mods):
     yield lambda key, value: _lib.set_tuning(key, value)
     _lib.set_tuning(_lib.TUNE_SGM_MAX_STRIP, 0)
     _lib.set_tuning(_lib.TUNE_SGM_SWEEP, 1)
-    _lib.set_tuning(_lib.TUNE_SGM_BYTE_SUMS, 0)
-    _lib.set_tuning(_lib.TUNE_SGM_FUSE_COST, 0)
+    _lib.set_tuning(_lib.TUNE_SGM_V_RED, 1)
 
 
 @pytest.mark.parametrize("strip", [32, 64, 100])
@@ -197,41 +196,18 @@ def test_sweep_cluster_strips(mods, orc, tuning, strip, shape, D, channels):
     for f, p in enumerate(frames):
         want = orc.compute_rsgm(p["left"], p["left"], p["right"], dmax=D)
         assert_same(st["out"][f], want, f"sweep strip={strip} {shape} D={D} frame {f}")
-    # the production path (last sweep fused with WTA): uint8 partial-sum volumes, then one read-modify-written uint16 S
+    # the production path (last sweep fused with WTA, the final S never written), with both forms of the S update
     fused16 = rsgm.compute_rsgm(left, left, right, dmax=D)
-    assert_same(fused16, st["out"], f"fused sweep with uint16 S, strip={strip}")
-    tuning(_lib.TUNE_SGM_BYTE_SUMS, 1)
-    fused8 = rsgm.compute_rsgm(left, left, right, dmax=D)
-    assert_same(fused8, st["out"], f"fused sweep with byte partial sums, strip={strip}")
-    tuning(_lib.TUNE_SGM_BYTE_SUMS, 0)
+    assert_same(fused16, st["out"], f"fused sweep, strip={strip}")
+    tuning(_lib.TUNE_SGM_V_RED, 0)
+    fused_ls = rsgm.compute_rsgm(left, left, right, dmax=D)
+    assert_same(fused_ls, st["out"], f"fused sweep with load + add + store instead of red.add, strip={strip}")
+    tuning(_lib.TUNE_SGM_V_RED, 1)
     # the aggregated volume itself, against the stand-alone operator (generic per-path kernel) on the same inputs
     tuning(_lib.TUNE_SGM_SWEEP, 0)
     st0 = rsgm.compute_rsgm_stages(left, left, right, dmax=D)
     assert_same(st["dsi_agg"], st0["dsi_agg"], f"aggregated volume, sweep strip={strip} vs per-path kernels")
     assert_same(st["out"], st0["out"], "sweep vs per-path kernels, final disparity")
-
-
-@pytest.mark.parametrize("shape,D,channels", [((40, 128), 64, 3), ((37, 250), 192, 1), ((30, 96), 8, 3), ((33, 156), 72, 3)])
-def test_cost_volume_from_the_forward_sweep(mods, orc, tuning, shape, D, channels):
-    """Unguided frames whose padded width is a multiple of 32: the forward h-sweep can produce the Hamming volume itself from the
-    census images (VPPB200_TUNE_SGM_FUSE_COST, an option: measured not faster).  Same disparities and same aggregated volume as with the stand-alone cost kernel, and as the oracle;
-    narrow strips and a 3-frame batch included."""
-    rsgm, synth, _lib = mods[1], mods[2], mods[3]
-    frames = [synth.make_pair(shape[0] + D + f, shape=shape, hints="random", channels=channels) for f in range(3)]
-    left = np.stack([p["left"] for p in frames]); right = np.stack([p["right"] for p in frames])
-    want = [orc.compute_rsgm(p["left"], p["left"], p["right"], dmax=D) for p in frames]
-    for strip in (0, 32):
-        tuning(_lib.TUNE_SGM_MAX_STRIP, strip)
-        res = {}
-        for fuse in (1, 0):
-            tuning(_lib.TUNE_SGM_FUSE_COST, fuse)
-            res[fuse] = (rsgm.compute_rsgm(left, left, right, dmax=D), rsgm.compute_rsgm_stages(left, left, right, dmax=D))
-        for f in range(3):
-            assert_same(res[1][0][f], want[f], f"forward sweep produces the costs, strip={strip}, frame {f}")
-        assert_same(res[1][0], res[0][0], "fused vs stand-alone cost kernel, disparities")
-        assert_same(res[1][1]["dsi_agg"], res[0][1]["dsi_agg"], "fused vs stand-alone cost kernel, aggregated volume")
-        assert_same(res[1][1]["out"], res[0][1]["out"], "stage path")
-    tuning(_lib.TUNE_SGM_FUSE_COST, 0)
 
 
 def test_compute_rsgm_random_shapes(mods, orc):

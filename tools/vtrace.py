@@ -20,21 +20,21 @@ pipe = VppRsgmPipeline(bench.H, bench.W, 3, batch=B, dmax=192)
 for _ in range(2):
     pipe.run_device_serial(*t)
 torch.cuda.synchronize()
-ROWS, ST = 24, 8
+ROWS, ST = 24, 12
 buf = np.zeros(32 * ROWS * ST, np.uint64)
 assert _lib.lib().vppb200_debug_vtrace(buf.ctypes.data_as(C.c_void_p), buf.size) == 0
 tr = buf.reshape(32, ROWS, ST).astype(np.int64)
 nw = int((tr[:, 0, 0] > 0).sum())
 t0 = tr[:nw, 0, 0].min()
 tr = tr[:nw] - t0
-names = ["start", "waited", "deposit", "loop", "loopend", "pushed", "arrived", "prefetch"]
+names = ["start", "waited", "deposit", "loop", "blk1", "blk2", "blk3", "blk4", "pushed", "arrived", "prefetch"]
 print("row period (cycles):", np.diff(tr[:, :, 0], axis=1).mean(axis=1).round().astype(int).tolist())
-print("per-warp mean durations (cycles):  wait | deposit | setup | loop | push | arrive | prefetch | total busy")
+print("per-warp mean durations (cycles):  wait | deposit | setup | blk1 | blk2 | blk3 | blk4 | push | arrive | prefetch")
 for w in range(nw):
-    d = np.diff(tr[w, :, :], axis=1).mean(axis=0)
+    d = np.diff(tr[w, :, :11], axis=1).mean(axis=0)
     print(f"warp {w:2d} (smsp {w%4}): " + " ".join(f"{x:7.0f}" for x in d) + f"  | row {np.diff(tr[w,:,0]).mean():7.0f}")
 print("row 5 timeline (start, waited, loop, loopend, arrived) per warp:")
 for w in range(nw):
     r = tr[w, 5]
-    print(f"warp {w:2d}: " + " ".join(f"{r[k]-tr[:,5,0].min():7d}" for k in (0, 1, 3, 4, 6)))
+    print(f"warp {w:2d}: " + " ".join(f"{r[k]-tr[:,5,0].min():7d}" for k in (0, 1, 3, 7, 9)))
 np.save(os.path.join("gpurun_out", "vtrace.npy"), tr)

@@ -175,7 +175,7 @@ static size_t rsgm_ws_layout(const RsgmDims &d, int n, int sets, int set, void *
         uint32_t *cl = (uint32_t *)take(np * 4), *cr = (uint32_t *)take(np * 4);
         if (k == set) { w.guide = guide; w.dsi = dsi; w.dl = dl; w.dr = dr; w.census_l = cl; w.census_r = cr; }
     }
-    w.S = (uint16_t *)take(vol * 3);                          // one uint16 S, or three uint8 partial-sum volumes
+    w.S = (uint16_t *)take(vol * 2);                          // the uint16 S (layout T)
     w.S_xyd = (uint16_t *)take(np * d.D * 2);                 // the reference's xyd order (WTA input, test tap)
     w.halo = (void *)take(sweep_halo_bytes(d.Wp, d.Hp, d.D, n));
     w.dlf = (float *)take(np * 4); w.drf = (float *)take(np * 4);
@@ -296,8 +296,8 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_SGM_CLUSTERS: sweep_set_clusters(value); return VPPB200_OK;
         case VPPB200_TUNE_VPP_ROWS: vpp_set_rows_kernel(value); return VPPB200_OK;
         case VPPB200_TUNE_VPP_MD_WAVE: vpp_set_md_wave(value); return VPPB200_OK;
-        case VPPB200_TUNE_SGM_BYTE_SUMS: sweep_set_byte_sums(value); return VPPB200_OK;
-        case VPPB200_TUNE_SGM_FUSE_COST: sweep_set_fuse_cost(value); return VPPB200_OK;
+        case VPPB200_TUNE_SGM_BYTE_SUMS: return VPPB200_OK;      // options of round 1, removed (measured slower): accepted, no effect
+        case VPPB200_TUNE_SGM_FUSE_COST: return VPPB200_OK;
         case VPPB200_TUNE_SGM_V_RED: sweep_set_v_red(value); return VPPB200_OK;
         case VPPB200_TUNE_RCP_HOST: g_rcp_host.store(value != 0); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
@@ -424,8 +424,6 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
     if (phases == 7) tm.begin(st);                           // per-stage timing covers whole-pipeline calls only
     const bool tiled = aggregate_tile_supported(d.Wp, d.Hp, D, n);
     const bool want_volume = taps && taps->dsi_agg;          // only the test tap needs the aggregated volume itself
-    // unguided frames: the Hamming volume is produced by the forward sweep itself (no stand-alone cost kernel)
-    const bool fuse_cost = tiled && !hints && sweep_fuses_cost(d.Wp, d.Hp, D, n, !want_volume);
     const uint16_t *S_final = w.S;
     if (front) {
         // rsgm.py:258-262  pad (BORDER_REFLECT) + RGB2GRAY; the P2 guide is the raw byte stream of the padded `left`
@@ -442,7 +440,7 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
         tm.done(VPPB200_STAGE_CENSUS);
         // rsgm.py:263-268  Hamming volume (+ optional guided modulation)
         if (tiled) {
-            if (!fuse_cost && (rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
+            if ((rc = launch_cost_tile(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
             if (hints && (rc = launch_guided_tile(w.dsi, hints, validhints, d, n, st))) return rc;
         } else {
             if ((rc = launch_cost_u8(w.census_l, w.census_r, w.dsi, d.Wp, d.Hp, D, n, st))) return rc;
@@ -457,12 +455,10 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
             const StageHook hook = {StageMarks::hook, &tm};
             if (!want_volume) {
                 // the last sweep consumes the final S on the fly: WTA left (+ sub-pixel) and right come out of the aggregation
-                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, hints == nullptr, &hook, st,
-                                                fuse_cost ? w.census_l : nullptr, fuse_cost ? w.census_r : nullptr)))
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, w.dl, w.dr, rcp_lut, hints == nullptr, &hook, st)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
             } else {
-                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, hints == nullptr, &hook, st,
-                                                fuse_cost ? w.census_l : nullptr, fuse_cost ? w.census_r : nullptr)))
+                if ((rc = launch_aggregate_tile(w.guide, w.dsi, w.S, w.halo, d.Wp, d.Hp, D, n, nullptr, nullptr, nullptr, hints == nullptr, &hook, st)))
                     return rc < 0 ? rc : VPPB200_ERR_ARG;
                 if ((rc = launch_s_tile_to_xyd(w.S, w.S_xyd, d.Wp, d.Hp, D, n, st))) return rc;
                 S_final = w.S_xyd;

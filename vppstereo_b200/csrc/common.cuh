@@ -60,14 +60,9 @@ int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int 
 int launch_guided_tile(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st);
 struct StageHook { void (*fn)(void *, int); void *ctx; };   // called with VPPB200_STAGE_* when that stage has been queued
 size_t sweep_halo_bytes(int W, int H, int D, int n);       // workspace of the v-sweep: inter-CTA halo lines, abort flag, P2 table
-// plain_costs: the costs are plain Hamming distances (<= 24, no guided modulation): un-normalised path state, and (option) each
-// sweep's partial sum fits a byte; S must hold 3 bytes per element
+// plain_costs: the costs are plain Hamming distances (<= 24, no guided modulation): un-normalised path state in the v-sweeps
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost, uint16_t *S, void *halo_ws, int W, int H, int D, int n, float *dl,
-                          float *dr, const float *lut, bool plain_costs, const StageHook *hook, cudaStream_t st,
-                          const uint32_t *cen_l = nullptr, const uint32_t *cen_r = nullptr);
-bool sweep_fuses_cost(int W, int H, int D, int n, bool byte_sums);   // the forward sweep can produce the cost volume itself
-void sweep_set_fuse_cost(int on);
-void sweep_set_byte_sums(int on);
+                          float *dr, const float *lut, bool plain_costs, const StageHook *hook, cudaStream_t st);
 void sweep_set_v_red(int on);
 int sweep_take_abort_flag(int *out);
 int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, int n, cudaStream_t st);

@@ -23,8 +23,10 @@
 // Alpha=0.25, Gamma=50 => P2 in [17,50]), so no uint16 saturation is reachable (L <= 255+50, S <= 8*305); packed
 // u16x2 DPX min/add (VIMNMX3 / VIADDMNMX).
 //
-// Internal "tile" layout T of the cost volume and of S (K2 = D/2 disparity pairs, G = ceil(W/32) column groups):
-//   word (y, x, k) = (((y*G + x/32)*K2 + k)*32 + x%32), low half = disparity 2k, high half = 2k+1;
+// Internal "tile" layout T of the cost volume and of S (K2 = D/2 words per pixel, G = ceil(W/32) column groups):
+//   word (y, x, k) = (((y*G + x/32)*K2 + k)*32 + x%32), low half = disparity k, high half = disparity k + K2 ("split-half"
+//   packing: the d-1 / d+1 neighbours of BOTH halves of word k are the halves of words k-1 / k+1, so the recurrences take
+//   their neighbours as whole words -- no byte permutes in the inner loops; only the seams at d = K2-1 | K2 need one);
 //   costs are uint8 (uint16 words), S is uint16 (uint32 words).  A v-sweep warp reads/writes 64 B / 128 B rows of a
 //   tile; an h-sweep warp (lane = disparity chunk) gathers 8-column chunks of a tile with cp.async into a padded
 //   shared-memory transpose.  vppb200 converts S to the reference's xyd order for WTA / the test tap.
@@ -65,10 +67,9 @@ __device__ __forceinline__ int sw_adapt_p2(int ip, int ipr)
 // ------------------------------------------------------------------------------------------------------------
 // cost volume in layout T: popc(L ^ R[x-d]) for d <= x on rows 2..H-3, 12 elsewhere (RSGM/StereoBMHelper.cpp:29-140);
 // padding columns (x >= W) hold 0.
-// One warp per tile (32 columns x K2 disparity pairs).  A thread owns 8 adjacent columns x one eighth of the pairs:
-// the 8 left codes stay in registers, the right codes are a 9-word register window that slides by two codes per pair
-// (2 loads per 16 costs), and a pair of disparities for 8 columns leaves as ONE 16-byte store (a 64-byte tile row is
-// written by 4 lanes).  POPC (16 lanes/clk/SM) is the floor of this kernel, not the 92 MB it writes per frame.
+// One warp per tile (32 columns x K2 words).  A thread owns 8 adjacent columns x one eighth of the words: the 8 left codes stay
+// in registers, the right codes are two 8-word register windows (one per half of the word) that slide by one code per word
+// (2 loads per 16 costs), and a word of 8 columns leaves as ONE 16-byte store (a 64-byte tile row is written by 4 lanes).  POPC (16 lanes/clk/SM) is the floor of this kernel, not the 92 MB it writes per frame.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
@@ -76,32 +77,33 @@ __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, ui
 }
 
 template <bool CHECK>
-__device__ __forceinline__ void cost_pairs(const uint32_t (&L)[8], const uint32_t *__restrict__ rp, int x, int W, int k0, int k1,
+__device__ __forceinline__ void cost_pairs(const uint32_t (&L)[8], const uint32_t *__restrict__ rp, int x, int W, int K2, int k0, int k1,
                                            uint4 *__restrict__ out)
 {
-    // w[j] = R[x - 2k - 1 + j]: hi cost (d = 2k+1) of column x+j uses w[j], lo cost (d = 2k) uses w[j+1]
+    // word k of column x+j holds the costs of disparities k (low byte) and k + K2 (high byte):
+    // wl[j] = R[x + j - k], wh[j] = R[x + j - k - K2]; both windows slide by one code per word
     auto rload = [&](int i) -> uint32_t { return (!CHECK || (i >= 0 && i < W)) ? rp[i] : 0u; };
-    uint32_t w[9];
+    uint32_t wl[8], wh[8];
 #pragma unroll
-    for (int j = 0; j < 9; j++) w[j] = rload(x - 2 * k0 - 1 + j);
+    for (int j = 0; j < 8; j++) { wl[j] = rload(x + j - k0); wh[j] = rload(x + j - k0 - K2); }
 #pragma unroll 4
     for (int k = k0; k < k1; k++) {
         uint32_t c[16];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            uint32_t lo = (uint32_t)__popc(L[j] ^ w[j + 1]), hi = (uint32_t)__popc(L[j] ^ w[j]);
+            uint32_t lo = (uint32_t)__popc(L[j] ^ wl[j]), hi = (uint32_t)__popc(L[j] ^ wh[j]);
             if (CHECK) {
-                if (2 * k > x + j) lo = 12u;
-                if (2 * k + 1 > x + j) hi = 12u;
+                if (k > x + j) lo = 12u;
+                if (k + K2 > x + j) hi = 12u;
             }
             c[2 * j] = lo; c[2 * j + 1] = hi;
         }
         out[k * 4] = make_uint4(pack4(c[0], c[1], c[2], c[3]), pack4(c[4], c[5], c[6], c[7]), pack4(c[8], c[9], c[10], c[11]),
                                 pack4(c[12], c[13], c[14], c[15]));
 #pragma unroll
-        for (int j = 8; j >= 2; j--) w[j] = w[j - 2];
-        w[1] = rload(x - 2 * k - 2);
-        w[0] = rload(x - 2 * k - 3);
+        for (int j = 7; j >= 1; j--) { wl[j] = wl[j - 1]; wh[j] = wh[j - 1]; }
+        wl[0] = rload(x - k - 1);
+        wh[0] = rload(x - k - 1 - K2);
     }
 }
 
@@ -133,8 +135,8 @@ __global__ void __launch_bounds__(256) cost_tile_kernel(const uint32_t *__restri
         L[0] = a.x; L[1] = a.y; L[2] = a.z; L[3] = a.w; L[4] = b.x; L[5] = b.y; L[6] = b.z; L[7] = b.w;
     }
     const uint32_t *rp = cr + row * t.W;
-    if (g * 32 >= t.D + 2) cost_pairs<false>(L, rp, x, t.W, k0, k1, out);       // every d <= x and every read inside the row
-    else cost_pairs<true>(L, rp, x, t.W, k0, k1, out);
+    if (g * 32 >= t.D + 2) cost_pairs<false>(L, rp, x, t.W, t.K2, k0, k1, out);       // every d <= x and every read inside the row
+    else cost_pairs<true>(L, rp, x, t.W, t.K2, k0, k1, out);
 }
 
 int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st)
@@ -162,8 +164,8 @@ __global__ void guided_tile_kernel(uint8_t *__restrict__ cost, const float *__re
     if (!(valid[s] > 0)) return;
     const double tt = __dsub_rn((double)hints[s], (double)dd);
     const float w = (float)__dmul_rn(10.0, __dsub_rn(1.0, exp(__ddiv_rn(-__dmul_rn(tt, tt), 2.0))));
-    const long word = f * t.frame + (((long)yp * t.G + xp / 32) * t.K2 + dd / 2) * 32 + xp % 32;
-    uint8_t *p = cost + word * 2 + (dd & 1);
+    const long word = f * t.frame + (((long)yp * t.G + xp / 32) * t.K2 + dd % t.K2) * 32 + xp % 32;
+    uint8_t *p = cost + word * 2 + (dd >= t.K2 ? 1 : 0);
     *p = (uint8_t)(uint16_t)__dmul_rn((double)*p, (double)w);
 }
 int launch_guided_tile(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st)
@@ -193,7 +195,11 @@ __global__ void __launch_bounds__(128) s_tile_to_xyd_kernel(const uint32_t *__re
         const int x = g * 32 + c;
         if (x >= t.W) break;
         uint32_t *dst = Sx + (row * t.W + x) * t.K2;
-        for (int k = lane; k < t.K2; k += 32) dst[k] = sm[k * 33 + c];
+        // output word m = disparities (2m, 2m+1): the low halves of words 2m, 2m+1, or (2m >= K2) the high halves of 2m-K2, 2m+1-K2
+        for (int m = lane; m < t.K2; m += 32) {
+            const int k = 2 * m < t.K2 ? 2 * m : 2 * m - t.K2;
+            dst[m] = __byte_perm(sm[k * 33 + c], sm[(k + 1) * 33 + c], 2 * m < t.K2 ? 0x5410 : 0x7632);
+        }
     }
 }
 int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, int n, cudaStream_t st)
@@ -209,12 +215,15 @@ int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// h-sweep: path r0 of one pass, one warp per image row, lane l owns disparity pairs [NW*l, NW*(l+1))
-// (RSGM/StereoSGM_SSE.hpp:100-113,:219-236 for the recursion; the line starts with L = C at the pass's first column and
-// every pixel is summed into S).  State is kept NORMALISED (L - min_d L): L_new = C + min(L'[d], min(L'[d-1], L'[d+1])
-// + P1, P2).  Operands arrive in 8-column chunks: cp.async gathers the chunk's K2 rows of a tile into shared memory
-// with odd row strides (bank-conflict-free transposed reads), two chunks in flight per warp; results go back through
-// the same chunk buffer so that the global stores are full 32-byte sectors.
+// h-sweep: path r0 of one pass, one warp per image row, lane l owns the words [NW*l, NW*(l+1)) of a pixel, i.e. the
+// disparities NW*l + j and K2 + NW*l + j (RSGM/StereoSGM_SSE.hpp:100-113,:219-236 for the recursion; the line starts with
+// L = C at the pass's first column and every pixel is summed into S).  State is kept NORMALISED (L - min_d L): L_new = C +
+// min(L'[d], min(L'[d-1], L'[d+1]) + P1, P2).  With the split-half packing the d-1 / d+1 neighbours of BOTH halves of word k
+// are the words k-1 / k+1, so a step is two shuffles (the lanes' edge words) and, per word, VIMNMX3 + VIADDMNMX + one add;
+// only the two seams (d = -1 | K2-1 below word 0, K2 | D above word K2-1) are patched with a byte permute.  Operands arrive in
+// 8-column chunks: cp.async gathers the chunk's K2 rows of a tile into shared memory with odd row strides (bank-conflict-free
+// transposed reads), two chunks in flight per warp; results go back through the same chunk buffer so that the global stores are
+// full 32-byte sectors.
 // ------------------------------------------------------------------------------------------------------------
 static constexpr int HWARPS = 4;   // warps per CTA
 static constexpr int HCROW = 16;   // bytes of a staged cost row: 8 columns x uint16 (16-byte pieces, dense)
@@ -229,27 +238,42 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// one SGM step on normalised state: nw = c + min(w[d], min(w[d-1], w[d+1]) + P1, P2);  p2m = (P2 - P1) * 0x10001
-template <int NW>
-__device__ __forceinline__ void sw_step(const uint32_t (&w)[NW], const uint32_t (&c)[NW], uint32_t p2m, int lane,
-                                        uint32_t (&nw)[NW])
+// one SGM step on normalised state: nw = c + min(w[k], min(w[k-1], w[k+1]) + P1, P2);  p2m = (P2 - P1) * 0x10001.
+// FULLK: K2 == 32 * NW (every word of every lane is real); otherwise jl = index of this lane's last real word (-1: none),
+// `last` = this lane holds word K2-1.
+template <int NW, bool FULLK>
+__device__ __forceinline__ void sw_step(const uint32_t (&w)[NW], const uint32_t (&c)[NW], uint32_t p2m, int lane, int lane_last,
+                                        int jl, uint32_t (&nw)[NW])
 {
-    uint32_t up = __shfl_up_sync(0xFFFFFFFFu, w[NW - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
-    if (lane == 0) up = SW_BIG2;
-    if (lane == 31) dn = SW_BIG2;
     uint32_t ext[NW + 2];
-    ext[0] = up;
 #pragma unroll
     for (int k = 0; k < NW; k++) ext[k + 1] = w[k];
-    ext[NW + 1] = dn;
-    uint32_t p[NW + 1];
+    if (FULLK) {
+        // rotating shuffles: lane 0 receives word K2-1, lane 31 receives word 0 -- exactly what the two seams need
+        const uint32_t up = __shfl_sync(0xFFFFFFFFu, w[NW - 1], (lane + 31) & 31);
+        const uint32_t dn = __shfl_sync(0xFFFFFFFFu, w[0], (lane + 1) & 31);
+        ext[0] = lane == 0 ? __byte_perm(SW_BIG2, up, 0x5410) : up;          // (BIG, L[K2-1]): below d = 0 | below d = K2
+        ext[NW + 1] = lane == 31 ? __byte_perm(dn, SW_BIG2, 0x5432) : dn;    // (L[K2], BIG): above d = K2-1 | above d = D-1
+    } else {
+        uint32_t tail = w[0];
 #pragma unroll
-    for (int k = 0; k <= NW; k++) p[k] = __byte_perm(ext[k], ext[k + 1], 0x5432);   // (hi(ext[k]), lo(ext[k+1]))
+        for (int k = 1; k < NW; k++) if (k == jl) tail = w[k];
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, w[NW - 1], 1);
+        const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
+        const uint32_t wlast = __shfl_sync(0xFFFFFFFFu, tail, lane_last);     // word K2-1
+        const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, w[0], 0);                // word 0
+        ext[0] = lane == 0 ? __byte_perm(SW_BIG2, wlast, 0x5410) : up;
+        ext[NW + 1] = dn;
+        if (lane == lane_last) {
+            const uint32_t seam = __byte_perm(w0, SW_BIG2, 0x5432);
+#pragma unroll
+            for (int k = 0; k < NW; k++) if (k == jl) ext[k + 2] = seam;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < NW; k++) {
-        uint32_t t = __vimin3_u16x2(p[k], p[k + 1], p2m);       // min(L[d-1], L[d+1], P2 - P1)
-        t = __viaddmin_u16x2(t, SW_P1X2, w[k]);                 // min(. + P1, L[d])
+        uint32_t t = __vimin3_u16x2(ext[k], ext[k + 2], p2m);       // min(L[d-1], L[d+1], P2 - P1)
+        t = __viaddmin_u16x2(t, SW_P1X2, w[k]);                     // min(. + P1, L[d])
         nw[k] = t + c[k];
     }
 }
@@ -272,47 +296,33 @@ __device__ __forceinline__ uint32_t &u4c(uint4 &v, int i) { return i == 0 ? v.x 
 // MODE 0: S = L (first sweep);  MODE 1: S += L;  MODE 2: S + L is the final aggregated volume and is consumed on the
 // fly by the winner-takes-all step instead of being written (RSGM/StereoBMHelper.cpp:634-750 left, :893-1015 right,
 // :1072-1102 sub-pixel; same arithmetic as wta_rows_kernel in rsgm_ops.cu, which sweeps x = W-1 .. 0 like this pass).
-// S8 ("byte partial sums", unguided costs only: C <= 24 and P2 <= 50 bound every L by 74 and a sweep's three paths by 222):
-// the sweeps do not read-modify-write a uint16 S; each writes its own uint8 volume in the cost volume's layout (MODE 0 -> a0,
-// the v-sweeps -> a1, a2) and MODE 2 adds the three to its own path on the fly.  Same integers, 37 % less DRAM traffic.
-// FULLK: K2 == NW * 32, every lane's NW pairs are real disparities (no validity selects)
-// GEN (forward sweep only): the Hamming costs are not read but PRODUCED here from the two census rows
-// (RSGM/StereoBMHelper.cpp:29-140: popc(L[x] ^ R[x-d]) for d <= x on rows 2..H-3, 12 elsewhere) and written to the cost
-// volume for the three sweeps that follow: the stand-alone cost kernel and one read of the volume disappear, the popcounts
-// ride the forward sweep's idle issue slots.
-template <int NW, int MODE, int DIR, bool S8, bool FULLK, bool GEN>
+// FULLK: K2 == NW * 32, every lane's NW words are real disparities (no validity selects)
+template <int NW, int MODE, int DIR, bool FULLK>
 __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__restrict__ img, const uint16_t *__restrict__ cost,
                                                             uint32_t *__restrict__ S, TL t, long total_rows,
                                                             float *__restrict__ disp_l, float *__restrict__ disp_r,
-                                                            const float *__restrict__ lut, uint16_t *__restrict__ a0,
-                                                            const uint16_t *__restrict__ a1, const uint16_t *__restrict__ a2,
-                                                            const uint32_t *__restrict__ cen_l, const uint32_t *__restrict__ cen_r,
-                                                            uint16_t *__restrict__ cost_out)
+                                                            const float *__restrict__ lut)
 {
-    static_assert(!GEN || (MODE == 0 && !S8 && DIR > 0), "costs are generated by the forward uint16 sweep");
     constexpr bool STORE = MODE == 0, WTA = MODE == 2;
     static_assert(!WTA || DIR < 0, "the fused WTA rides the backward sweep");
-    static_assert(!S8 || MODE != 1, "byte partial sums: forward store or fused WTA only");
-    static_assert(!S8 || !STORE || DIR > 0, "the byte store packs even columns first");
-    constexpr int NA = (S8 && WTA) ? 3 : 0;         // staged partial-sum volumes
     extern __shared__ __align__(16) uint8_t hsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * HWARPS + warp;
     if (row >= total_rows) return;
     const int K2 = t.K2, W = t.W, D = t.D;
-    const int stage_b = S8 ? K2 * HCROW * (1 + NA) : K2 * (HCROW + HSROW);
+    const int stage_b = K2 * (HCROW + HSROW);
     uint8_t *base = hsm + (size_t)warp * 2 * stage_b;
     const uint8_t *irow = img + row * W;
     const uint16_t *crow = cost + row * (long)t.G * K2 * 32;     // tiles of this row (rows run over all frames)
     uint32_t *srow = S + row * (long)t.G * K2 * 32;
-    const long aoff = S8 ? row * (long)t.G * K2 * 32 : 0;
-    const uint16_t *arow[3] = {a0 + aoff, a1 + aoff, a2 + aoff};
     bool wv[NW];
 #pragma unroll
     for (int j = 0; j < NW; j++) wv[j] = FULLK || NW * lane + j < K2;
+    const int lane_last = (K2 - 1) / NW;            // the lane that holds word K2-1 ...
+    const int jl = FULLK ? NW - 1 : min(NW - 1, K2 - 1 - NW * lane);          // ... and every lane's last real word (< 0: none)
     const int nchunks = W / 8;                      // W % 16 == 0
     const int xs = DIR > 0 ? 0 : W - 1;
-    const int d0 = 2 * NW * lane;
+    const int d0 = NW * lane;                       // word j of this lane: disparities d0 + j (low half) and K2 + d0 + j (high half)
 
     // gather chunk q (sweep order) into stage q & 1: 16-byte pieces, one per cost row, two per S row
     auto issue = [&](int q) {
@@ -320,20 +330,13 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             const int xc = DIR > 0 ? q : nchunks - 1 - q;
             const int toff = ((xc >> 2) * K2) * 32 + (xc & 3) * 8;       // tile start + first column of the chunk
             uint8_t *sb = base + (q & 1) * stage_b;
-            if (!GEN) {
+            {
                 const uint16_t *src = crow + toff + lane * 32;
                 const uint32_t dst = smem_u32(sb) + lane * HCROW;
                 for (int r0 = 0; r0 < K2; r0 += 32)
                     if (r0 + lane < K2) cp_async16(dst + r0 * HCROW, src + r0 * 32);
             }
-#pragma unroll
-            for (int v = 0; v < NA; v++) {
-                const uint16_t *src = arow[v] + toff + lane * 32;
-                const uint32_t dst = smem_u32(sb) + (v + 1) * K2 * HCROW + lane * HCROW;
-                for (int r0 = 0; r0 < K2; r0 += 32)
-                    if (r0 + lane < K2) cp_async16(dst + r0 * HCROW, src + r0 * 32);
-            }
-            if (!S8 && !STORE) {
+            if (!STORE) {
                 const uint32_t *src = srow + toff + (lane >> 1) * 32 + (lane & 1) * 4;
                 const uint32_t dst = smem_u32(sb + K2 * HCROW) + (lane >> 1) * HSROW + (lane & 1) * 16;
                 for (int r0 = 0; r0 < K2; r0 += 16)
@@ -359,17 +362,11 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     uint32_t w[NW];
 #pragma unroll
     for (int j = 0; j < NW; j++) w[j] = 0;
-    uint32_t bucket[2 * NW];                        // WTA right: best (cost << 16 | d) of the in-flight target pixels
+    // WTA right: best (cost << 16 | d) of the in-flight target pixels, a conveyor over the disparities in this lane's order:
+    // ba[j] rides disparity d0 + j, bb[j] disparity K2 + d0 + j; every pixel the conveyor moves one disparity down
+    uint32_t ba[NW], bb[NW];
 #pragma unroll
-    for (int k = 0; k < 2 * NW; k++) bucket[k] = 0xFFFFFFFFu;
-    // GEN: this lane's window of the right census row, R[xlo - d0 - (2NW-1) + j], j = 0 .. 2NW+6 (slides by 8 per chunk)
-    constexpr int RWN = 2 * NW + 7;
-    uint32_t rw[RWN];
-#pragma unroll
-    for (int j = 0; j < RWN; j++) rw[j] = 0;
-    const uint32_t *clrow = GEN ? cen_l + row * W : nullptr, *crrow = GEN ? cen_r + row * W : nullptr;
-    const int yrow = (int)(row % t.H);
-    const bool row_ok = yrow >= 2 && yrow < t.H - 2;
+    for (int k = 0; k < NW; k++) { ba[k] = 0xFFFFFFFFu; bb[k] = 0xFFFFFFFFu; }
     int step = 0, ring = 0;
     for (int q = 0; q < nchunks; q++) {
         cp_async_wait<1>();
@@ -377,54 +374,17 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
         uint8_t *sb = base + (q & 1) * stage_b;
         uint8_t *ssb = sb + K2 * HCROW;
         const int xlo = (DIR > 0 ? q : nchunks - 1 - q) * 8;
-        // this lane's rows of the chunk: 8 pixels x NW disparity pairs, costs (uint16) and S words
+        // this lane's rows of the chunk: 8 pixels x NW words, costs (uint16) and S words
         uint4 cv[NW], s0[NW], s1[NW];
-        uint4 av[NA > 0 ? NA : 1][NW];               // S8: the three byte volumes (WTA) / the packed output (STORE, av[0])
 #pragma unroll
         for (int j = 0; j < NW; j++) {
             cv[j] = make_uint4(0, 0, 0, 0); s0[j] = cv[j]; s1[j] = cv[j];
-#pragma unroll
-            for (int v = 0; v < (NA > 0 ? NA : 1); v++) av[v][j] = cv[j];
             if (wv[j]) {
-                if (!GEN) cv[j] = *reinterpret_cast<const uint4 *>(sb + (NW * lane + j) * HCROW);
-#pragma unroll
-                for (int v = 0; v < NA; v++)
-                    av[v][j] = *reinterpret_cast<const uint4 *>(sb + (v + 1) * K2 * HCROW + (NW * lane + j) * HCROW);
-                if (!S8 && !STORE) {
+                cv[j] = *reinterpret_cast<const uint4 *>(sb + (NW * lane + j) * HCROW);
+                if (!STORE) {
                     s0[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW);
                     s1[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW + 16);
                 }
-            }
-        }
-        if (GEN) {
-            uint32_t Lc[8];
-            {
-                const uint4 la = *reinterpret_cast<const uint4 *>(clrow + xlo), lb = *reinterpret_cast<const uint4 *>(clrow + xlo + 4);
-                Lc[0] = la.x; Lc[1] = la.y; Lc[2] = la.z; Lc[3] = la.w; Lc[4] = lb.x; Lc[5] = lb.y; Lc[6] = lb.z; Lc[7] = lb.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 2 * NW - 1; j++) rw[j] = rw[j + 8];
-#pragma unroll
-            for (int j = 2 * NW - 1; j < RWN; j++) {
-                const int idx = xlo - d0 - (2 * NW - 1) + j;
-                rw[j] = idx >= 0 ? crrow[idx] : 0u;
-            }
-            const bool chk = xlo < d0 + 2 * NW;          // some (pixel, disparity) of this lane's block has d > x
-#pragma unroll
-            for (int j = 0; j < NW; j++) {
-                uint32_t comp[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int pp = 0; pp < 8; pp++) {
-                    uint32_t lo = (uint32_t)__popc(Lc[pp] ^ rw[pp - 2 * j + (2 * NW - 1)]);
-                    uint32_t hi = (uint32_t)__popc(Lc[pp] ^ rw[pp - 2 * j - 1 + (2 * NW - 1)]);
-                    if (chk) {
-                        if (d0 + 2 * j > xlo + pp) lo = 12u;
-                        if (d0 + 2 * j + 1 > xlo + pp) hi = 12u;
-                    }
-                    if (!row_ok) { lo = 12u; hi = 12u; }
-                    comp[pp >> 1] |= (lo | (hi << 8)) << (16 * (pp & 1));
-                }
-                cv[j] = make_uint4(comp[0], comp[1], comp[2], comp[3]);
             }
         }
 
@@ -449,7 +409,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
 #pragma unroll
                 for (int j = 0; j < NW; j++) nw[j] = cc[j];
             } else {
-                sw_step<NW>(w, cc, p2m, lane, nw);
+                sw_step<NW, FULLK>(w, cc, p2m, lane, lane_last, jl, nw);
             }
 #pragma unroll
             for (int j = 0; j < NW; j++) if (!wv[j]) nw[j] = SW_BIG2;
@@ -458,45 +418,37 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 w[j] = nw[j] - m2;
-                if (S8) {
-                    if (STORE) {
-                        const uint32_t packed = __byte_perm(nw[j], 0, 0x4420);                 // both values <= 74
-                        uint32_t &o = u4c(av[0][j], p >> 1);
-                        o = (p & 1) ? __byte_perm(o, packed, 0x5410) : packed;
-                        fin[j] = 0;
-                    } else {
-                        fin[j] = nw[j] + __byte_perm(u4c(av[0][j], p >> 1), 0, bsel) + __byte_perm(u4c(av[NA > 1 ? 1 : 0][j], p >> 1), 0, bsel) +
-                                 __byte_perm(u4c(av[NA > 2 ? 2 : 0][j], p >> 1), 0, bsel);
-                    }
-                } else {
-                    uint32_t &acc = p < 4 ? u4c(s0[j], p) : u4c(s1[j], p - 4);
-                    acc = STORE ? nw[j] : acc + nw[j];
-                    fin[j] = acc;
-                }
+                uint32_t &acc = p < 4 ? u4c(s0[j], p) : u4c(s1[j], p - 4);
+                acc = STORE ? nw[j] : acc + nw[j];
+                fin[j] = acc;
             }
             if (WTA) {
                 const int x = xlo + p;
-                uint32_t key[2 * NW];
+                uint32_t ka[NW], kb[NW];              // (cost << 16 | d) of the low-half and of the high-half disparities
 #pragma unroll
                 for (int j = 0; j < NW; j++) {
-                    const int d = d0 + 2 * j;
-                    key[2 * j] = wv[j] ? ((fin[j] << 16) | (uint32_t)d) : 0xFFFFFFFFu;
-                    key[2 * j + 1] = wv[j] ? ((fin[j] & 0xFFFF0000u) | (uint32_t)(d + 1)) : 0xFFFFFFFFu;
+                    // (multiply-add and one logic op: the byte-permute unit shares the integer pipe this kernel is bound by)
+                    ka[j] = wv[j] ? fin[j] * 65536u + (uint32_t)(d0 + j) : 0xFFFFFFFFu;
+                    kb[j] = wv[j] ? ((fin[j] & 0xFFFF0000u) | (uint32_t)(K2 + d0 + j)) : 0xFFFFFFFFu;
                 }
                 // left: first arg-min over d <= min(D-1, x)
                 const int end = min(D - 1, x);
                 uint32_t m = 0xFFFFFFFFu;
                 if (nomask) {
 #pragma unroll
-                    for (int k = 0; k < 2 * NW; k++) m = min(m, key[k]);
+                    for (int k = 0; k < NW; k++) m = min(m, min(ka[k], kb[k]));
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 2 * NW; k++) m = min(m, (d0 + k <= end) ? key[k] : 0xFFFFFFFFu);
+                    for (int k = 0; k < NW; k++) {
+                        m = min(m, (d0 + k <= end) ? ka[k] : 0xFFFFFFFFu);
+                        m = min(m, (K2 + d0 + k <= end) ? kb[k] : 0xFFFFFFFFu);
+                    }
                 }
                 m = __reduce_min_sync(0xFFFFFFFFu, m);
                 const int best = (int)(m & 0xFFFFu);
                 float o = (float)best;
-                // final S of this pixel -> scratch (the previous buffer of the ring still holds pixel x+1)
+                // final S of this pixel -> scratch (the previous buffer of the ring still holds pixel x+1); disparity d sits in
+                // half d / K2 of word d % K2
                 uint32_t *sc = scr + ring * K2;
                 const uint32_t *sc_prev = scr + (ring == 0 ? 2 : ring - 1) * K2;
                 ring = ring == 2 ? 0 : ring + 1;
@@ -506,9 +458,10 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                 if (x >= 1 && x <= W - 2) {
                     if (best > 0) {
                         const uint16_t *s16 = reinterpret_cast<const uint16_t *>(sc);
-                        const int c0 = s16[best - 1], c1 = (int)(m >> 16);
+                        auto at = [&](int d) -> int { return d < K2 ? s16[2 * d] : s16[2 * (d - K2) + 1]; };
+                        const int c0 = at(best - 1), c1 = (int)(m >> 16);
                         // best = D-1 reads the next pixel's d = 0 (xyd stream order)
-                        const int c2 = best + 1 < D ? s16[best + 1] : reinterpret_cast<const uint16_t *>(sc_prev)[0];
+                        const int c2 = best + 1 < D ? at(best + 1) : reinterpret_cast<const uint16_t *>(sc_prev)[0];
                         const int lower = min(c1 - c0, c1 - c2);            // <= 0
                         o = __fadd_rn((float)best, __fmul_rn((float)(c2 - c0), lut[-lower]));
                     } else {
@@ -516,16 +469,33 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                     }
                 }
                 if (lane == 0) wout[p] = o;
-                // right: every in-flight target absorbs its disparity slot, slot 0 retires to disp_r[x]
+                // right: every in-flight target absorbs its disparity slot, slot d = 0 retires to disp_r[x], the conveyor moves
+                // one disparity down: within the halves by register moves, between lanes by a rotating shuffle (lane 31
+                // receives lane 0's slots: its low-half tail takes d = K2 from there, its high-half tail starts empty)
 #pragma unroll
-                for (int k = 0; k < 2 * NW; k++) bucket[k] = min(bucket[k], key[k]);
-                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bucket[0], 0);
+                for (int k = 0; k < NW; k++) { ba[k] = min(ba[k], ka[k]); bb[k] = min(bb[k], kb[k]); }
+                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, ba[0], 0);
                 if (lane == 0) wout[8 + p] = (float)(b0 & 0xFFFFu);
-                uint32_t from_up = __shfl_down_sync(0xFFFFFFFFu, bucket[0], 1);
-                if (lane == 31) from_up = 0xFFFFFFFFu;
+                const uint32_t fa = __shfl_sync(0xFFFFFFFFu, ba[0], (lane + 1) & 31);
+                const uint32_t fb = __shfl_sync(0xFFFFFFFFu, bb[0], (lane + 1) & 31);
 #pragma unroll
-                for (int k = 0; k < 2 * NW - 1; k++) bucket[k] = bucket[k + 1];
-                bucket[2 * NW - 1] = from_up;
+                for (int k = 0; k < NW - 1; k++) { ba[k] = ba[k + 1]; bb[k] = bb[k + 1]; }
+                if (FULLK) {
+                    ba[NW - 1] = lane == 31 ? fb : fa;
+                    bb[NW - 1] = lane == 31 ? 0xFFFFFFFFu : fb;
+                } else {
+                    // the lane that holds word K2-1: its low-half tail (disparity K2-1) takes over disparity K2 = lane 0's first
+                    // high-half slot; slots past K2-1 stay empty
+                    const uint32_t fb0 = __shfl_sync(0xFFFFFFFFu, fb, 31);          // = lane 0's bb[0] before the move
+                    ba[NW - 1] = fa; bb[NW - 1] = fb;
+                    if (lane >= lane_last) {
+#pragma unroll
+                        for (int k = 0; k < NW; k++) {
+                            if (lane > lane_last || k > jl) { ba[k] = 0xFFFFFFFFu; bb[k] = 0xFFFFFFFFu; }
+                            else if (k == jl) { ba[k] = fb0; bb[k] = 0xFFFFFFFFu; }
+                        }
+                    }
+                }
             }
         }
         if (WTA) {
@@ -534,20 +504,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                 disp_l[row * W + xlo + lane] = wout[lane];
                 disp_r[row * W + xlo + lane] = wout[8 + lane];
             }
-        } else if (S8) {
-            // the chunk's byte rows leave from registers: one 16-byte piece (8 columns x 2 disparities) per tile row
-            uint16_t *dst = a0 + aoff + ((xlo >> 5) * K2) * 32 + (xlo & 31);
-#pragma unroll
-            for (int j = 0; j < NW; j++)
-                if (wv[j]) *reinterpret_cast<uint4 *>(dst + (NW * lane + j) * 32) = av[0][j];
         } else {
-            if (GEN) {
-                // the generated cost rows of the chunk: one 16-byte piece (8 columns x 2 disparities) per tile row
-                uint16_t *dst = cost_out + row * (long)t.G * K2 * 32 + ((xlo >> 5) * K2) * 32 + (xlo & 31);
-#pragma unroll
-                for (int j = 0; j < NW; j++)
-                    if (wv[j]) *reinterpret_cast<uint4 *>(dst + (NW * lane + j) * 32) = cv[j];
-            }
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 if (wv[j]) {
@@ -570,40 +527,29 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     cp_async_wait<0>();
 }
 
-struct ByteVols { uint16_t *a0, *a1, *a2; };       // S8: the three byte partial-sum volumes (layout T, uint16 words)
-
-struct CostGen { const uint32_t *cl, *cr; uint16_t *out; };     // forward sweep that produces the cost volume (cl == NULL: reads it)
-
-template <int NW, int MODE, int DIR, bool S8>
+template <int NW, int MODE, int DIR>
 static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int n, float *dl, float *dr,
-                   const float *lut, const ByteVols &bv, cudaStream_t st, const CostGen &cg = CostGen{nullptr, nullptr, nullptr})
+                   const float *lut, cudaStream_t st)
 {
     const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
-    const size_t stage = S8 ? (size_t)t.K2 * HCROW * (MODE == 2 ? 4 : 1) : h_stage_bytes(t.K2);
+    const size_t stage = h_stage_bytes(t.K2);
     const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * (3 * t.K2 + 16) * 4 : 0);
-    auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, S8, true, false> : sgm_h_kernel<NW, MODE, DIR, S8, false, false>;
-    if constexpr (MODE == 0 && !S8 && DIR > 0) {
-        if (cg.cl) kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, 0, 1, false, true, true> : sgm_h_kernel<NW, 0, 1, false, false, true>;
-    }
+    auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, true> : sgm_h_kernel<NW, MODE, DIR, false>;
     if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows, dl, dr, lut, bv.a0, bv.a1, bv.a2, cg.cl, cg.cr, cg.out);
+    kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows, dl, dr, lut);
     VPP_LAUNCH_CHECK("sgm_h_kernel");
     return VPPB200_OK;
 }
 
 // mode 0: forward sweep, S = L;  mode 1: backward sweep, S += L;  mode 2: backward sweep fused with WTA (dl, dr, lut)
-// s8: byte partial sums (modes 0 and 2 only)
 static int run_h(const uint8_t *img, const uint16_t *cost, uint32_t *S, const TL &t, int mode, int n, float *dl, float *dr,
-                 const float *lut, bool s8, const ByteVols &bv, cudaStream_t st, const CostGen &cg = CostGen{nullptr, nullptr, nullptr})
+                 const float *lut, cudaStream_t st)
 {
 #define VPP_RUN_H(NW)                                                                                                  \
-    if (s8)                                                                                                            \
-        return mode == 0 ? run_h_t<NW, 0, 1, true>(img, cost, S, t, n, nullptr, nullptr, nullptr, bv, st)              \
-                         : run_h_t<NW, 2, -1, true>(img, cost, S, t, n, dl, dr, lut, bv, st);                          \
-    return mode == 0 ? run_h_t<NW, 0, 1, false>(img, cost, S, t, n, nullptr, nullptr, nullptr, bv, st, cg)             \
-         : mode == 1 ? run_h_t<NW, 1, -1, false>(img, cost, S, t, n, nullptr, nullptr, nullptr, bv, st)                \
-                     : run_h_t<NW, 2, -1, false>(img, cost, S, t, n, dl, dr, lut, bv, st)
+    return mode == 0 ? run_h_t<NW, 0, 1>(img, cost, S, t, n, nullptr, nullptr, nullptr, st)                            \
+         : mode == 1 ? run_h_t<NW, 1, -1>(img, cost, S, t, n, nullptr, nullptr, nullptr, st)                           \
+                     : run_h_t<NW, 2, -1>(img, cost, S, t, n, dl, dr, lut, st)
     switch ((t.K2 + 31) / 32) {
         case 1: VPP_RUN_H(1);
         case 2: VPP_RUN_H(2);
@@ -731,9 +677,22 @@ __device__ __noinline__ uint32_t halo_wait2(const uint32_t *p, uint32_t tag, uin
     return 0u;
 }
 
+#ifdef VPP_TRACE
+// debug build only (tools/vtrace.py): clock64 stamps of one CTA's warps over a window of rows
+static constexpr int TR_ROW0 = 100, TR_ROWS = 24, TR_STAMPS = 12, TR_CTA = 3;
+__device__ unsigned long long g_vtrace[32 * TR_ROWS * TR_STAMPS];
+#define VTRACE(k)                                                                                                      \
+    do {                                                                                                               \
+        if (blockIdx.x == TR_CTA && lane == 0 && t >= TR_ROW0 && t < TR_ROW0 + TR_ROWS)                                 \
+            g_vtrace[(warp * TR_ROWS + (t - TR_ROW0)) * TR_STAMPS + (k)] = clock64();                                  \
+    } while (0)
+#else
+#define VTRACE(k) do { } while (0)
+#endif
+
 struct VPath2 {
-    uint32_t cur;      // Lt[2k], Lt[2k+1] of the predecessor
-    uint32_t lo;       // Lt[2k-1], Lt[2k]
+    uint32_t cur;      // word k of the predecessor: Lt[k], Lt[k + K2]
+    uint32_t prev;     // word k-1 (for word 0: the seam (inf, Lt[K2-1]))
     uint32_t q;        // (min + P2 - P1) x2
     uint32_t ng;       // NORM: min of the predecessor
     uint32_t mr;       // running min of the new values
@@ -744,14 +703,16 @@ __device__ __forceinline__ void red_add_u32(uint32_t *p, uint32_t v)
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// One block of up to VU words for the three paths.  s* = predecessor state rows of the block (stride NS), w* = this row's state
+// rows (same slots), Sg = the block's S words (stride 32).  GUARD: only the first `cnt` words exist; `last`: the block ends this
+// warp's share, whose upper neighbour word was read before the column group's barrier (wr*).
 // RED: S += goes out as a fire-and-forget reduction to L2 (the addend's halves are <= 3 * 74 resp. 3 * 305 and S's halves never
 // overflow, so the 32-bit add is exact for both halves): no load of S, no operand registers, no latency to hide
-template <int NS, bool GUARD, bool S8, bool NORM, bool RED>
+template <int NS, bool GUARD, bool NORM, bool RED>
 __device__ __forceinline__ void v2_block(const uint32_t (&cb)[VU], const uint32_t (&sb)[VU], const uint32_t *s1,
                                          const uint32_t *s2, const uint32_t *s3, uint32_t *w1, uint32_t *w2, uint32_t *w3,
                                          uint32_t wr1, uint32_t wr2, uint32_t wr3, VPath2 &p1, VPath2 &p2, VPath2 &p3,
-                                         uint32_t negm, typename std::conditional<S8, uint16_t, uint32_t>::type *Sg, int cnt,
-                                         bool last)
+                                         uint32_t negm, uint32_t *Sg, int cnt, bool last)
 {
     uint32_t nx1[VU], nx2[VU], nx3[VU];
     uint32_t tp1 = 0, tp2 = 0, tp3 = 0;
@@ -769,10 +730,9 @@ __device__ __forceinline__ void v2_block(const uint32_t (&cb)[VU], const uint32_
     for (int u = 0; u < VU; u++) {
         if (!GUARD || u < cnt) {
             const uint32_t c = __byte_perm(cb[u], 0, 0x4140);                        // two uint8 costs -> u16x2
-            const uint32_t hi1 = __byte_perm(p1.cur, nx1[u], 0x5432), hi2 = __byte_perm(p2.cur, nx2[u], 0x5432),
-                           hi3 = __byte_perm(p3.cur, nx3[u], 0x5432);                // Lt[2k+1], Lt[2k+2]
-            uint32_t t1 = __vimin3_u16x2(p1.lo, hi1, p1.q), t2 = __vimin3_u16x2(p2.lo, hi2, p2.q),
-                     t3 = __vimin3_u16x2(p3.lo, hi3, p3.q);                          // min(Lt[d-1], Lt[d+1], min + P2 - P1)
+            // split-half packing: the neighbours d-1 / d+1 of both halves are the words k-1 / k+1 as they stand
+            uint32_t t1 = __vimin3_u16x2(p1.prev, nx1[u], p1.q), t2 = __vimin3_u16x2(p2.prev, nx2[u], p2.q),
+                     t3 = __vimin3_u16x2(p3.prev, nx3[u], p3.q);                     // min(Lt[d-1], Lt[d+1], min + P2 - P1)
             t1 = __viaddmin_u16x2(t1, SW_P1X2, p1.cur);                              // min(. + P1, Lt[d])
             t2 = __viaddmin_u16x2(t2, SW_P1X2, p2.cur);
             t3 = __viaddmin_u16x2(t3, SW_P1X2, p3.cur);
@@ -792,31 +752,28 @@ __device__ __forceinline__ void v2_block(const uint32_t (&cb)[VU], const uint32_
                 p1.mr = __vminu2(p1.mr, t1); p2.mr = __vminu2(p2.mr, t2); p3.mr = __vminu2(p3.mr, t3);
             }
             tp1 = t1; tp2 = t2; tp3 = t3;
-            if (S8) Sg[u * 32] = (uint16_t)__byte_perm(sum, 0, 0x4420);                      // each sum <= 222
-            else if (RED) red_add_u32(reinterpret_cast<uint32_t *>(Sg) + u * 32, sum);
+            if (RED) red_add_u32(Sg + u * 32, sum);
             else Sg[u * 32] = sum + sb[u];
-            p1.lo = hi1; p2.lo = hi2; p3.lo = hi3;
+            p1.prev = p1.cur; p2.prev = p2.cur; p3.prev = p3.cur;
             p1.cur = nx1[u]; p2.cur = nx2[u]; p3.cur = nx3[u];
         }
     }
 }
 
 // NS = GC * 32 ring slots + the border slot.
-// FULL: every warp's third of the disparity pairs is a whole number of VU-blocks (no guards in the inner loop).
-// S8: the sweep's own sum L1+L2+L3 goes out as a uint8 volume (layout of the cost volume) instead of S += (see sgm_h_kernel).
-// NORM: see above.
+// FULL: every warp's share of the words is a whole number of VU-blocks (no guards in the inner loop).  NORM, RED: see above.
 // halo: [CTA][r1 | r3][row parity][K2 state words + VPARTS part minima] inbound buffers, then one abort word at the end
 // Register cap: 96 where the S update is a reduction (no operand registers for S; no spills): the one-CTA-per-SM grid then
 // leaves a quarter of the register file and ~30 KB of shared memory per SM to the front / tail kernels of the neighbouring
 // batches, which run beside the sweep (measured: the sweep alone 6.09 -> 6.39 ms, the pipelined step 23.7 -> 23.3 ms)
-template <int NS, bool FULL, bool S8, bool NORM, bool RED>
-__global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_t *__restrict__ p2q_all,
+template <int NS, bool FULL, bool NORM, bool RED>
+__global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__restrict__ p2q_all,
                                                                                  const uint16_t *__restrict__ cost_all,
                                                                                  uint32_t *__restrict__ S_all, uint32_t *halo,
                                                                                  uint32_t *abort_flag, VArgs a)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    using SW = typename std::conditional<S8, uint16_t, uint32_t>::type;
+    using SW = uint32_t;
     const int rank = (int)(blockIdx.x % a.csize);
     const int cid = blockIdx.x / a.csize, nteams = gridDim.x / a.csize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -919,7 +876,7 @@ __global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_
             for (int u = 0; u < VU; u++) {
                 if (FULL || u < cnt) {
                     c[u] = cp[u * 32];
-                    sv[u] = (!S8 && !RED && with_s) ? sp[u * 32] : 0u;
+                    sv[u] = (!RED && with_s) ? sp[u * 32] : 0u;
                 }
             }
         };
@@ -930,9 +887,11 @@ __global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_
             int slotA = lc - sh; if (slotA < 0) slotA += n;
             int slotB = lc + sh; if (slotB >= n) slotB -= n;
             const int d1 = dj > 0 ? slotA : slotB, d2 = lc, d3 = dj > 0 ? slotB : slotA;
+            VTRACE(0);
             if (t > 0) {
                 // ---- rows t-1 of the groups this row depends on
                 wait_rows(t - 1u);
+                VTRACE(1);
                 // ---- lines entering from the neighbour CTAs: row t-1 of their edge column, into the ring slot of the entering lane
                 if (enter1 | enter3) {
                     const unsigned pp = (t - 1u) & 1u, tag = ((t - 1u) >> 1) & 7u;
@@ -959,13 +918,14 @@ __global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_
                     group_barrier();
                 }
             }
+            VTRACE(2);
             const long tb0 = (((long)i * G + g) * K2 + k0) * 32;
             const uint16_t *cp = cost_f + tb0;
             SW *sp = S_f + tb0;
             if (s + 1 < H) {
                 // pull the next row's operands of this warp into L2 while this row is being processed
                 const long tbn = (((long)(i + di) * G + g) * K2 + k0) * 32 - lane;
-                if (!S8 && k0 + lane < k1) prefetch_l2(S_f + tbn + lane * 32);       // (RED: the line is in L2 when the reduction arrives)
+                if (k0 + lane < k1) prefetch_l2(S_f + tbn + lane * 32);       // (RED: the line is in L2 when the reduction arrives)
                 if (k0 + 2 * lane < k1) prefetch_l2(cost_f + tbn + lane * 64);
             }
             uint32_t *w1 = st + (0 * K2 + k0) * NS + d1, *w2 = st + (1 * K2 + k0) * NS + d2, *w3 = st + (2 * K2 + k0) * NS + d3;
@@ -984,7 +944,6 @@ __global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_
                             const uint32_t c = __byte_perm(cb[u], 0, 0x4140);
                             w1[u * NS] = c; w2[u * NS] = c; w3[u * NS] = c;
                             p1.mr = __vminu2(p1.mr, c);
-                            if (S8) sp[u * 32] = 0;
                         }
                     }
 #pragma unroll
@@ -1009,24 +968,33 @@ __global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_
                 p3.q = (m3 + (p2w >> 16)) * 0x10001u;
                 p1.ng = m1; p2.ng = m2; p3.ng = m3;
                 const uint32_t negm = 0u - ((m1 + m2) + m3) * 0x10001u;
-                const uint32_t pv1 = k0 > 0 ? s1[-NS] : SW_INF2, pv2 = k0 > 0 ? s2[-NS] : SW_INF2, pv3 = k0 > 0 ? s3[-NS] : SW_INF2;
-                const int ke = (k1 - k0) * NS;
-                const uint32_t wr1 = k1 < K2 ? s1[ke] : SW_INF2, wr2 = k1 < K2 ? s2[ke] : SW_INF2, wr3 = k1 < K2 ? s3[ke] : SW_INF2;
+                // the words just outside this warp's share are read before the other warps of the column group may overwrite them;
+                // at the two ends of the disparity range they are the seams of the split-half packing:
+                // below word 0: (inf, Lt[K2-1]) from word K2-1; above word K2-1: (Lt[K2], inf) from word 0
+                const int ke = (k1 - k0) * NS, kt = (K2 - 1 - k0) * NS, kz = -k0 * NS;
+                p1.prev = k0 > 0 ? s1[-NS] : __byte_perm(SW_INF2, s1[kt], 0x5410);
+                p2.prev = k0 > 0 ? s2[-NS] : __byte_perm(SW_INF2, s2[kt], 0x5410);
+                p3.prev = k0 > 0 ? s3[-NS] : __byte_perm(SW_INF2, s3[kt], 0x5410);
+                const uint32_t wr1 = k1 < K2 ? s1[ke] : __byte_perm(s1[kz], SW_INF2, 0x5432),
+                               wr2 = k1 < K2 ? s2[ke] : __byte_perm(s2[kz], SW_INF2, 0x5432),
+                               wr3 = k1 < K2 ? s3[ke] : __byte_perm(s3[kz], SW_INF2, 0x5432);
                 p1.cur = s1[0]; p2.cur = s2[0]; p3.cur = s3[0];
-                p1.lo = __byte_perm(pv1, p1.cur, 0x5432); p2.lo = __byte_perm(pv2, p2.cur, 0x5432);
-                p3.lo = __byte_perm(pv3, p3.cur, 0x5432);
                 group_barrier();                    // every warp of the group has read its neighbours' boundary pairs and minima
+                VTRACE(3);
+                int trb = 4;
                 for (int kb = k0; kb < k1; kb += 2 * VU) {
                     uint32_t cn[VU], sn[VU];
                     const bool last1 = kb + VU >= k1;
                     if (!last1) load_block(cp + VU * 32, sp + VU * 32, k1 - kb - VU, cn, sn, true);
-                    v2_block<NS, !FULL, S8, NORM, RED>(cb, sb, s1, s2, s3, w1, w2, w3, wr1, wr2, wr3, p1, p2, p3, negm, sp, k1 - kb, last1);
+                    v2_block<NS, !FULL, NORM, RED>(cb, sb, s1, s2, s3, w1, w2, w3, wr1, wr2, wr3, p1, p2, p3, negm, sp, k1 - kb, last1);
+                    VTRACE(trb); trb++;
                     cp += VU * 32; sp += VU * 32;
                     s1 += VU * NS; s2 += VU * NS; s3 += VU * NS; w1 += VU * NS; w2 += VU * NS; w3 += VU * NS;
                     if (last1) break;
                     const bool last2 = kb + 2 * VU >= k1;
                     if (!last2) load_block(cp + VU * 32, sp + VU * 32, k1 - kb - 2 * VU, cb, sb, true);
-                    v2_block<NS, !FULL, S8, NORM, RED>(cn, sn, s1, s2, s3, w1, w2, w3, wr1, wr2, wr3, p1, p2, p3, negm, sp, k1 - kb - VU, last2);
+                    v2_block<NS, !FULL, NORM, RED>(cn, sn, s1, s2, s3, w1, w2, w3, wr1, wr2, wr3, p1, p2, p3, negm, sp, k1 - kb - VU, last2);
+                    VTRACE(trb); trb++;
                     cp += VU * 32; sp += VU * 32;
                     s1 += VU * NS; s2 += VU * NS; s3 += VU * NS; w1 += VU * NS; w2 += VU * NS; w3 += VU * NS;
                 }
@@ -1057,7 +1025,9 @@ __global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_
                 for (int k = k0 + lane; k < k1; k += 32) st_relaxed_gpu(dst + k, (st[(2 * K2 + k) * NS + sl] - mv * 0x10001u) | otag);
                 if (lane == 0) st_relaxed_gpu(dst + K2 + part, mv | otag);
             }
+            VTRACE(8);
             row_done(t);
+            VTRACE(9);
             // prefetch for the next row: its P2 word and first operand block
             if (s + 1 < H) {
                 const int in = i + di;
@@ -1068,10 +1038,18 @@ __global__ void __maxnreg__((RED && !S8) ? 96 : 128) sgm_v2_kernel(const uint32_
                 const uint16_t *cost_n = cost_all + (long)(f + nteams) * a.t.frame + lane;
                 load_block(cost_n + (((long)i1 * G + g) * K2 + k0) * 32, nullptr, k1 - k0, cb, sb, false);
             }
+            VTRACE(10);
             if (++sh == n) sh = 0;
         }
     }
 }
+
+#ifdef VPP_TRACE
+extern "C" int vppb200_debug_vtrace(unsigned long long *host, int n)
+{
+    return cudaMemcpyFromSymbol(host, g_vtrace, sizeof(unsigned long long) * (size_t)n) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 static size_t v_smem_bytes(int GC, int K2) { return ((size_t)3 * K2 * (GC * 32 + 1) + (size_t)3 * VPARTS * (GC * 32 + 1) + 4 + 4 * GC) * 4; }
 
@@ -1091,9 +1069,12 @@ static int v_resident_ctas(size_t smem, int threads, int *out)
     VPP_CUDA_TRY(cudaGetDevice(&dev));
     VPP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     constexpr int NS = GC * 32 + 1;
-    VPP_CUDA_TRY(cudaFuncSetAttribute(sgm_v2_kernel<NS, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VPP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgm_v2_kernel<NS, true, false, false, false>, threads, smem));
-    *out = per_sm >= 1 ? sms : 0;                   // one CTA per SM: a second one would only share the SM's issue slots
+    VPP_CUDA_TRY(cudaFuncSetAttribute(sgm_v2_kernel<NS, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VPP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgm_v2_kernel<NS, true, false, false>, threads, smem));
+    // One CTA per SM.  (Measured: two CTAs of different frames per SM on 64-column strips take 3.83 us per row for their 4
+    // column groups, one CTA with 5 groups 3.97 us -- the row time is a latency chain, wait -> hand-off -> setup -> loop ->
+    // push, that does not shrink with the strip, so the widest strip that fits wins.)
+    *out = per_sm >= 1 ? sms : 0;
     return VPPB200_OK;
 }
 static int v_resident(int GC, size_t smem, int *out)
@@ -1173,7 +1154,7 @@ void sweep_set_v_red(int on) { g_v_red = on != 0; }
 
 template <int GC>
 static int run_v_t(const uint32_t *p2q, const uint16_t *cost, uint32_t *S, uint32_t *halo, uint32_t *abort_flag, const TL &t, int pass,
-                   int n, const VPlan &p, bool s8, bool norm, cudaStream_t st)
+                   int n, const VPlan &p, bool norm, cudaStream_t st)
 {
     constexpr int NS = GC * 32 + 1;
     VArgs a;
@@ -1182,11 +1163,10 @@ static int run_v_t(const uint32_t *p2q, const uint16_t *cost, uint32_t *S, uint3
     const bool full = t.K2 % (VPARTS * VU) == 0;
     void *args[] = {(void *)&p2q, (void *)&cost, (void *)&S, (void *)&halo, (void *)&abort_flag, (void *)&a};
     const void *kern;
-    if (s8) kern = full ? (const void *)sgm_v2_kernel<NS, true, true, false, false> : (const void *)sgm_v2_kernel<NS, false, true, false, false>;
-    else if (norm && g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, true, true> : (const void *)sgm_v2_kernel<NS, false, false, true, true>;
-    else if (norm) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, true, false> : (const void *)sgm_v2_kernel<NS, false, false, true, false>;
-    else if (g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, false, true> : (const void *)sgm_v2_kernel<NS, false, false, false, true>;
-    else kern = full ? (const void *)sgm_v2_kernel<NS, true, false, false, false> : (const void *)sgm_v2_kernel<NS, false, false, false, false>;
+    if (norm && g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, true, true> : (const void *)sgm_v2_kernel<NS, false, true, true>;
+    else if (norm) kern = full ? (const void *)sgm_v2_kernel<NS, true, true, false> : (const void *)sgm_v2_kernel<NS, false, true, false>;
+    else if (g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, true> : (const void *)sgm_v2_kernel<NS, false, false, true>;
+    else kern = full ? (const void *)sgm_v2_kernel<NS, true, false, false> : (const void *)sgm_v2_kernel<NS, false, false, false>;
     VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     // cooperative launch: all CTAs resident (they poll each other's halo words), one grid sync at the start
     VPP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(p.csize * p.nteams)), dim3((unsigned)(p.GC * VPARTS * 32)), args,
@@ -1195,10 +1175,9 @@ static int run_v_t(const uint32_t *p2q, const uint16_t *cost, uint32_t *S, uint3
     return VPPB200_OK;
 }
 
-// s8: S is a uint8 volume (uint16 words, layout T) that receives this sweep's L1+L2+L3 instead of S += ...
 // norm: per-path normalisation (costs above the Hamming range, or frames too tall for the un-normalised state)
 static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, void *halo_ws, const TL &t, int pass, int n,
-                 const VPlan &p, bool s8, bool norm, cudaStream_t st)
+                 const VPlan &p, bool norm, cudaStream_t st)
 {
     uint32_t *halo = static_cast<uint32_t *>(halo_ws);
     uint32_t *abort_flag = nullptr;
@@ -1209,11 +1188,11 @@ static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, void *ha
     sgm_p2_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, p2q, t.W, t.H, G32, pass, total);
     VPP_LAUNCH_CHECK("sgm_p2_kernel");
     switch (p.GC) {
-        case 1: return run_v_t<1>(p2q, cost, S, halo, abort_flag, t, pass, n, p, s8, norm, st);
-        case 2: return run_v_t<2>(p2q, cost, S, halo, abort_flag, t, pass, n, p, s8, norm, st);
-        case 3: return run_v_t<3>(p2q, cost, S, halo, abort_flag, t, pass, n, p, s8, norm, st);
-        case 4: return run_v_t<4>(p2q, cost, S, halo, abort_flag, t, pass, n, p, s8, norm, st);
-        default: return run_v_t<5>(p2q, cost, S, halo, abort_flag, t, pass, n, p, s8, norm, st);
+        case 1: return run_v_t<1>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
+        case 2: return run_v_t<2>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
+        case 3: return run_v_t<3>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
+        case 4: return run_v_t<4>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
+        default: return run_v_t<5>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
     }
 }
 
@@ -1242,28 +1221,13 @@ bool aggregate_tile_supported(int W, int H, int D, int n)
 // 0 = done; 1 = this shape does not fit the sweep (caller uses sgm.cu); < 0 = error.
 // dl != NULL: the last sweep is fused with the winner-takes-all step (left + sub-pixel into dl, right into dr) and the
 // final S is never written; dl == NULL: S holds the aggregated volume in layout T.
-// byte_sums (needs dl and costs <= 24, i.e. no guided modulation): the S buffer (3 bytes per volume element) holds three uint8
-// partial-sum volumes instead of one uint16 S (see sgm_h_kernel).
-// Measured on B200 (batch 64 @K, profiles/r01_summary_v3.md): DRAM traffic of the four sweeps 94.5 -> 59.8 GB, but the step
-// is not faster (v-sweeps 7.1 -> 6.2 ms, h-sweeps 3.6 -> 4.4 and 5.9 -> 7.5 ms): the sweeps are bound by the integer ALU
-// pipe and by synchronisation, not by HBM.  Kept as an option (VPPB200_TUNE_SGM_BYTE_SUMS), off by default.
-static int g_byte_sums_off = 1;
-void sweep_set_byte_sums(int on) { g_byte_sums_off = !on; }
-// cen_l / cen_r != NULL: the cost volume cost8 is not an input but is produced by the forward sweep from the census images
-// (sweep_fuses_cost tells the caller when that is available and selected).
-// Measured on B200 (batch 64 @K): the stand-alone cost kernel (1.47 ms) disappears and the forward sweep grows from 3.56 to
-// 5.27 ms -- POPC issues on the same integer pipe the sweep saturates, so the popcounts do not hide in its idle issue slots;
-// step 25.87 vs 25.75 ms.  Bit-identical, kept as an option (VPPB200_TUNE_SGM_FUSE_COST), off by default.
-static int g_fuse_cost_off = 1;
-void sweep_set_fuse_cost(int on) { g_fuse_cost_off = !on; }
-bool sweep_fuses_cost(int W, int H, int D, int n, bool byte_sums)
-{
-    (void)H; (void)D; (void)n;
-    return !g_fuse_cost_off && W % 32 == 0 && (!byte_sums || g_byte_sums_off);
-}
+// plain_costs: the costs are plain Hamming distances (<= 24, no guided modulation): the v-sweeps keep their path state
+// un-normalised (see sgm_v2_kernel).
+// (Two variants of round 1 were measured again on this kernel generation and removed: uint8 partial-sum volumes instead of one
+// uint16 S -- 37 % less traffic, but the extra unpacking in the ALU-bound h-sweeps costs more than the v-sweeps gain, 25.4 vs
+// 25.1 ms per step -- and a forward h-sweep that produces the cost volume itself, 5.27 ms vs 3.56 + 1.47 ms.)
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, void *halo_ws, int W, int H, int D, int n,
-                          float *dl, float *dr, const float *lut, bool plain_costs, const StageHook *hook, cudaStream_t st,
-                          const uint32_t *cen_l, const uint32_t *cen_r)
+                          float *dl, float *dr, const float *lut, bool plain_costs, const StageHook *hook, cudaStream_t st)
 {
     const TL t = make_tl(W, H, D);
     VPlan plan;
@@ -1271,24 +1235,16 @@ int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S1
     if (rc) return rc;
     const uint16_t *cost = reinterpret_cast<const uint16_t *>(cost8);
     uint32_t *S = reinterpret_cast<uint32_t *>(S16);
-    const bool s8 = plain_costs && dl && !g_byte_sums_off;
-    // un-normalised path state (see sgm_v2_kernel): Hamming costs only, and 24 per row must stay inside uint16
+    // un-normalised path state: Hamming costs only, and 24 per row must stay inside uint16
     const bool norm = !plain_costs || 24L * H + 128 > 65535;
-    ByteVols bv{nullptr, nullptr, nullptr};
-    if (s8) { bv.a0 = S16; bv.a1 = S16 + (size_t)n * t.frame; bv.a2 = S16 + (size_t)2 * n * t.frame; }
     auto done = [&](int stage) { if (hook) hook->fn(hook->ctx, stage); };
-    CostGen cg{nullptr, nullptr, nullptr};
-    if (cen_l && cen_r) {
-        if (s8 || W % 32 != 0) return VPPB200_ERR_ARG;
-        cg = CostGen{cen_l, cen_r, reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(cost8))};
-    }
-    if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, s8, bv, st, cg))) return rc;
+    if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, st))) return rc;
     done(VPPB200_STAGE_SGM_H_FWD);
-    if ((rc = run_v(img, cost, s8 ? reinterpret_cast<uint32_t *>(bv.a1) : S, halo_ws, t, 0, n, plan, s8, norm, st))) return rc;
+    if ((rc = run_v(img, cost, S, halo_ws, t, 0, n, plan, norm, st))) return rc;
     done(VPPB200_STAGE_SGM_V_DOWN);
-    if ((rc = run_v(img, cost, s8 ? reinterpret_cast<uint32_t *>(bv.a2) : S, halo_ws, t, 1, n, plan, s8, norm, st))) return rc;
+    if ((rc = run_v(img, cost, S, halo_ws, t, 1, n, plan, norm, st))) return rc;
     done(VPPB200_STAGE_SGM_V_UP);
-    if ((rc = run_h(img, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, s8, bv, st))) return rc;
+    if ((rc = run_h(img, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, st))) return rc;
     done(VPPB200_STAGE_SGM_H_BWD);
     return VPPB200_OK;
 }
