@@ -172,6 +172,33 @@ int vppb200_compute_rsgm_tapped(const uint8_t *left, const uint8_t *left_vpp, co
                                 void *workspace, size_t workspace_bytes, int n, void *stream,
                                 const vppb200_rsgm_taps *taps);
 
+/* ---- one frame split into row bands over several GPUs (an oversized frame) -------------------------------
+ * compute_rsgm (models/rsgm/rsgm.py:250-294) as three calls so that the aggregation -- the 2.2 GB of volumes of a Middlebury
+ * frame -- runs band by band on different GPUs, EXACTLY (unlike the reference's approximate StripedStereoSGM,
+ * RSGM/StereoSGM.h:116-133): the vertical / diagonal sweeps of a band continue from the row state the neighbouring band exported.
+ *   vppb200_rsgm_front_census: pad + RGB2GRAY + census 5x5 of the WHOLE frame (rsgm.py:254-262,:8-28) ->
+ *       guide uint8 [Hp*Wp] (the first Hp*Wp bytes of the padded `left`), census_l / census_r uint32 [Hp][Wp]
+ *   vppb200_sgm_band: rows [row0, row0 + rows) of the padded frame.  phases (bit mask, queued in this order):
+ *       1 Hamming volume of the band, 2 h-sweep forward, 4 v-sweep down, 8 v-sweep up, 16 h-sweep backward + WTA / sub-pixel.
+ *       cost_band: uint8 layout-T volume of the band (vppb200_banded_dims: volume_bytes_per_row * rows bytes), S_band twice that.
+ *       state_in / state_out: the row state of the three vertical / diagonal paths (state_words uint32 each): phase 4 of a band
+ *       with row0 > 0 reads state_in = what phase 4 of the band above wrote to its state_out; phase 8 of a band that does not end
+ *       at Hp reads state_in = state_out of phase 8 of the band below.  dl_band / dr_band: float32 [rows][Wp] raw disparities.
+ *   vppb200_rsgm_tail: median .. background fill (rsgm.py:273-292) on the gathered raw maps dl, dr float32 [Hp][Wp] -> disp_out
+ *       float32 [H][W] (flags bit 0: sub-pixel).  dl / dr are read only.
+ * workspace: vppb200_banded_workspace_bytes, private to one call at a time. */
+size_t vppb200_banded_workspace_bytes(int H, int W, int C, int D);
+int vppb200_banded_dims(int H, int W, int C, int D, int *Hp, int *Wp, int64_t *state_words, int64_t *volume_bytes_per_row);
+int vppb200_rsgm_front_census(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp, uint8_t *guide,
+                              uint32_t *census_l, uint32_t *census_r, int H, int W, int C, int D, void *workspace,
+                              size_t workspace_bytes, void *stream);
+int vppb200_sgm_band(const uint8_t *guide, const uint32_t *census_l, const uint32_t *census_r, uint8_t *cost_band,
+                     uint16_t *S_band, int H, int W, int C, int D, int row0, int rows, int phases, const uint32_t *state_in,
+                     uint32_t *state_out, float *dl_band, float *dr_band, const float *rcp_lut, void *workspace,
+                     size_t workspace_bytes, void *stream);
+int vppb200_rsgm_tail(float *dl, float *dr, float *disp_out, int H, int W, int C, int D, int flags, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
 /* ---- vpp_core_opt operators ---------------------------------------------------------------------------------
  * virtual_projection_scan_rnd(l, r, g, width, height, channels, uniform_color, wsize, direction, c, c_occ, g_occ,
  *                             discard_occluded, interpolate) -> #hints                vpp_core_opt.pyx:53-131

@@ -27,6 +27,7 @@ SYMBOLS = [
     "vppb200_vpp_scan_max_dist_adaptive", "vppb200_bilateral_filling", "vppb200_f32chw_to_u8hwc", "vppb200_gt_reshape",
     "vppb200_u8hwc_to_f32chw", "vppb200_set_tuning",
     "vppb200_occlusion_workspace_bytes", "vppb200_occlusion_heuristic",
+    "vppb200_banded_workspace_bytes", "vppb200_banded_dims", "vppb200_rsgm_front_census", "vppb200_sgm_band", "vppb200_rsgm_tail",
 ]
 
 _lib = None
@@ -52,6 +53,7 @@ def lib():
         l.vppb200_vpp_max_dist_workspace_bytes.restype = C.c_size_t
         l.vppb200_rsgm_workspace_bytes_sets.restype = C.c_size_t
         l.vppb200_occlusion_workspace_bytes.restype = C.c_size_t
+        l.vppb200_banded_workspace_bytes.restype = C.c_size_t
         _lib = l
     return _lib
 

@@ -523,6 +523,105 @@ extern "C" int vppb200_compute_rsgm_phases(const uint8_t *left, const uint8_t *l
                        workspace_bytes, n, stream, nullptr, phases, sets, set);
 }
 
+// ---- one frame split into row bands over several GPUs ------------------------------
+// The stages of compute_rsgm as three calls, so that a caller (vppstereo_b200/banded.py) can run the aggregation of a band on
+// each GPU and hand the vertical sweeps' row state from band to band:
+//   front_census: pad + gray + census of the WHOLE frame (a few MB; every rank does it) -> guide, census_l, census_r
+//   sgm_band:     Hamming volume and the four sweeps for rows [row0, row0 + rows) only (the 2.2 GB of a Middlebury frame's
+//                 volumes are what is split), raw left / right disparities of those rows out
+//   tail:         median .. background fill on the gathered raw disparities of the whole frame
+namespace vppb200 {
+struct BandWs { uint8_t *gray_l, *gray_r; void *halo; float *dlf, *drf; TailBufs tail; };
+static size_t band_ws_layout(const RsgmDims &d, int rows, void *base, BandWs *ws)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return b ? b + o : (char *)nullptr; };
+    const size_t np = (size_t)d.Hp * d.Wp, nc = (size_t)d.H * tail_stride(d.W);
+    BandWs w;
+    w.gray_l = (uint8_t *)take(np); w.gray_r = (uint8_t *)take(np);
+    w.halo = (void *)take(sweep_halo_bytes(d.Wp, rows > 0 ? rows : d.Hp, d.D, 1));
+    w.dlf = (float *)take(np * 4); w.drf = (float *)take(np * 4);
+    w.tail.u8 = (uint8_t *)take(nc); w.tail.label = (int *)take(nc * 4); w.tail.count = (int *)take(nc * 4);
+    if (ws) *ws = w;
+    return off;
+}
+}  // namespace vppb200
+
+extern "C" size_t vppb200_banded_workspace_bytes(int H, int W, int C, int D)
+{
+    if (H <= 0 || W <= 0 || D <= 0 || D % 8 || D > 256 || (C != 1 && C != 3)) return 0;
+    return band_ws_layout(make_dims(H, W, C, D), 0, nullptr, nullptr);
+}
+
+extern "C" int vppb200_banded_dims(int H, int W, int C, int D, int *Hp, int *Wp, int64_t *state_words, int64_t *volume_bytes_per_row)
+{
+    if (H <= 0 || W <= 0 || D <= 0 || D % 8 || D > 256 || (C != 1 && C != 3)) return VPPB200_ERR_ARG;
+    const RsgmDims d = make_dims(H, W, C, D);
+    if (Hp) *Hp = d.Hp;
+    if (Wp) *Wp = d.Wp;
+    if (state_words) *state_words = sweep_state_words(d.Wp, D);
+    if (volume_bytes_per_row) *volume_bytes_per_row = (int64_t)(tile_volume_elems(d.Wp, 1, D, 1));      // uint8 costs; S = 2x
+    return VPPB200_OK;
+}
+
+extern "C" int vppb200_rsgm_front_census(const uint8_t *left, const uint8_t *left_vpp, const uint8_t *right_vpp, uint8_t *guide,
+                                         uint32_t *census_l, uint32_t *census_r, int H, int W, int C, int D, void *workspace,
+                                         size_t workspace_bytes, void *stream)
+{
+    if (!left || !left_vpp || !right_vpp || !guide || !census_l || !census_r || H <= 0 || W <= 0 || (C != 1 && C != 3)) return VPPB200_ERR_ARG;
+    if (D <= 0 || D % 8 != 0 || D > 256) return VPPB200_ERR_DISP;
+    const RsgmDims d = make_dims(H, W, C, D);
+    if (!workspace || workspace_bytes < band_ws_layout(d, 0, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    BandWs w;
+    band_ws_layout(d, 0, workspace, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, 1, st))) return rc;
+    if ((rc = launch_census(w.gray_r, census_r, d.Wp, d.Hp, 1, st))) return rc;
+    if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, 1, st))) return rc;
+    if ((rc = launch_pad_flatbytes(left, guide, d, 1, st))) return rc;
+    return launch_census(w.gray_l, census_l, d.Wp, d.Hp, 1, st);
+}
+
+extern "C" int vppb200_sgm_band(const uint8_t *guide, const uint32_t *census_l, const uint32_t *census_r, uint8_t *cost_band,
+                                uint16_t *S_band, int H, int W, int C, int D, int row0, int rows, int phases, const uint32_t *state_in,
+                                uint32_t *state_out, float *dl_band, float *dr_band, const float *rcp_lut, void *workspace,
+                                size_t workspace_bytes, void *stream)
+{
+    if (!guide || !cost_band || !S_band || H <= 0 || W <= 0 || (C != 1 && C != 3) || phases <= 0 || phases > 31) return VPPB200_ERR_ARG;
+    if (D <= 0 || D % 8 != 0 || D > 256) return VPPB200_ERR_DISP;
+    if ((phases & 1) && (!census_l || !census_r)) return VPPB200_ERR_ARG;
+    if ((phases & 16) && (!dl_band || !dr_band)) return VPPB200_ERR_ARG;
+    const RsgmDims d = make_dims(H, W, C, D);
+    if (!workspace || workspace_bytes < band_ws_layout(d, 0, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    BandWs w;
+    band_ws_layout(d, 0, workspace, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!rcp_lut) rcp_lut = device_rcp_lut(st);
+    if (!rcp_lut) return cuda_fail("device_rcp_lut", cudaGetLastError());
+    return launch_aggregate_band(guide, census_l, census_r, cost_band, S_band, w.halo, d.Wp, d.Hp, D, row0, rows, 1, phases, state_in,
+                                 state_out, dl_band, dr_band, rcp_lut, true, st);
+}
+
+extern "C" int vppb200_rsgm_tail(float *dl, float *dr, float *disp_out, int H, int W, int C, int D, int flags, void *workspace,
+                                 size_t workspace_bytes, void *stream)
+{
+    if (!dl || !dr || !disp_out || H <= 0 || W <= 0 || (C != 1 && C != 3)) return VPPB200_ERR_ARG;
+    if (D <= 0 || D % 8 != 0 || D > 256) return VPPB200_ERR_DISP;
+    const RsgmDims d = make_dims(H, W, C, D);
+    if (!workspace || workspace_bytes < band_ws_layout(d, 0, nullptr, nullptr)) return VPPB200_ERR_WORKSPACE;
+    BandWs w;
+    band_ws_layout(d, 0, workspace, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = launch_median(dr, w.drf, d.Wp, d.Hp, 1, st))) return rc;
+    if ((rc = launch_interp_clip(w.drf, d.Wp, d.Hp, 1, st))) return rc;
+    if ((rc = launch_median(dl, w.dlf, d.Wp, d.Hp, 1, st))) return rc;
+    if ((rc = launch_interp_clip(w.dlf, d.Wp, d.Hp, 1, st))) return rc;
+    return launch_tail(w.dlf, w.drf, disp_out, d, flags & 1, w.tail, 1, st);
+}
+
 // ---- hand-off to the networks (test.py:179-197) -----------------------------------------------------------
 namespace vppb200 {
 __global__ void u8hwc_to_f32chw_kernel(const uint8_t *__restrict__ src, float *__restrict__ dst, int H, int W, int C, int pt,

@@ -57,6 +57,12 @@ int launch_aggregate_fast(const uint8_t *img, const uint8_t *dsi, uint16_t *S, i
 bool aggregate_tile_supported(int W, int H, int D, int n);
 size_t tile_volume_elems(int W, int H, int D, int n);
 int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st);
+int launch_cost_tile_band(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int Hfull, int D, int row0, int rows, int n,
+                          cudaStream_t st);
+long sweep_state_words(int W, int D);
+int launch_aggregate_band(const uint8_t *guide_full, const uint32_t *cen_l_full, const uint32_t *cen_r_full, uint8_t *cost8, uint16_t *S16,
+                          void *halo_ws, int W, int Hfull, int D, int row0, int rows, int n, int phases, const uint32_t *state_in,
+                          uint32_t *state_out, float *dl, float *dr, const float *lut, bool plain_costs, cudaStream_t st);
 int launch_guided_tile(uint8_t *cost, const float *hints, const float *valid, const RsgmDims &d, int n, cudaStream_t st);
 struct StageHook { void (*fn)(void *, int); void *ctx; };   // called with VPPB200_STAGE_* when that stage has been queued
 size_t sweep_halo_bytes(int W, int H, int D, int n);       // workspace of the v-sweep: inter-CTA halo lines, abort flag, P2 table

@@ -107,8 +107,11 @@ __device__ __forceinline__ void cost_pairs(const uint32_t (&L)[8], const uint32_
     }
 }
 
+// Row bands: cl / cr / cost point at the band's first row, t.H = rows of the band, row0 / Hfull place it in the frame (the
+// constant-12 rows are the first and last two rows of the FRAME).
 __global__ void __launch_bounds__(256) cost_tile_kernel(const uint32_t *__restrict__ cl, const uint32_t *__restrict__ cr,
-                                                        uint16_t *__restrict__ cost, TL t, long total_tiles)
+                                                        uint16_t *__restrict__ cost, TL t, long total_tiles, int row0, int Hfull,
+                                                        long census_frame_stride)
 {
     const long tile = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (tile >= total_tiles) return;
@@ -116,7 +119,8 @@ __global__ void __launch_bounds__(256) cost_tile_kernel(const uint32_t *__restri
     const int xq = lane & 3, kq = lane >> 2;
     const int g = (int)(tile % t.G);
     const long row = tile / t.G;                   // row over all frames
-    const int y = (int)(row % t.H);
+    const int y = row0 + (int)(row % t.H);         // row inside the frame
+    const long crow = (row / t.H) * census_frame_stride + (row % t.H) * (long)t.W;      // census words of this band row
     const int x = g * 32 + 8 * xq;
     const int KB = (t.K2 + 7) / 8;
     const int k0 = kq * KB, k1 = min(t.K2, k0 + KB);
@@ -125,25 +129,32 @@ __global__ void __launch_bounds__(256) cost_tile_kernel(const uint32_t *__restri
         for (int k = k0; k < k1; k++) out[k * 4] = make_uint4(0, 0, 0, 0);
         return;
     }
-    if (y < 2 || y >= t.H - 2) {
+    if (y < 2 || y >= Hfull - 2) {
         for (int k = k0; k < k1; k++) out[k * 4] = make_uint4(0x0C0C0C0Cu, 0x0C0C0C0Cu, 0x0C0C0C0Cu, 0x0C0C0C0Cu);
         return;
     }
     uint32_t L[8];
     {
-        const uint4 a = *reinterpret_cast<const uint4 *>(cl + row * t.W + x), b = *reinterpret_cast<const uint4 *>(cl + row * t.W + x + 4);
+        const uint4 a = *reinterpret_cast<const uint4 *>(cl + crow + x), b = *reinterpret_cast<const uint4 *>(cl + crow + x + 4);
         L[0] = a.x; L[1] = a.y; L[2] = a.z; L[3] = a.w; L[4] = b.x; L[5] = b.y; L[6] = b.z; L[7] = b.w;
     }
-    const uint32_t *rp = cr + row * t.W;
+    const uint32_t *rp = cr + crow;
     if (g * 32 >= t.D + 2) cost_pairs<false>(L, rp, x, t.W, t.K2, k0, k1, out);       // every d <= x and every read inside the row
     else cost_pairs<true>(L, rp, x, t.W, t.K2, k0, k1, out);
 }
 
 int launch_cost_tile(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int H, int D, int n, cudaStream_t st)
 {
-    const TL t = make_tl(W, H, D);
-    const long tiles = (long)n * H * t.G;
-    cost_tile_kernel<<<cdiv(tiles * 32, 256), 256, 0, st>>>(cl, cr, reinterpret_cast<uint16_t *>(cost), t, tiles);
+    return launch_cost_tile_band(cl, cr, cost, W, H, D, 0, H, n, st);
+}
+// rows [row0, row0 + rows) of frames of Hfull rows: cl / cr are the FULL census images, cost holds the band only
+int launch_cost_tile_band(const uint32_t *cl, const uint32_t *cr, uint8_t *cost, int W, int Hfull, int D, int row0, int rows, int n,
+                          cudaStream_t st)
+{
+    const TL t = make_tl(W, rows, D);
+    const long tiles = (long)n * rows * t.G;
+    cost_tile_kernel<<<cdiv(tiles * 32, 256), 256, 0, st>>>(cl + (long)row0 * W, cr + (long)row0 * W, reinterpret_cast<uint16_t *>(cost), t,
+                                                            tiles, row0, Hfull, (long)W * Hfull);
     VPP_LAUNCH_CHECK("cost_tile_kernel");
     return VPPB200_OK;
 }
@@ -568,6 +579,14 @@ struct VArgs {
     int pass;          // 0: top-down (di = dj = +1), 1: bottom-up (di = dj = -1)
     int csize;         // CTAs per team (one frame)
     int GC;            // 32-column groups per CTA, ceil(G / csize)
+    // Row bands (a frame split over several GPUs): t.H is the band's row count, the volumes hold the band's
+    // rows only.  pass_start = the band begins with the pass's first image row (L = C there); otherwise the sweep continues from
+    // `state_in`, the path state of the row before the band as another band's sweep left it in `state_out`:
+    // [frame][3 paths][G*32 columns][K2 words], then [frame][3][G*32][VPARTS] part minima (state_words per frame in total).
+    int pass_start;
+    const uint32_t *state_in;
+    uint32_t *state_out;
+    long state_words;
 };
 
 #ifndef VPP_VPARTS
@@ -633,15 +652,16 @@ static constexpr uint32_t HALO_INVALID = 0xF0000000u;
 // (P2 - P1) of the three paths of one pass for every pixel, packed q1 | q2 << 8 | q3 << 16; [n][H][G*32] words.
 // P2 = adaptP2(I(p), I(p - r)) with I read from the FLAT byte stream of the guide (RSGM/StereoSGM.hpp:92-99,
 // StereoSGM_SSE.hpp:221,:238-243: on the row after the pass's first row the "previous line" is that same row).
+// Row bands: the table covers rows [row0, row0 + Hb) of frames of H rows (img_all = the full guide images).
 __global__ void __launch_bounds__(256) sgm_p2_kernel(const uint8_t *__restrict__ img_all, uint32_t *__restrict__ p2q, int W, int H,
-                                                     int G32, int pass, long total)
+                                                     int G32, int pass, long total, int row0, int Hb)
 {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int x = (int)(t % G32);
     const long r = t / G32;
-    const int i = (int)(r % H);
-    const long f = r / H;
+    const int i = row0 + (int)(r % Hb);
+    const long f = r / Hb;
     const int dj = pass == 0 ? 1 : -1, di = dj, i1 = pass == 0 ? 0 : H - 1;
     uint32_t out = 0;
     if (i != i1) {
@@ -880,7 +900,8 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
                 }
             }
         };
-        if (f == cid) load_block(cost_f + (((long)i1 * G + g) * K2 + k0) * 32, nullptr, k1 - k0, cb, sb, false);
+        const bool cont = !a.pass_start;            // row band that continues a sweep: its first row is an ordinary row
+        if (f == cid) load_block(cost_f + (((long)i1 * G + g) * K2 + k0) * 32, S_f + (((long)i1 * G + g) * K2 + k0) * 32, k1 - k0, cb, sb, cont);
         for (int s = 0; s < H; s++, t++) {
             const int i = i1 + s * di;
             // ring slots: a line moving +1 column per row sits in slot (lc - t) mod n, one moving -1 in (lc + t) mod n
@@ -918,6 +939,24 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
                     group_barrier();
                 }
             }
+            if (s == 0 && cont) {
+                // ---- row band that continues a sweep: the predecessors of this row come from the state another band's sweep
+                // exported (columns x - dj, x, x + dj of the row before the band), straight into the ring slots this row reads
+                const uint32_t *imp = a.state_in + (long)f * a.state_words;
+                const uint32_t *impm = imp + (long)3 * G32 * K2;
+                const int xs[3] = {x - dj, x, x + dj};
+                const int sl[3] = {d1, d2, d3};
+#pragma unroll
+                for (int pth = 0; pth < 3; pth++) {
+                    if (xs[pth] >= 0 && xs[pth] < W) {
+                        const uint32_t *src = imp + ((long)pth * G32 + xs[pth]) * K2;
+                        for (int k = k0; k < k1; k++) st[(pth * K2 + k) * NS + sl[pth]] = src[k];
+                        mn[(pth * VPARTS + part) * NS + sl[pth]] = impm[((long)pth * G32 + xs[pth]) * VPARTS + part];
+                    }
+                }
+                p2w = p2_f[(long)i * G32];
+                group_barrier();
+            }
             VTRACE(2);
             const long tb0 = (((long)i * G + g) * K2 + k0) * 32;
             const uint16_t *cp = cost_f + tb0;
@@ -931,7 +970,7 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
             uint32_t *w1 = st + (0 * K2 + k0) * NS + d1, *w2 = st + (1 * K2 + k0) * NS + d2, *w3 = st + (2 * K2 + k0) * NS + d3;
             VPath2 p1, p2, p3;
             p1.mr = p2.mr = p3.mr = SW_INF2;
-            if (s == 0) {
+            if (s == 0 && !cont) {
                 // first row of the pass: L = C on all three paths, nothing is summed (StereoSGM_SSE.hpp:116-218)
                 for (int kb = k0; kb < k1; kb += VU) {
                     uint32_t cn[VU], sn[VU];
@@ -1005,6 +1044,20 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
             mn[(0 * VPARTS + part) * NS + d1] = mr1;
             mn[(1 * VPARTS + part) * NS + d2] = mr2;
             mn[(2 * VPARTS + part) * NS + d3] = mr3;
+            if (s == H - 1 && a.state_out != nullptr) {
+                // ---- last row of a band: this column's new state of the three paths for the band that continues the sweep
+                uint32_t *ex = a.state_out + (long)f * a.state_words;
+                uint32_t *exm = ex + (long)3 * G32 * K2;
+                const int sl[3] = {d1, d2, d3};
+                const uint32_t mrs[3] = {mr1, mr2, mr3};
+                __syncwarp();
+#pragma unroll
+                for (int pth = 0; pth < 3; pth++) {
+                    uint32_t *dst = ex + ((long)pth * G32 + x) * K2;
+                    for (int k = k0; k < k1; k++) dst[k] = st[(pth * K2 + k) * NS + sl[pth]];
+                    exm[((long)pth * G32 + x) * VPARTS + part] = mrs[pth];
+                }
+            }
             // push the lines that leave the strip to the neighbour's inbound buffer of this row's parity: state relative to
             // this part's minimum (<= max C + P2 per half: the tag bits stay free), then the minimum itself
             const unsigned par = t & 1u;
@@ -1036,7 +1089,8 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
                 load_block(cost_f + tbn, S_f + tbn, k1 - k0, cb, sb, true);
             } else if (f + nteams < a.n) {
                 const uint16_t *cost_n = cost_all + (long)(f + nteams) * a.t.frame + lane;
-                load_block(cost_n + (((long)i1 * G + g) * K2 + k0) * 32, nullptr, k1 - k0, cb, sb, false);
+                const SW *S_n = reinterpret_cast<SW *>(S_all) + (long)(f + nteams) * a.t.frame + lane;
+                load_block(cost_n + (((long)i1 * G + g) * K2 + k0) * 32, S_n + (((long)i1 * G + g) * K2 + k0) * 32, k1 - k0, cb, sb, cont);
             }
             VTRACE(10);
             if (++sh == n) sh = 0;
@@ -1152,13 +1206,21 @@ size_t sweep_halo_bytes(int W, int H, int D, int n)
 static int g_v_red = 1;             // S += by red.global.add (default) instead of load + add + store
 void sweep_set_v_red(int on) { g_v_red = on != 0; }
 
+// words of one frame's exported row state: [3][G*32][K2] path words + [3][G*32][VPARTS] part minima
+long sweep_state_words(int W, int D) { return (long)3 * ((W + 31) / 32) * 32 * (D / 2 + VPARTS); }
+
+// a row band inside frames of Hfull rows (whole frame: row0 = 0, Hfull = t.H, pass_start = 1, no state hand-off)
+struct VBand { int Hfull, row0, pass_start; const uint32_t *state_in; uint32_t *state_out; };
+
 template <int GC>
 static int run_v_t(const uint32_t *p2q, const uint16_t *cost, uint32_t *S, uint32_t *halo, uint32_t *abort_flag, const TL &t, int pass,
-                   int n, const VPlan &p, bool norm, cudaStream_t st)
+                   int n, const VPlan &p, bool norm, const VBand &band, cudaStream_t st)
 {
     constexpr int NS = GC * 32 + 1;
     VArgs a;
     a.t = t; a.n = n; a.pass = pass; a.csize = p.csize; a.GC = p.GC;
+    a.pass_start = band.pass_start; a.state_in = band.state_in; a.state_out = band.state_out;
+    a.state_words = sweep_state_words(t.W, t.D);
     // FULL: K2 splits into VPARTS equal shares of whole VU-blocks
     const bool full = t.K2 % (VPARTS * VU) == 0;
     void *args[] = {(void *)&p2q, (void *)&cost, (void *)&S, (void *)&halo, (void *)&abort_flag, (void *)&a};
@@ -1177,22 +1239,23 @@ static int run_v_t(const uint32_t *p2q, const uint16_t *cost, uint32_t *S, uint3
 
 // norm: per-path normalisation (costs above the Hamming range, or frames too tall for the un-normalised state)
 static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, void *halo_ws, const TL &t, int pass, int n,
-                 const VPlan &p, bool norm, cudaStream_t st)
+                 const VPlan &p, bool norm, cudaStream_t st, const VBand *bandp = nullptr)
 {
+    const VBand band = bandp ? *bandp : VBand{t.H, 0, 1, nullptr, nullptr};
     uint32_t *halo = static_cast<uint32_t *>(halo_ws);
     uint32_t *abort_flag = nullptr;
     VPP_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void **>(&abort_flag), g_sweep_abort));
     uint32_t *p2q = reinterpret_cast<uint32_t *>(static_cast<char *>(halo_ws) + HALO_LINES_BYTES + 256);
     const int G32 = t.G * 32;
     const long total = (long)n * t.H * G32;
-    sgm_p2_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, p2q, t.W, t.H, G32, pass, total);
+    sgm_p2_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, p2q, t.W, band.Hfull, G32, pass, total, band.row0, t.H);
     VPP_LAUNCH_CHECK("sgm_p2_kernel");
     switch (p.GC) {
-        case 1: return run_v_t<1>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
-        case 2: return run_v_t<2>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
-        case 3: return run_v_t<3>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
-        case 4: return run_v_t<4>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
-        default: return run_v_t<5>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, st);
+        case 1: return run_v_t<1>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, band, st);
+        case 2: return run_v_t<2>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, band, st);
+        case 3: return run_v_t<3>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, band, st);
+        case 4: return run_v_t<4>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, band, st);
+        default: return run_v_t<5>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, band, st);
     }
 }
 
@@ -1246,6 +1309,46 @@ int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S1
     done(VPPB200_STAGE_SGM_V_UP);
     if ((rc = run_h(img, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, st))) return rc;
     done(VPPB200_STAGE_SGM_H_BWD);
+    return VPPB200_OK;
+}
+
+// One row band [row0, row0 + rows) of frames of Hfull rows, for a frame that is split over several GPUs (the
+// exact banded pipeline, not the reference's approximate StripedStereoSGM, RSGM/StereoSGM.h:116-133).  `phases` selects the
+// steps to queue: COST (Hamming volume of the band from the full census images) | H_FWD | V_DOWN | V_UP | H_BWD (fused with WTA).
+// The vertical sweeps continue across bands through the exported row state: V_DOWN of a band that does not start at row 0 reads
+// state_in (= state_out of the band above), V_UP of a band that does not end at the last row reads state_in (= state_out of the
+// band below); state_out == NULL: nothing is exported.  cost8 / S16 / dl / dr hold the band's rows only.
+int launch_aggregate_band(const uint8_t *guide_full, const uint32_t *cen_l_full, const uint32_t *cen_r_full, uint8_t *cost8, uint16_t *S16,
+                          void *halo_ws, int W, int Hfull, int D, int row0, int rows, int n, int phases, const uint32_t *state_in,
+                          uint32_t *state_out, float *dl, float *dr, const float *lut, bool plain_costs, cudaStream_t st)
+{
+    const TL t = make_tl(W, rows, D);
+    if (row0 < 0 || rows < 3 || row0 + rows > Hfull) return VPPB200_ERR_ARG;
+    VPlan plan;
+    int rc = plan_v(t, n, &plan);
+    if (rc) return rc < 0 ? rc : VPPB200_ERR_ARG;
+    const uint16_t *cost = reinterpret_cast<const uint16_t *>(cost8);
+    uint32_t *S = reinterpret_cast<uint32_t *>(S16);
+    const uint8_t *guide_band = guide_full + (long)row0 * W;       // the h-sweeps read the band's own rows of the guide (per frame: + f * W * Hfull)
+    const bool norm = !plain_costs || 24L * Hfull + 128 > 65535;
+    if (n != 1 && Hfull != rows) {
+        // frames are Hfull * W apart in the guide but rows * W apart in an h-sweep's row numbering: one frame per call when banded
+        return VPPB200_ERR_ARG;
+    }
+    if (phases & 1) if ((rc = launch_cost_tile_band(cen_l_full, cen_r_full, cost8, W, Hfull, D, row0, rows, n, st))) return rc;
+    if (phases & 2) if ((rc = run_h(guide_band, cost, S, t, 0, n, nullptr, nullptr, nullptr, st))) return rc;
+    if (phases & 4) {
+        const VBand b{Hfull, row0, row0 == 0 ? 1 : 0, row0 == 0 ? nullptr : state_in, state_out};
+        if (!b.pass_start && !state_in) return VPPB200_ERR_ARG;
+        if ((rc = run_v(guide_full, cost, S, halo_ws, t, 0, n, plan, norm, st, &b))) return rc;
+    }
+    if (phases & 8) {
+        const bool last = row0 + rows == Hfull;
+        const VBand b{Hfull, row0, last ? 1 : 0, last ? nullptr : state_in, state_out};
+        if (!b.pass_start && !state_in) return VPPB200_ERR_ARG;
+        if ((rc = run_v(guide_full, cost, S, halo_ws, t, 1, n, plan, norm, st, &b))) return rc;
+    }
+    if (phases & 16) if ((rc = run_h(guide_band, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, st))) return rc;
     return VPPB200_OK;
 }
 

@@ -236,6 +236,37 @@ class PeerGather:
                 self._copy(cs, self.peer_bufs[p][k % self.depth, self.rank], local)
                 self._copy(cs, self.peer_words[p][0, self.rank:self.rank + 1], self.ticks[k + 1:k + 2])
 
+    # ---- point-to-point use of the same buffers (a mailbox per (slot, source rank)): the row state of a banded sweep travels to
+    # ONE neighbour.  Messages of one sender to one receiver carry increasing k; message k lands in bufs[k % depth, sender].
+    def send(self, k, local, dst):
+        """message k (produced on the current stream) to rank `dst` only"""
+        torch = self.torch
+        if not self.available:
+            raise RuntimeError(f"PeerGather.send needs peer-mapped buffers ({self.why})")
+        local = local.contiguous()
+        cs = self.copy_stream
+        cs.wait_stream(torch.cuda.current_stream(self.device))
+        local.record_stream(cs)
+        with torch.cuda.device(self.device):
+            if k >= self.depth:
+                self._wait_word(cs, self.words[1], dst, k - self.depth + 1)          # dst has released this sender's message k - depth
+            self._copy(cs, self.peer_bufs[dst][k % self.depth, self.rank].view(-1)[:local.numel()], local.view(-1))
+            self._copy(cs, self.peer_words[dst][0, self.rank:self.rank + 1], self.ticks[k + 1:k + 2])
+
+    def wait_from(self, k, src):
+        """the current stream waits until message k of rank `src` has landed in bufs[k % depth, src]"""
+        with self.torch.cuda.device(self.device):
+            self._wait_word(self.torch.cuda.current_stream(self.device), self.words[0], src, k + 1)
+        return self.bufs[k % self.depth, src]
+
+    def release_to(self, k, src):
+        """the reads of message k of rank `src` have been queued on the current stream: `src` may overwrite that mailbox"""
+        torch = self.torch
+        cs = self.credit_stream
+        cs.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.device(self.device):
+            self._copy(cs, self.peer_words[src][1, self.rank:self.rank + 1], self.ticks[k + 1:k + 2])
+
     def wait(self, k):
         """[world, *shape] of step k; the current stream waits (on the device) until every rank's shard has landed."""
         torch = self.torch
