@@ -162,6 +162,43 @@ def main(args, reference=False):
         sync_all(); t_1 = (time.perf_counter() - t0) * 1e3
         bands = {"vpp_rnd_one_frame_banded_ms": t_b, "vpp_rnd_one_frame_single_gpu_ms": t_1,
                  "note": "exact (tests/test_gpu_bands.py); the gather of the bands costs more than the 5 % hint projection saves at this size"}
+    # one frame's aggregation split into one row band per rank (vppstereo_b200.banded: exact, the row state of the vertical sweeps
+    # travels over NVLink): latency of a single frame, and frames per second when consecutive frames are in flight on alternating
+    # streams -- against the unsplit compute_rsgm of one frame at a time on one GPU
+    banded = None
+    if world > 1:
+        from vppstereo_b200.banded import BandedRsgmDist
+        pb = synth.make_pair(7, shape="M", hints="random")             # the SAME frame on every rank (the batch above is per rank)
+        l1, r1, g1 = (torch.from_numpy(pb[k_])[None].to(dev) for k_ in ("left", "right", "hints"))
+        lv1, rv1 = vpp_standalone.vpp(l1[0], r1[0], g1[0], wsize=3, wsizeAgg_x=64, wsizeAgg_y=3, blending=0.4, method="maxDistance")
+        lanes = [BandedRsgmDist(H, W, C, dmax=D, device=dev) for _ in range(3)]
+        streams = [torch.cuda.Stream(dev) for _ in lanes]
+        ref = rsgm.compute_rsgm(l1[0], lv1, rv1, dmax=D)
+        got = lanes[0].compute(l1[0], lv1, rv1)
+        same = bool((got.view(torch.int32) == ref.view(torch.int32)).all())
+        def t_loop(fn, n):
+            sync_all(); t0 = time.perf_counter()
+            for k in range(n):
+                fn(k)
+            sync_all(); return (time.perf_counter() - t0) * 1e3 / n
+        def banded_sync(k):
+            lanes[0].compute(l1[0], lv1, rv1); torch.cuda.synchronize(dev)
+        def banded_pipe(k):
+            with torch.cuda.stream(streams[k % 3]):
+                lanes[k % 3].compute(l1[0], lv1, rv1)
+        def unsplit_sync(k):
+            rsgm.compute_rsgm(l1[0], lv1, rv1, dmax=D); torch.cuda.synchronize(dev)
+        def unsplit_stream(k):
+            rsgm.compute_rsgm(l1[0], lv1, rv1, dmax=D)
+        banded_sync(0); banded_pipe(0); banded_pipe(1); banded_pipe(2); unsplit_sync(0)
+        banded = {"bit_exact_vs_unsplit": same, "bands": lanes[0].bands,
+                  "volume_bytes_per_gpu": int(lanes[0].band[1] * lanes[0].vol_row_bytes * 3), "volume_bytes_unsplit": int(lanes[0].Hp * lanes[0].vol_row_bytes * 3),
+                  "row_state_bytes": int(lanes[0].state_words * 4),
+                  "latency_ms_banded": t_loop(banded_sync, 10), "latency_ms_unsplit_one_gpu": t_loop(unsplit_sync, 10),
+                  "ms_per_frame_banded_3_in_flight": t_loop(banded_pipe, 30), "ms_per_frame_unsplit_one_gpu_stream": t_loop(unsplit_stream, 30),
+                  "note": "compute_rsgm only (the projection is per frame, not banded); frames of a stream shard by frame instead (`value`)"}
+        for b_ in lanes:
+            b_.close()
     pg = pg_save
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -193,7 +230,7 @@ def main(args, reference=False):
                        "batch_per_gpu": B, "frames_per_step": world * B,
                        "stage_ms_per_batch": {k: round(v, 2) for k, v in stage_ms.items()},
                        "single_frame_latency_ms": {k: round(v, 2) for k, v in lat_ms.items()},
-                       "max_dist_channels": md_ms, "bands": bands,
+                       "max_dist_channels": md_ms, "bands": bands, "banded_rsgm": banded,
                        "collective": "none" if world == 1 else f"per step, copy-engine gather of the disparities (PeerGather available={pg.available})"},
             "roofline": {"bound": "hbm", "kernel": "compute_rsgm at M (the projection is bound by the hint dependency chain, not by bandwidth: DESIGN.md 4)",
                          "achieved": alg_rsgm / (stage_ms["rsgm"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
