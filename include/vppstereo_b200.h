@@ -43,9 +43,9 @@ const char *vppb200_version(void);
 /* name of the last failing CUDA call + cudaGetErrorString, thread-local; "" if none */
 const char *vppb200_last_cuda_error(void);
 /* Asynchronous failures of earlier launches on the current device that cannot be reported by the launching call: the
- * v-sweep's CTAs hand path state to each other through memory and wait for one another; a wait that times out (a CTA of the
- * cooperative grid not making progress) raises a device flag and lets the grid finish with undefined results instead of
- * trapping the context.  Returns VPPB200_OK, or VPPB200_ERR_CUDA once per incident (flag cleared).  Synchronises the device. */
+ * v-sweep's CTAs hand path state to each other through memory and wait for one another, and so do the rows of the maxDistance
+ * wavefront; a wait that times out (a CTA of the cooperative grid not making progress) raises a device flag and lets the grid
+ * finish with undefined results instead of trapping the context.  Returns VPPB200_OK, or VPPB200_ERR_CUDA once per incident (flag cleared).  Synchronises the device. */
 int vppb200_async_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t vppb200_launch_count(void);

@@ -277,9 +277,15 @@ extern "C" int vppb200_stage_times(float *ms_out, int *calls_out)
 
 extern "C" int vppb200_async_error(void)
 {
-    int hit = 0;
+    int hit = 0, hit_md = 0;
     int rc = sweep_take_abort_flag(&hit);
     if (rc) return rc;
+    if ((rc = vpp_take_md_abort_flag(&hit_md))) return rc;
+    if (hit_md) {
+        snprintf(g_err, sizeof g_err, "vpp_max_dist_wave_kernel: a dependency wait of the row wavefront timed out (results of the affected "
+                                      "calls are undefined)");
+        return VPPB200_ERR_CUDA;
+    }
     if (hit) {
         snprintf(g_err, sizeof g_err, "sgm_v2_kernel: a hand-off wait between the CTAs of a team timed out (results of the affected "
                                       "calls are undefined); were all CTAs of the cooperative grid resident?");

@@ -77,6 +77,7 @@ void sweep_set_enabled(int on);
 void sweep_set_clusters(int c);
 void vpp_set_rows_kernel(int on);
 void vpp_set_md_wave(int on);
+int vpp_take_md_abort_flag(int *out);
 int launch_wta_both_subpix(const uint16_t *S, float *dl, float *dr, int W, int H, int D, const float *lut, int plane, int n,
                            cudaStream_t st);
 int launch_wta_left(const uint16_t *S, float *disp, int W, int H, int D, int n, cudaStream_t st);

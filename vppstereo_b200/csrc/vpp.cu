@@ -922,14 +922,20 @@ __device__ __forceinline__ int md_ld_acquire(const int *p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// long dependency wait (the rows far ahead of the wavefront): bounded, so a protocol error traps instead of hanging the device
+// Raised by a dependency wait of the maxDistance wavefront that timed out (a protocol error, or the device so oversubscribed
+// that the rows ahead made no progress for a minute).  The scan then continues with undefined results instead of trapping the
+// context; the host reads the flag with vppb200_async_error().
+__device__ unsigned int g_md_abort = 0;
+
+// long dependency wait (the rows far ahead of the wavefront): bounded, so a protocol error cannot hang the device
 __device__ __noinline__ void md_long_wait(const int *p, int need)
 {
     for (unsigned spins = 0; spins < (1u << 26); spins++) {
         if (!__any_sync(0xFFFFFFFFu, need != 0 && md_ld_acquire(p) < need)) return;
+        if ((spins & 1023u) == 1023u && *(volatile unsigned int *)&g_md_abort != 0u) return;
         __nanosleep(1024u);
     }
-    __trap();
+    g_md_abort = 1u;
 }
 __device__ __forceinline__ void md_st_release(int *p, int v)
 {
@@ -1110,6 +1116,15 @@ static int prepare_hints(const float *g, int W, int H, int n_patch, int directio
 static int g_vpp_rows_on = 1;       // test hook: 0 = ordered per-row replay only
 void vpp_set_rows_kernel(int on) { g_vpp_rows_on = on != 0; }
 static int g_vpp_md_wave = 1;       // test hook: 0 = maxDistance by the serial one-warp-per-(frame, channel) kernel only
+int vpp_take_md_abort_flag(int *out)
+{
+    unsigned int v = 0, zero = 0;
+    VPP_CUDA_TRY(cudaMemcpyFromSymbol(&v, g_md_abort, sizeof v));
+    if (v) VPP_CUDA_TRY(cudaMemcpyToSymbol(g_md_abort, &zero, sizeof zero));
+    *out = v != 0;
+    return VPPB200_OK;
+}
+
 void vpp_set_md_wave(int on) { g_vpp_md_wave = on < 0 ? 0 : on; }   // > 1: rows in flight per SM (experiments)
 
 static VppArgs make_args(int W, int H, int C, int uniform, int wsize, int wax, int way, int direction, double c, double c_occ,
