@@ -378,7 +378,8 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     uint32_t ba[NW], bb[NW];
 #pragma unroll
     for (int k = 0; k < NW; k++) { ba[k] = 0xFFFFFFFFu; bb[k] = 0xFFFFFFFFu; }
-    int step = 0, ring = 0;
+    int step = 0;
+    uint32_t carry = 0;
     for (int q = 0; q < nchunks; q++) {
         cp_async_wait<1>();
         __syncwarp();
@@ -399,12 +400,10 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             }
         }
 
-        // per-warp scratch behind the stages: final S of the current and of the previous pixel (sub-pixel lookups); a ring
-        // of three buffers, so the buffer written at step s+1 is not one a slower lane still reads at step s
-        uint32_t *scr = reinterpret_cast<uint32_t *>(hsm + (size_t)HWARPS * 2 * stage_b) + warp * 3 * K2;
-        // the chunk's 8 + 8 results (uniform across the warp) are parked in shared memory by lane 0: two LSU stores per pixel
-        // instead of two compare + select pairs on the integer pipe
-        float *wout = reinterpret_cast<float *>(hsm + (size_t)HWARPS * 2 * stage_b + (size_t)HWARPS * 3 * K2 * 4) + warp * 16;
+        // WTA: the chunk's 8 left minima (cost << 16 | d) and 8 retired right winners are parked in shared memory (uniform values,
+        // one store each); the sub-pixel step is deferred to the end of the chunk, where the final S of all 8 pixels sits in the
+        // stage buffer and lanes 0..7 finish one pixel each
+        uint32_t *wout = reinterpret_cast<uint32_t *>(hsm + (size_t)HWARPS * 2 * stage_b) + warp * 16;
         const bool nomask = xlo >= D - 1;             // every d <= x in this chunk: the left arg-min needs no range mask
 #pragma unroll
         for (int pp = 0; pp < 8; pp++, step++) {
@@ -456,37 +455,13 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                     }
                 }
                 m = __reduce_min_sync(0xFFFFFFFFu, m);
-                const int best = (int)(m & 0xFFFFu);
-                float o = (float)best;
-                // final S of this pixel -> scratch (the previous buffer of the ring still holds pixel x+1); disparity d sits in
-                // half d / K2 of word d % K2
-                uint32_t *sc = scr + ring * K2;
-                const uint32_t *sc_prev = scr + (ring == 0 ? 2 : ring - 1) * K2;
-                ring = ring == 2 ? 0 : ring + 1;
-#pragma unroll
-                for (int j = 0; j < NW; j++) if (wv[j]) sc[NW * lane + j] = fin[j];
-                __syncwarp();
-                if (x >= 1 && x <= W - 2) {
-                    if (best > 0) {
-                        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(sc);
-                        auto at = [&](int d) -> int { return d < K2 ? s16[2 * d] : s16[2 * (d - K2) + 1]; };
-                        const int c0 = at(best - 1), c1 = (int)(m >> 16);
-                        // best = D-1 reads the next pixel's d = 0 (xyd stream order)
-                        const int c2 = best + 1 < D ? at(best + 1) : reinterpret_cast<const uint16_t *>(sc_prev)[0];
-                        const int lower = min(c1 - c0, c1 - c2);            // <= 0
-                        o = __fadd_rn((float)best, __fmul_rn((float)(c2 - c0), lut[-lower]));
-                    } else {
-                        o = -10.0f;
-                    }
-                }
-                if (lane == 0) wout[p] = o;
+                wout[p] = m;
                 // right: every in-flight target absorbs its disparity slot, slot d = 0 retires to disp_r[x], the conveyor moves
                 // one disparity down: within the halves by register moves, between lanes by a rotating shuffle (lane 31
                 // receives lane 0's slots: its low-half tail takes d = K2 from there, its high-half tail starts empty)
 #pragma unroll
                 for (int k = 0; k < NW; k++) { ba[k] = min(ba[k], ka[k]); bb[k] = min(bb[k], kb[k]); }
-                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, ba[0], 0);
-                if (lane == 0) wout[8 + p] = (float)(b0 & 0xFFFFu);
+                if (lane == 0) wout[8 + p] = ba[0];
                 const uint32_t fa = __shfl_sync(0xFFFFFFFFu, ba[0], (lane + 1) & 31);
                 const uint32_t fb = __shfl_sync(0xFFFFFFFFu, bb[0], (lane + 1) & 31);
 #pragma unroll
@@ -510,11 +485,40 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             }
         }
         if (WTA) {
+            // final S of the chunk's 8 pixels -> the (consumed) S rows of the stage; disparity d of pixel p sits in half d / K2 of
+            // column p of row d % K2
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                if (wv[j]) {
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW) = s0[j];
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW + 16) = s1[j];
+                }
+            }
             __syncwarp();
             if (lane < 8) {
-                disp_l[row * W + xlo + lane] = wout[lane];
-                disp_r[row * W + xlo + lane] = wout[8 + lane];
+                const int x = xlo + lane;
+                const uint32_t m = wout[lane];
+                const int best = (int)(m & 0xFFFFu);
+                float o = (float)best;
+                if (x >= 1 && x <= W - 2) {
+                    if (best > 0) {
+                        auto at = [&](int d) -> int {
+                            return *reinterpret_cast<const uint16_t *>(ssb + (d < K2 ? d : d - K2) * HSROW + lane * 4 + (d < K2 ? 0 : 2));
+                        };
+                        const int c0 = at(best - 1), c1 = (int)(m >> 16);
+                        // best = D-1 reads the next pixel's d = 0 (xyd stream order): column x+1, in the previous chunk for lane 7
+                        const int c2 = best + 1 < D ? at(best + 1)
+                                                    : (lane < 7 ? (int)*reinterpret_cast<const uint16_t *>(ssb + (lane + 1) * 4) : (int)carry);
+                        const int lower = min(c1 - c0, c1 - c2);            // <= 0
+                        o = __fadd_rn((float)best, __fmul_rn((float)(c2 - c0), lut[-lower]));
+                    } else {
+                        o = -10.0f;
+                    }
+                }
+                disp_l[row * W + x] = o;
+                disp_r[row * W + x] = (float)(wout[8 + lane] & 0xFFFFu);
             }
+            carry = __shfl_sync(0xFFFFFFFFu, s0[0].x, 0) & 0xFFFFu;         // S(d = 0) of the chunk's first column
         } else {
 #pragma unroll
             for (int j = 0; j < NW; j++) {
@@ -545,7 +549,7 @@ static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const 
     const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
     const size_t stage = h_stage_bytes(t.K2);
-    const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * (3 * t.K2 + 16) * 4 : 0);
+    const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * 16 * 4 : 0);
     auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, true> : sgm_h_kernel<NW, MODE, DIR, false>;
     if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, HWARPS * 32, smem, st>>>(img, cost, S, t, rows, dl, dr, lut);
