@@ -790,7 +790,9 @@ __device__ __forceinline__ void v2_block(const uint32_t (&cb)[VU], const uint32_
 // Register cap: 96 where the S update is a reduction (no operand registers for S; no spills): the one-CTA-per-SM grid then
 // leaves a quarter of the register file and ~30 KB of shared memory per SM to the front / tail kernels of the neighbouring
 // batches, which run beside the sweep (measured: the sweep alone 6.09 -> 6.39 ms, the pipelined step 23.7 -> 23.3 ms)
-template <int NS, bool FULL, bool NORM, bool RED>
+// BAND: the launch covers a row band of taller frames (state import / export at the band's ends); whole-frame launches are
+// compiled without that code (it costs the hot loop 0.3 ms per launch under the register cap).
+template <int NS, bool FULL, bool NORM, bool RED, bool BAND>
 __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__restrict__ p2q_all,
                                                                                  const uint16_t *__restrict__ cost_all,
                                                                                  uint32_t *__restrict__ S_all, uint32_t *halo,
@@ -909,7 +911,7 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
                 }
             }
         };
-        const bool cont = !a.pass_start;            // row band that continues a sweep: its first row is an ordinary row
+        const bool cont = BAND && !a.pass_start;    // row band that continues a sweep: its first row is an ordinary row
         if (f == cid) load_block(cost_f + (((long)i1 * G + g) * K2 + k0) * 32, S_f + (((long)i1 * G + g) * K2 + k0) * 32, k1 - k0, cb, sb, cont);
         for (int s = 0; s < H; s++, t++) {
             const int i = i1 + s * di;
@@ -948,7 +950,7 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
                     group_barrier();
                 }
             }
-            if (s == 0 && cont) {
+            if (BAND && s == 0 && cont) {
                 // ---- row band that continues a sweep: the predecessors of this row come from the state another band's sweep
                 // exported (columns x - dj, x, x + dj of the row before the band), straight into the ring slots this row reads
                 const uint32_t *imp = a.state_in + (long)f * a.state_words;
@@ -1053,7 +1055,7 @@ __global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__rest
             mn[(0 * VPARTS + part) * NS + d1] = mr1;
             mn[(1 * VPARTS + part) * NS + d2] = mr2;
             mn[(2 * VPARTS + part) * NS + d3] = mr3;
-            if (s == H - 1 && a.state_out != nullptr) {
+            if (BAND && s == H - 1 && a.state_out != nullptr) {
                 // ---- last row of a band: this column's new state of the three paths for the band that continues the sweep
                 uint32_t *ex = a.state_out + (long)f * a.state_words;
                 uint32_t *exm = ex + (long)3 * G32 * K2;
@@ -1132,8 +1134,8 @@ static int v_resident_ctas(size_t smem, int threads, int *out)
     VPP_CUDA_TRY(cudaGetDevice(&dev));
     VPP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     constexpr int NS = GC * 32 + 1;
-    VPP_CUDA_TRY(cudaFuncSetAttribute(sgm_v2_kernel<NS, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VPP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgm_v2_kernel<NS, true, false, false>, threads, smem));
+    VPP_CUDA_TRY(cudaFuncSetAttribute(sgm_v2_kernel<NS, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VPP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgm_v2_kernel<NS, true, false, false, true>, threads, smem));
     // One CTA per SM.  (Measured: two CTAs of different frames per SM on 64-column strips take 3.83 us per row for their 4
     // column groups, one CTA with 5 groups 3.97 us -- the row time is a latency chain, wait -> hand-off -> setup -> loop ->
     // push, that does not shrink with the strip, so the widest strip that fits wins.)
@@ -1233,11 +1235,14 @@ static int run_v_t(const uint32_t *p2q, const uint16_t *cost, uint32_t *S, uint3
     // FULL: K2 splits into VPARTS equal shares of whole VU-blocks
     const bool full = t.K2 % (VPARTS * VU) == 0;
     void *args[] = {(void *)&p2q, (void *)&cost, (void *)&S, (void *)&halo, (void *)&abort_flag, (void *)&a};
+    const bool banded = !band.pass_start || band.state_in != nullptr || band.state_out != nullptr;
     const void *kern;
-    if (norm && g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, true, true> : (const void *)sgm_v2_kernel<NS, false, true, true>;
-    else if (norm) kern = full ? (const void *)sgm_v2_kernel<NS, true, true, false> : (const void *)sgm_v2_kernel<NS, false, true, false>;
-    else if (g_v_red) kern = full ? (const void *)sgm_v2_kernel<NS, true, false, true> : (const void *)sgm_v2_kernel<NS, false, false, true>;
-    else kern = full ? (const void *)sgm_v2_kernel<NS, true, false, false> : (const void *)sgm_v2_kernel<NS, false, false, false>;
+#define VPP_VK(F, N, R) (banded ? (const void *)sgm_v2_kernel<NS, F, N, R, true> : (const void *)sgm_v2_kernel<NS, F, N, R, false>)
+    if (norm && g_v_red) kern = full ? VPP_VK(true, true, true) : VPP_VK(false, true, true);
+    else if (norm) kern = full ? VPP_VK(true, true, false) : VPP_VK(false, true, false);
+    else if (g_v_red) kern = full ? VPP_VK(true, false, true) : VPP_VK(false, false, true);
+    else kern = full ? VPP_VK(true, false, false) : VPP_VK(false, false, false);
+#undef VPP_VK
     VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     // cooperative launch: all CTAs resident (they poll each other's halo words), one grid sync at the start
     VPP_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3((unsigned)(p.csize * p.nteams)), dim3((unsigned)(p.GC * VPARTS * 32)), args,
