@@ -593,6 +593,9 @@ struct VArgs {
     long state_words;
 };
 
+#ifndef VPP_VREGS
+#define VPP_VREGS 96
+#endif
 #ifndef VPP_VPARTS
 #define VPP_VPARTS 3
 #endif
@@ -793,7 +796,7 @@ __device__ __forceinline__ void v2_block(const uint32_t (&cb)[VU], const uint32_
 // BAND: the launch covers a row band of taller frames (state import / export at the band's ends); whole-frame launches are
 // compiled without that code (it costs the hot loop 0.3 ms per launch under the register cap).
 template <int NS, bool FULL, bool NORM, bool RED, bool BAND>
-__global__ void __maxnreg__(RED ? 96 : 128) sgm_v2_kernel(const uint32_t *__restrict__ p2q_all,
+__global__ void __maxnreg__(RED ? VPP_VREGS : 128) sgm_v2_kernel(const uint32_t *__restrict__ p2q_all,
                                                                                  const uint16_t *__restrict__ cost_all,
                                                                                  uint32_t *__restrict__ S_all, uint32_t *halo,
                                                                                  uint32_t *abort_flag, VArgs a)
