@@ -883,7 +883,8 @@ __global__ void __maxnreg__(RED ? VPP_VREGS : 128) sgm_v2_kernel(const uint32_t 
     };
     // (Measured alternatives, all slower than this loop's 6.11 ms per launch: three blocking try_waits one after the other 6.43 ms;
     // one barrier per group that collects the arrivals of all the warps the group depends on, polled alone, 6.34 ms with
-    // try_wait, 6.48 ms with test_wait, 6.41-6.9 ms with test_wait + nanosleep 30 / 100 / 300.  Here a try_wait on a phase
+    // try_wait, 6.48 ms with test_wait, 6.41-6.9 ms with test_wait + nanosleep 30 / 100 / 300.  A suspend-time hint on the try_wait (2 us, 10 ms)
+    // takes the polling instructions away but not the wait: 6.20 vs 6.09 ms, same step time.  Here a try_wait on a phase
     // that is already complete returns at once, so the loop polls the pending ones ~20 times per row: fast wake-up without a
     // tight spin that would starve the lower-priority working warps.)
     auto wait_rows = [&](unsigned tt) {              // every warp of this group and of its ring neighbours has completed row tt
