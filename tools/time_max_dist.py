@@ -28,6 +28,16 @@ def run(shape, N, wave, reps):
     return lt, rt
 
 if __name__ == "__main__":
+    if "--k64" in sys.argv:
+        run("K", 64, 1, 1)
+        sys.exit(0)
+    if "--scale" in sys.argv:
+        for nb in (24, 48, 72):
+            run("M", nb, 1, 1)
+        sys.exit(0)
+    if "--batch" in sys.argv:
+        run("M", 1, 1, 2); run("M", 12, 1, 2); run("K", 64, 1, 3); run("V", 1, 1, 3)
+        sys.exit(0)
     a = run("M", 1, 1, 3)
     if "--serial" in sys.argv:
         b = run("M", 1, 0, 1)

@@ -802,7 +802,39 @@ __device__ __forceinline__ double md_colour_region(const VppArgs &a, const MdReg
     const int W = a.W, H = a.H, wx = 2 * a.nax + 1;
     const bool count_all = !(a.arith == 0 && uniform_branch);
     int pa = 0, pb = 255, zeros = 0;
-    {
+    // one reduction step of the fold: the first pending sample (in window order) that lies strictly inside (pa, pb) moves a bound
+    auto fold = [&](int vl, int vr, int keyl, int keyr) {
+        int done = -1;
+        while (true) {
+            const bool pl = vl > pa && vl < pb && keyl > done;
+            const bool pr = vr > pa && vr < pb && keyr > done;
+            const unsigned key = pl ? (unsigned)keyl : (pr ? (unsigned)keyr : 0xFFFFFFFFu);
+            const unsigned m = __reduce_min_sync(0xFFFFFFFFu, key);
+            if (m == 0xFFFFFFFFu) break;
+            const int v = (int)(m & 255u);
+            done = (int)m;
+            if (v - pa > pb - v) pb = v;
+            else if (v - pa < pb - v) pa = v;
+        }
+    };
+    if (wx <= 64) {
+        // windows of up to 64 columns (the default 64 x 3): the two 32-column halves' validity does not depend on the row and is
+        // worked out once per window; the four samples of a row are fetched together
+        const int xa = cx - a.nax + lane, xb = xa + 32;
+        const bool ina = lane < wx && xa >= 0 && xa <= W - 1, inb = lane + 32 < wx && xb >= 0 && xb <= W - 1;
+        const bool hra = ina && xa - shift >= 0 && xa - shift <= W - 1, hrb = inb && xb - shift >= 0 && xb - shift <= W - 1;
+        const bool hla = ina && (!occ || !hra), hlb = inb && (!occ || !hrb);
+        const int kla = (2 * lane) << 8, kra = kla + 256, klb = (2 * lane + 64) << 8, krb = klb + 256;
+        const uint8_t *pl0 = src.sL + (max(cy - a.nay, 0) - src.oy) * src.RW + (cx - a.nax - src.ox) + lane;
+        const uint8_t *pr0 = src.sR + (pl0 - src.sL);
+        for (int yy = max(cy - a.nay, 0); yy <= min(cy + a.nay, H - 1); yy++, pl0 += src.RW, pr0 += src.RW) {
+            const int vla = hla ? (int)pl0[0] : -1, vra = hra ? (int)pr0[0] : -1;
+            const int vlb = hlb ? (int)pl0[32] : -1, vrb = hrb ? (int)pr0[32] : -1;
+            zeros += (vla == 0) + (vra == 0) + (vlb == 0) + (vrb == 0);
+            fold(vla, vra, kla | (vla & 255), kra | (vra & 255));
+            if (wx > 32) fold(vlb, vrb, klb | (vlb & 255), krb | (vrb & 255));
+        }
+    } else {
         const int keyl0 = (2 * lane) << 8, keyr0 = (2 * lane + 1) << 8;
         for (int yy = max(cy - a.nay, 0); yy <= min(cy + a.nay, H - 1); yy++) {
             const int base = (yy - src.oy) * src.RW + (cx - a.nax - src.ox);
@@ -814,19 +846,7 @@ __device__ __forceinline__ double md_colour_region(const VppArgs &a, const MdReg
                 const int vl = has_l ? (int)src.sL[base + dx] : -1;
                 const int vr = has_r ? (int)src.sR[base + dx] : -1;
                 zeros += (vl == 0) + (vr == 0);
-                const int keyl = keyl0 | (vl & 255), keyr = keyr0 | (vr & 255);
-                int done = -1;
-                while (true) {
-                    const bool pl = vl > pa && vl < pb && keyl > done;
-                    const bool pr = vr > pa && vr < pb && keyr > done;
-                    const unsigned key = pl ? (unsigned)keyl : (pr ? (unsigned)keyr : 0xFFFFFFFFu);
-                    const unsigned m = __reduce_min_sync(0xFFFFFFFFu, key);
-                    if (m == 0xFFFFFFFFu) break;
-                    const int v = (int)(m & 255u);
-                    done = (int)m;
-                    if (v - pa > pb - v) pb = v;
-                    else if (v - pa < pb - v) pa = v;
-                }
+                fold(vl, vr, keyl0 | (vl & 255), keyr0 | (vr & 255));
             }
         }
     }
@@ -931,7 +951,8 @@ __device__ unsigned int g_md_abort = 0;
 __device__ __noinline__ void md_long_wait(const int *p, int need)
 {
     for (unsigned spins = 0; spins < (1u << 26); spins++) {
-        if (!__any_sync(0xFFFFFFFFu, need != 0 && md_ld_acquire(p) < need)) return;
+        const int got = md_ld_acquire(p);           // every lane polls its own (always valid) word: no divergence in the loop
+        if (!__any_sync(0xFFFFFFFFu, got < need)) return;
         if ((spins & 1023u) == 1023u && *(volatile unsigned int *)&g_md_abort != 0u) return;
         __nanosleep(1024u);
     }
@@ -966,7 +987,10 @@ struct MdSplat {
     }
 };
 
-__global__ void __launch_bounds__(32) vpp_max_dist_wave_kernel(uint8_t *l, uint8_t *r, const float *__restrict__ g,
+#ifndef VPP_MD_MINB
+#define VPP_MD_MINB 12
+#endif
+__global__ void __launch_bounds__(32, VPP_MD_MINB) vpp_max_dist_wave_kernel(uint8_t *l, uint8_t *r, const float *__restrict__ g,
                                                                const uint8_t *__restrict__ g_occ, VppWs ws, MdWs md, VppArgs a,
                                                                int units, int RD)
 {
@@ -1018,7 +1042,7 @@ __global__ void __launch_bounds__(32) vpp_max_dist_wave_kernel(uint8_t *l, uint8
             // wait for the hints of the rows above that interact with this one
             {
                 unsigned ns = 32;
-                while (__any_sync(0xFFFFFFFFu, need != 0 && md_ld_acquire(mydep) < need)) {
+                while (__any_sync(0xFFFFFFFFu, md_ld_acquire(mydep) < need)) {       // need == 0: no dependency (progress >= 0)
                     if (ns > 1024u) { md_long_wait(mydep, need); break; }      // (kept out of line: the short waits are the hot path)
                     __nanosleep(ns);
                     ns *= 2;
