@@ -81,10 +81,11 @@ def main(args, reference=False):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # frames per rank and step.  The projection is bound by the depth of its hint dependency chain (~0.28 s for one frame and
-    # for eight alike), so a step projects all B frames in one call; the matcher then runs in chunks of CHUNK frames
+    # frames per rank and step.  The projection is bound by the depth of its hint dependency chain (~0.27 s for one frame and
+    # 0.30 s for twelve; 24 / 48 / 72 frames: 0.39 / 0.58 / 0.77 s: the resident row warps saturate at ~8 ms per added frame), so
+    # a step projects all B frames in one call; the matcher then runs in chunks of CHUNK frames
     # (8 M frames = 8 teams of 18 SMs in the v-sweeps, ~8.5 GB of workspace each)
-    B = args.batch if args.batch != 64 else 24
+    B = args.batch if args.batch != 64 else 48
     CHUNK = 8
     steps = min(args.steps, 5) if args.steps != 200 else 3
     uniq = [synth.make_pair(rank * 100 + f, shape="M", hints="random") for f in range(2)]
