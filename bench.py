@@ -393,6 +393,8 @@ def main():
     pg = PeerGather((B, H, W), torch.float32, dev, depth=2) if world > 1 else None
     consumer = torch.cuda.Stream(dev) if world > 1 else None
     gstep = [0]
+    if os.environ.get("VPPB200_V_SPLIT", "1") == "0":         # experiment: single-plan v-sweeps
+        _lib.set_tuning(_lib.TUNE_SGM_V_SPLIT, 0)
     gmode = os.environ.get("VPPB200_GATHER", "p2p")           # experiments: none | nccl | p2p (default)
     if pg is not None and gmode == "nccl":
         pg.available, pg.why = False, "forced by VPPB200_GATHER=nccl"

@@ -180,6 +180,7 @@ def tuning(mods):
     _lib.set_tuning(_lib.TUNE_SGM_MAX_STRIP, 0)
     _lib.set_tuning(_lib.TUNE_SGM_SWEEP, 1)
     _lib.set_tuning(_lib.TUNE_SGM_V_RED, 1)
+    _lib.set_tuning(_lib.TUNE_SGM_V_SPLIT, 1)
 
 
 @pytest.mark.parametrize("strip", [32, 64, 100])
@@ -208,6 +209,23 @@ def test_sweep_cluster_strips(mods, orc, tuning, strip, shape, D, channels):
     st0 = rsgm.compute_rsgm_stages(left, left, right, dmax=D)
     assert_same(st["dsi_agg"], st0["dsi_agg"], f"aggregated volume, sweep strip={strip} vs per-path kernels")
     assert_same(st["out"], st0["out"], "sweep vs per-path kernels, final disparity")
+
+
+def test_sweep_split_launches(mods, orc, tuning):
+    """a batch that does not fill its last round of teams is swept in two launches with different strip widths (plan_v_split):
+    same result as the single-plan sweep, and as the oracle on the frames either side of the split"""
+    rsgm, synth, _lib = mods[1], mods[2], mods[3]
+    shape, D, n = (24, 200), 16, 90
+    frames = [synth.make_pair(500 + f, shape=shape, hints="random", channels=1) for f in range(n)]
+    left = np.stack([p["left"] for p in frames]); right = np.stack([p["right"] for p in frames])
+    got = rsgm.compute_rsgm(left, left, right, dmax=D)
+    tuning(_lib.TUNE_SGM_V_SPLIT, 0)
+    single = rsgm.compute_rsgm(left, left, right, dmax=D)
+    tuning(_lib.TUNE_SGM_V_SPLIT, 1)
+    assert_same(got, single, "split sweep vs single-plan sweep")
+    for f in (0, 73, 74, 89):
+        want = orc.compute_rsgm(frames[f]["left"], frames[f]["left"], frames[f]["right"], dmax=D)
+        assert_same(got[f], want, f"split sweep frame {f}")
 
 
 def test_compute_rsgm_random_shapes(mods, orc):

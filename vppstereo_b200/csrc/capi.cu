@@ -305,6 +305,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_SGM_BYTE_SUMS: return VPPB200_OK;      // options of round 1, removed (measured slower): accepted, no effect
         case VPPB200_TUNE_SGM_FUSE_COST: return VPPB200_OK;
         case VPPB200_TUNE_SGM_V_RED: sweep_set_v_red(value); return VPPB200_OK;
+        case VPPB200_TUNE_SGM_V_SPLIT: sweep_set_v_split(value); return VPPB200_OK;
         case VPPB200_TUNE_RCP_HOST: g_rcp_host.store(value != 0); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }

@@ -70,6 +70,7 @@ size_t sweep_halo_bytes(int W, int H, int D, int n);       // workspace of the v
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost, uint16_t *S, void *halo_ws, int W, int H, int D, int n, float *dl,
                           float *dr, const float *lut, bool plain_costs, const StageHook *hook, cudaStream_t st);
 void sweep_set_v_red(int on);
+void sweep_set_v_split(int on);
 int sweep_take_abort_flag(int *out);
 int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, int n, cudaStream_t st);
 void sweep_set_max_strip(int cols);

@@ -1210,6 +1210,65 @@ static int plan_v(const TL &t, int n, VPlan *plan)
     return VPPB200_OK;
 }
 
+// A batch whose last round would leave most teams idle is swept in two launches: the first rounds with the widest strips, the
+// rest with narrower strips and more CTAs per frame -- the row time falls with the strip width (measured at K, us per row: 3.97 /
+// 3.67 / 3.50 / 3.40 for 5 / 4 / 3 / 2 column groups per CTA), so e.g. 64 K frames run as 36 frames x 8 CTAs (two rounds of 18
+// teams) + 28 frames x 10 CTAs (two rounds of 14 teams) instead of four rounds of 18 teams with the last one 10 / 18 full.
+struct VSplit { int n1; VPlan p1; int n2; VPlan p2; };
+static int g_v_split = 1;
+void sweep_set_v_split(int on) { g_v_split = on != 0; }
+static int plan_v_split(const TL &t, int n, VSplit *out)
+{
+    static thread_local struct { int W, H, D, n, dev, strip, teams, split; VSplit s; bool ok; } memo = {0, 0, 0, 0, -1, 0, 0, 0, {}, false};
+    int dev = 0;
+    VPP_CUDA_TRY(cudaGetDevice(&dev));
+    if (memo.ok && memo.W == t.W && memo.H == t.H && memo.D == t.D && memo.n == n && memo.dev == dev && memo.strip == g_max_strip &&
+        memo.teams == g_force_teams && memo.split == g_v_split) {
+        *out = memo.s;
+        return VPPB200_OK;
+    }
+    VSplit best{};
+    int rc = plan_v(t, n, &best.p1);
+    if (rc) return rc;
+    best.n1 = n; best.n2 = 0;
+    if (g_v_split && g_max_strip == 0 && g_force_teams == 0 && n > best.p1.nteams) {
+        static const double trow[6] = {0.0, 3.30, 3.40, 3.50, 3.67, 3.97};      // relative row time by groups per CTA
+        const int gc_max = best.p1.GC;
+        VPlan cand[6];
+        bool have[6] = {false, false, false, false, false, false};
+        for (int gc = 1; gc <= gc_max; gc++) {
+            VPlan q;
+            q.GC = gc; q.csize = (t.G + gc - 1) / gc; q.smem = v_smem_bytes(gc, t.K2);
+            int resident = 0;
+            if ((rc = v_resident(gc, q.smem, &resident))) return rc;
+            q.nteams = resident / q.csize;
+            if (q.nteams < 1) continue;
+            cand[gc] = q; have[gc] = true;
+        }
+        auto rounds = [](int m, int teams) { return (m + teams - 1) / teams; };
+        double best_cost = rounds(n, best.p1.nteams) * trow[best.p1.GC];
+        const double launch = 0.05;                      // a second cooperative launch + P2 table, in the same units
+        for (int a = 1; a <= gc_max; a++) {
+            if (!have[a]) continue;
+            for (int r1 = 1; r1 * cand[a].nteams < n; r1++) {
+                const int n1 = r1 * cand[a].nteams, n2 = n - n1;
+                for (int b = 1; b <= gc_max; b++) {
+                    if (!have[b] || b == a) continue;
+                    const double c = r1 * trow[a] + rounds(n2, cand[b].nteams) * trow[b] + launch;
+                    if (c < best_cost - 1e-9) {
+                        best_cost = c;
+                        best.n1 = n1; best.p1 = cand[a]; best.p1.nteams = std::min(cand[a].nteams, n1);
+                        best.n2 = n2; best.p2 = cand[b]; best.p2.nteams = std::min(cand[b].nteams, n2);
+                    }
+                }
+            }
+        }
+    }
+    *out = best;
+    memo = {t.W, t.H, t.D, n, dev, g_max_strip, g_force_teams, g_v_split, best, true};
+    return VPPB200_OK;
+}
+
 // the v-sweep's scratch behind the inbound halo lines: [abort flag (256 B)] [P2 table: n * H * G * 32 words]
 static constexpr size_t HALO_LINES_BYTES = (size_t)1024 * 2 * 2 * (128 + 8) * 4;     // generously 1024 CTAs, D <= 256
 size_t sweep_halo_bytes(int W, int H, int D, int n)
@@ -1307,23 +1366,34 @@ bool aggregate_tile_supported(int W, int H, int D, int n)
 // (Two variants of round 1 were measured again on this kernel generation and removed: uint8 partial-sum volumes instead of one
 // uint16 S -- 37 % less traffic, but the extra unpacking in the ALU-bound h-sweeps costs more than the v-sweeps gain, 25.4 vs
 // 25.1 ms per step -- and a forward h-sweep that produces the cost volume itself, 5.27 ms vs 3.56 + 1.47 ms.)
+// (Measured at the end of round 2 and removed: the forward h-sweep leaving its L as BYTE pairs -- <= 74 with Hamming costs -- and the
+// first v-sweep writing S = that + its paths with plain stores: 11.8 GB less traffic per step, but the h-sweep's 16-byte pieces
+// only bring it from 3.59 to 3.06 ms and the v-sweep with an operand load instead of the fire-and-forget reduction goes from 5.93 to
+// 6.78 ms: step 22.3 vs 22.0 ms.)
 int launch_aggregate_tile(const uint8_t *img, const uint8_t *cost8, uint16_t *S16, void *halo_ws, int W, int H, int D, int n,
                           float *dl, float *dr, const float *lut, bool plain_costs, const StageHook *hook, cudaStream_t st)
 {
     const TL t = make_tl(W, H, D);
-    VPlan plan;
-    int rc = plan_v(t, n, &plan);
+    VSplit sp;
+    int rc = plan_v_split(t, n, &sp);
     if (rc) return rc;
     const uint16_t *cost = reinterpret_cast<const uint16_t *>(cost8);
     uint32_t *S = reinterpret_cast<uint32_t *>(S16);
     // un-normalised path state: Hamming costs only, and 24 per row must stay inside uint16
     const bool norm = !plain_costs || 24L * H + 128 > 65535;
     auto done = [&](int stage) { if (hook) hook->fn(hook->ctx, stage); };
+    auto sweep = [&](int pass) -> int {
+        int r = run_v(img, cost, S, halo_ws, t, pass, sp.n1, sp.p1, norm, st);
+        if (r == VPPB200_OK && sp.n2 > 0)
+            r = run_v(img + (long)sp.n1 * t.W * t.H, cost + (long)sp.n1 * t.frame, S + (long)sp.n1 * t.frame, halo_ws, t, pass, sp.n2,
+                      sp.p2, norm, st);
+        return r;
+    };
     if ((rc = run_h(img, cost, S, t, 0, n, nullptr, nullptr, nullptr, st))) return rc;
     done(VPPB200_STAGE_SGM_H_FWD);
-    if ((rc = run_v(img, cost, S, halo_ws, t, 0, n, plan, norm, st))) return rc;
+    if ((rc = sweep(0))) return rc;
     done(VPPB200_STAGE_SGM_V_DOWN);
-    if ((rc = run_v(img, cost, S, halo_ws, t, 1, n, plan, norm, st))) return rc;
+    if ((rc = sweep(1))) return rc;
     done(VPPB200_STAGE_SGM_V_UP);
     if ((rc = run_h(img, cost, S, t, dl ? 2 : 1, n, dl, dr, lut, st))) return rc;
     done(VPPB200_STAGE_SGM_H_BWD);
