@@ -393,6 +393,8 @@ def main():
     pg = PeerGather((B, H, W), torch.float32, dev, depth=2) if world > 1 else None
     consumer = torch.cuda.Stream(dev) if world > 1 else None
     gstep = [0]
+    if os.environ.get("VPPB200_CENSUS_FUSED", "1") == "0":    # experiment: pad_gray + census as two kernels
+        _lib.set_tuning(_lib.TUNE_CENSUS_FUSED, 0)
     if os.environ.get("VPPB200_V_SPLIT", "1") == "0":         # experiment: single-plan v-sweeps
         _lib.set_tuning(_lib.TUNE_SGM_V_SPLIT, 0)
     gmode = os.environ.get("VPPB200_GATHER", "p2p")           # experiments: none | nccl | p2p (default)
@@ -559,7 +561,8 @@ def main():
             # the other kernels of the step against the same peak, each on SURVEY.md 8(d)'s bytes for its row
             "roofline_aggregate_8_paths": roof(ALG_BYTES_AGG * B, agg_s * 1e3, "h_fwd + v_down + v_up + h_bwd(+WTA) vs SURVEY 8d aggregate bytes (4WHD+WH)"),
             "roofline_vpp": roof(vpp_bytes, vpp_ms, "VPP rnd: images in/out + hints + mask + pattern draws (SURVEY 8d)"),
-            "roofline_census": roof(2 * 5 * WP * HP * B, stage_ms["census"], "census 5x5 of both images: 1 byte in, 4 bytes out per pixel (SURVEY 8d)"),
+            "roofline_census": roof(2 * (H * W * C + 4 * WP * HP) * B, stage_ms["census"],
+                                    "pad + RGB2GRAY + census 5x5 of both images in one kernel each (TMA-staged row bands): the uint8 image in, 4 bytes out per padded pixel"),
             "roofline_cost_volume": roof((8 * WP * HP + WP * HP * D) * B, stage_ms["cost_volume"], "Hamming volume: two census images in, uint8 volume out"),
             "roofline_h_fwd": roof(3 * WP * HP * D * B, stage_ms["sgm_h_fwd"], "h-sweep fwd: uint8 costs in, uint16 S out"),
             "roofline_h_bwd_wta": roof((3 * WP * HP * D + 8 * WP * HP) * B, stage_ms["sgm_h_bwd_wta"], "h-sweep bwd + WTA: costs + S in, two disparity maps out"),

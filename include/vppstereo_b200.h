@@ -96,6 +96,7 @@ int vppb200_stage_times(float *ms_out, int *calls_out);
 #define VPPB200_TUNE_SGM_FUSE_COST 6  /* round-1 option (forward h-sweep producing the cost volume), measured slower and removed: accepted, no effect */
 #define VPPB200_TUNE_RCP_HOST 7       /* 0 = sub-pixel reciprocal from the fixed Intel RCPSS table (default), 1 = from the host CPU's RCPSS instruction */
 #define VPPB200_TUNE_SGM_V_RED 8      /* 1 = the v-sweeps add into S with red.global.add (no load of S; default), 0 = load + add + store */
+#define VPPB200_TUNE_CENSUS_FUSED 10  /* 1 = compute_rsgm's pad + gray + census run as one kernel per image (default), 0 = pad_gray then census */
 #define VPPB200_TUNE_SGM_V_SPLIT 9    /* 1 = a batch whose last round would leave teams idle is swept in two launches with different strip widths (default) */
 #define VPPB200_TUNE_SGM_BYTE_SUMS 4  /* round-1 option (uint8 partial-sum volumes), measured slower and removed: accepted, no effect */
 int vppb200_set_tuning(int key, int value);

@@ -181,6 +181,7 @@ def tuning(mods):
     _lib.set_tuning(_lib.TUNE_SGM_SWEEP, 1)
     _lib.set_tuning(_lib.TUNE_SGM_V_RED, 1)
     _lib.set_tuning(_lib.TUNE_SGM_V_SPLIT, 1)
+    _lib.set_tuning(_lib.TUNE_CENSUS_FUSED, 1)
 
 
 @pytest.mark.parametrize("strip", [32, 64, 100])
@@ -209,6 +210,24 @@ def test_sweep_cluster_strips(mods, orc, tuning, strip, shape, D, channels):
     st0 = rsgm.compute_rsgm_stages(left, left, right, dmax=D)
     assert_same(st["dsi_agg"], st0["dsi_agg"], f"aggregated volume, sweep strip={strip} vs per-path kernels")
     assert_same(st["out"], st0["out"], "sweep vs per-path kernels, final disparity")
+
+
+@pytest.mark.parametrize("shape,channels", [((37, 70), 3), ((5, 17), 1), ((64, 333), 3), ((23, 1242), 3), ((130, 64), 1)])
+def test_census_fused_front(mods, orc, tuning, shape, channels):
+    """pad + gray + census as one kernel per image (bulk-copied source window, gray band in shared memory) against the two-kernel
+    front and the oracle; frames 1.. of a batch start at addresses that are not 16-byte aligned"""
+    rsgm, synth, _lib = mods[1], mods[2], mods[3]
+    D = 32 if shape[1] >= 64 else 8
+    frames = [synth.make_pair(900 + f, shape=shape, hints="random", channels=channels) for f in range(3)]
+    left = np.stack([p["left"] for p in frames]); right = np.stack([p["right"] for p in frames])
+    got = rsgm.compute_rsgm(left, left, right, dmax=D)
+    tuning(_lib.TUNE_CENSUS_FUSED, 0)
+    two = rsgm.compute_rsgm(left, left, right, dmax=D)
+    tuning(_lib.TUNE_CENSUS_FUSED, 1)
+    assert_same(got, two, f"fused front vs pad_gray + census {shape} C={channels}")
+    for f in (0, 2):
+        want = orc.compute_rsgm(frames[f]["left"], frames[f]["left"], frames[f]["right"], dmax=D)
+        assert_same(got[f], want, f"fused front {shape} C={channels} frame {f}")
 
 
 def test_sweep_split_launches(mods, orc, tuning):

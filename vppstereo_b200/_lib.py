@@ -59,7 +59,7 @@ def lib():
 
 
 TUNE_SGM_MAX_STRIP, TUNE_SGM_SWEEP, TUNE_SGM_CLUSTERS, TUNE_VPP_ROWS, TUNE_SGM_BYTE_SUMS, TUNE_VPP_MD_WAVE, TUNE_SGM_FUSE_COST, TUNE_RCP_HOST, TUNE_SGM_V_RED = 0, 1, 2, 3, 4, 5, 6, 7, 8
-TUNE_SGM_V_SPLIT = 9
+TUNE_SGM_V_SPLIT, TUNE_CENSUS_FUSED = 9, 10
 
 
 _tuning = {}

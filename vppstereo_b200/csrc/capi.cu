@@ -306,6 +306,7 @@ extern "C" int vppb200_set_tuning(int key, int value)
         case VPPB200_TUNE_SGM_FUSE_COST: return VPPB200_OK;
         case VPPB200_TUNE_SGM_V_RED: sweep_set_v_red(value); return VPPB200_OK;
         case VPPB200_TUNE_SGM_V_SPLIT: sweep_set_v_split(value); return VPPB200_OK;
+        case VPPB200_TUNE_CENSUS_FUSED: census_set_fused(value); return VPPB200_OK;
         case VPPB200_TUNE_RCP_HOST: g_rcp_host.store(value != 0); return VPPB200_OK;
         default: return VPPB200_ERR_ARG;
     }
@@ -437,12 +438,19 @@ static int rsgm_phases(const uint8_t *left, const uint8_t *left_vpp, const uint8
         cudaStream_t side = side_stream(0);
         if (!side) side = st;                                // no side stream: everything in order on the caller's stream
         if (side != st && (rc = stream_chain(st, side))) return rc;
-        if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, side))) return rc;
-        if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, side))) return rc;
-        if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, n, st))) return rc;
+        // pad + gray + census in one kernel per image (the gray image stays in shared memory); two kernels where that does not apply
+        if ((rc = launch_census_fused(right_vpp, w.census_r, d, n, side)) < 0) return rc;
+        if (rc == 1) {
+            if ((rc = launch_pad_gray(right_vpp, w.gray_r, d, n, side))) return rc;
+            if ((rc = launch_census(w.gray_r, w.census_r, d.Wp, d.Hp, n, side))) return rc;
+        }
         if ((rc = launch_pad_flatbytes(left, w.guide, d, n, st))) return rc;
         tm.done(VPPB200_STAGE_PAD_GRAY);
-        if ((rc = launch_census(w.gray_l, w.census_l, d.Wp, d.Hp, n, st))) return rc;
+        if ((rc = launch_census_fused(left_vpp, w.census_l, d, n, st)) < 0) return rc;
+        if (rc == 1) {
+            if ((rc = launch_pad_gray(left_vpp, w.gray_l, d, n, st))) return rc;
+            if ((rc = launch_census(w.gray_l, w.census_l, d.Wp, d.Hp, n, st))) return rc;
+        }
         if (side != st && (rc = stream_chain(side, st))) return rc;
         tm.done(VPPB200_STAGE_CENSUS);
         // rsgm.py:263-268  Hamming volume (+ optional guided modulation)

@@ -177,6 +177,184 @@ __global__ void __launch_bounds__(256) census5x5_kernel(const uint8_t *__restric
     reinterpret_cast<uint4 *>(dst + f * n)[c0 / 4] = out;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// pad + RGB2GRAY + census5x5 in one kernel (the compute_rsgm front: rsgm.py:258-262 then FastFilters.cpp:181-442): the gray image
+// never goes to HBM.  One CTA = CB_ROWS rows of the padded frame.  The source rows the band needs (its rows +-3, mapped back through
+// BORDER_REFLECT: always one contiguous range of the interleaved uint8 image) arrive in shared memory as ONE bulk asynchronous
+// copy (TMA engine, cp.async.bulk + mbarrier complete_tx; 16-byte aligned window around the range); the CTA converts them into the
+// band's gray rows in shared memory (rows outside the frame = 0, which is what the flat-stream census reads there) and runs the
+// same 4-codes-per-thread census as census5x5_kernel out of it.  Band height: 8 rows (70 KB per CTA at K).  16-row bands re-read less
+// (22 source rows per 16 instead of 14 per 8: the kernel alone 0.14 vs 0.17 ms per 64 frames), but their 110 KB CTAs only fit on SMs
+// that the v-sweeps of the neighbouring batch have left, and the pipelined step loses 0.5 ms (22.2 vs 21.7 ms); with 8 rows the step
+// is where the two-kernel front was (21.7 ms), the gray image's round trip through HBM is gone and so is one launch per image.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef VPP_CB_ROWS
+#define VPP_CB_ROWS 8
+#endif
+#ifndef VPP_CB_NT
+#define VPP_CB_NT 256
+#endif
+static constexpr int CB_ROWS = VPP_CB_ROWS, CB_HALO = 3, CB_NT = VPP_CB_NT, CB_BAND = CB_ROWS + 2 * CB_HALO;
+
+__device__ __forceinline__ uint32_t cb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(CB_NT) census_fused_kernel(const uint8_t *__restrict__ src, uint32_t *__restrict__ dst, RsgmDims d,
+                                                            long src_bytes, int bands, int raw_cap)
+{
+    extern __shared__ __align__(16) uint8_t csm[];
+    uint8_t *raw = csm;                                            // [raw_cap] window of the source image
+    uint8_t *gray = csm + raw_cap;                                 // [CB_BAND][Wp]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(gray + CB_BAND * d.Wp);
+    const int tid = threadIdx.x;
+    const int band = blockIdx.x % bands;
+    const long f = blockIdx.x / bands;
+    const int W = d.Wp, H = d.Hp;
+    const int y0 = band * CB_ROWS, ylo = y0 - CB_HALO;
+    // source rows of the band (every thread: a dozen reflections)
+    int sy_lo = d.H, sy_hi = -1;
+    for (int r = 0; r < CB_BAND; r++) {
+        const int yp = ylo + r;
+        if (yp < 0 || yp >= H) continue;
+        const int sy = reflect_idx(yp - d.pt, d.H);
+        sy_lo = min(sy_lo, sy); sy_hi = max(sy_hi, sy);
+    }
+    const long row_bytes = (long)d.W * d.C;
+    const long g_lo = (f * d.H + sy_lo) * row_bytes, g_hi = (f * d.H + sy_hi + 1) * row_bytes;     // byte range inside src
+    const long a_lo = g_lo & ~15L;
+    const long a_hi = min((g_hi + 15) & ~15L, src_bytes & ~15L);   // the bulk copy never reads past the tensor
+    const int skew = (int)(g_lo - a_lo);
+    const uint32_t mb = cb_smem_u32(mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(a_hi - a_lo);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t part = min(32768u, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(cb_smem_u32(raw + off)), "l"(src + a_lo + off), "r"(part), "r"(mb) : "memory");
+        }
+    }
+    // (at most 15 bytes at the very end of the tensor are not covered by an aligned 16-byte piece)
+    if (a_hi < g_hi && tid < (int)(g_hi - a_hi)) raw[(a_hi - a_lo) + tid] = src[a_hi + tid];
+    {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(mb) : "memory");
+    }
+    __syncthreads();
+    // the band's gray rows (cv2.copyMakeBorder BORDER_REFLECT + RGB2GRAY as pad_gray_kernel): a warp per row, 4 pixels per lane and
+    // step; only the quads that touch the left / right border go through the reflection
+    const int qw = W / 4;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < CB_BAND; r += CB_NT / 32) {
+        const int yp = ylo + r;
+        uint32_t *grow = reinterpret_cast<uint32_t *>(gray + r * W);
+        if (yp < 0 || yp >= H) {
+            for (int q = lane; q < qw; q += 32) grow[q] = 0u;
+            continue;
+        }
+        const uint8_t *rowp = raw + skew + (long)(reflect_idx(yp - d.pt, d.H) - sy_lo) * row_bytes;
+        for (int q = lane; q < qw; q += 32) {
+            const int sx0 = q * 4 - d.pl;
+            const bool inner = sx0 >= 0 && sx0 + 3 < d.W;
+            uint32_t out = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint8_t *px = rowp + (inner ? sx0 + i : reflect_idx(sx0 + i, d.W)) * d.C;
+                uint32_t v;
+                if (d.C == 3) v = (px[0] * 9798u + px[1] * 19235u + px[2] * 3735u + 16384u) >> 15;
+                else v = px[0];
+                out |= (v & 255u) << (8 * i);
+            }
+            grow[q] = out;
+        }
+    }
+    __syncthreads();
+    // census of rows y0 .. y0 + CB_ROWS - 1 out of the band: flat index a of the frame = gray[a - ylo * W]
+    const long n = (long)W * H;
+    const long lo = 2L * W + 2, hi = (long)W * (H - 2) - 17;
+    const uint8_t *img = gray - (long)ylo * W;
+    for (int rr = warp; rr < CB_ROWS; rr += CB_NT / 32)
+    for (int qx = lane; qx < qw; qx += 32) {
+        const int row = y0 + rr, col = qx * 4;
+        if (row >= H) break;
+        const long c0 = (long)row * W + col;
+        uint4 out = make_uint4(0, 0, 0, 0);
+        const bool any_body = (c0 + 3 >= lo) && (c0 <= hi);
+        const bool tail_row = (row == H - 3) && (col >= W - 16);
+        if (any_body || tail_row) {
+            uint32_t wlo[5], whi[5];
+#pragma unroll
+            for (int dy = 0; dy < 5; dy++) {
+                const uint32_t *a0 = reinterpret_cast<const uint32_t *>(img + c0 + (long)(dy - 2) * W - 4);   // inside the band (halo 3)
+                const uint32_t w0 = a0[0], w1 = a0[1], w2 = a0[2];
+                wlo[dy] = __byte_perm(w0, w1, 0x5432); whi[dy] = __byte_perm(w1, w2, 0x5432);
+            }
+            const uint32_t cw = __byte_perm(wlo[2], whi[2], 0x5432);
+            uint32_t acc[3] = {0u, 0u, 0u};
+            {
+                int k = 0;
+#pragma unroll
+                for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 5; dx++) {
+                        if (dy == 2 && dx == 2) continue;
+                        const uint32_t nb = __byte_perm(wlo[dy], whi[dy], 0x3210u + 0x1111u * dx);
+                        acc[k / 8] = acc[k / 8] * 2u + __vsetltu4(nb, cw);
+                        k++;
+                    }
+            }
+            uint32_t r4[4];
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                const long c = c0 + o;
+                const int cc = col + o;
+                if (c >= lo && c <= hi) {
+                    r4[o] = ((acc[0] >> (8 * o)) & 255u) | (((acc[1] >> (8 * o)) & 255u) << 8) | (((acc[2] >> (8 * o)) & 255u) << 16);
+                } else if (row == H - 3 && cc >= W - 14 && cc <= W - 3) {
+                    uint8_t win[5][8];
+#pragma unroll
+                    for (int dy = 0; dy < 5; dy++)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) win[dy][i] = (uint8_t)((i < 4 ? wlo[dy] : whi[dy]) >> (8 * (i & 3)));
+                    r4[o] = census_tail_order(win, o);
+                } else {
+                    r4[o] = 0;
+                }
+            }
+            out = make_uint4(r4[0], r4[1], r4[2], r4[3]);
+        }
+        reinterpret_cast<uint4 *>(dst + f * n)[c0 / 4] = out;
+    }
+}
+
+static int g_census_fused = 1;      // test hook: 0 = always the two-kernel path
+void census_set_fused(int on) { g_census_fused = on != 0; }
+
+// 0 = done; 1 = not applicable here (source not 16-byte aligned, band beyond shared memory): the caller runs pad_gray + census
+int launch_census_fused(const uint8_t *src, uint32_t *dst, const RsgmDims &d, int n, cudaStream_t st)
+{
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) != 0 || d.Wp % 16 != 0) return 1;
+    const long row_bytes = (long)d.W * d.C;
+    const int raw_cap = (int)((CB_BAND * row_bytes + 32 + 15) & ~15L);
+    const size_t smem = (size_t)raw_cap + (size_t)CB_BAND * d.Wp + 16;
+    int dev = 0, smem_optin = 0;
+    VPP_CUDA_TRY(cudaGetDevice(&dev));
+    VPP_CUDA_TRY(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)smem_optin || !g_census_fused) return 1;
+    const int bands = cdiv(d.Hp, CB_ROWS);
+    if ((long)bands * n > 0x7FFFFFFFL) return 1;
+    VPP_CUDA_TRY(cudaFuncSetAttribute(census_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    census_fused_kernel<<<(unsigned)(bands * n), CB_NT, smem, st>>>(src, dst, d, (long)n * d.H * row_bytes, bands, raw_cap);
+    VPP_LAUNCH_CHECK("census_fused_kernel");
+    return VPPB200_OK;
+}
+
 int launch_census(const uint8_t *src, uint32_t *dst, int W, int H, int n, cudaStream_t st)
 {
     long qpf = (long)W * H / 4, total = qpf * n;
