@@ -8,8 +8,8 @@ One step = one pass of the hot path (VPP random-pattern projection, then compute
 (configs[1]: 1242x375, LiDAR-like 5 % hints, D=192, batch 64 per GPU).  Prints ONE JSON line (rank 0).
   value      whole-job pairs/s with the inputs resident in HBM
   e2e        the same through the host-buffer API (pinned H2D of inputs + D2H of disparities inside the timed region)
-  roofline   the dominant kernel, sgm_v_kernel (one vertical+diagonal sweep = 3 of the 8 SGM paths, 2 launches per step):
-             its compulsory bytes per launch (cost volume read + S read-modify-write = 5*W*H*D per frame) /
+  roofline   the dominant kernel, sgm_v2_kernel (one vertical+diagonal sweep = 3 of the 8 SGM paths, 2 sweeps per step):
+             its compulsory bytes per sweep of the batch (cost volume read + S read-modify-write = 5*W*H*D per frame) /
              its average launch duration measured live with CUDA events on the launching stream, against
              MEASURED_PEAKS.json hbm_gbs; the whole aggregation against SURVEY.md 8d's 4*W*H*D + W*H is reported beside it
   cpu_baseline  the reference's own CPU code (oracle/_ref) on the host cores, bounded sample, rank 0 at N=1
@@ -554,7 +554,7 @@ def main():
             "sustained": None if not sus_n else {"steps": sus_n, "value": world * B * sus_n / (ms_sus_m * 1e-3), "ms_per_step": ms_sus_m / sus_n,
                                                  "e2e_value": world * B * sus_n / (e2e_sus_m * 1e-3), "seconds": ms_sus_m * 1e-3,
                                                  "what": "the same two timed regions run for --sustained-steps steps (>= 5 s each)"},
-            "roofline": {"bound": "hbm", "kernel": "sgm_v2_kernel (v-sweep: paths r1+r2+r3 of one pass, 2 launches per step)",
+            "roofline": {"bound": "hbm", "kernel": "sgm_v2_kernel (v-sweep: paths r1+r2+r3 of one pass over the batch; 2 sweeps per step, each 36 frames x 8 CTAs + 28 frames x 10 CTAs = two cooperative launches timed together)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic if B == 64 else None, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_VSWEEP * B, "launch_ms": v_s * 1e3},
