@@ -516,7 +516,52 @@ __global__ void __launch_bounds__(VR_NT) vpp_rnd_rows_kernel(uint8_t *__restrict
         }
         return v;
     };
-    // the (pixel, channel) items are distinct bytes: four pixel loads in flight per thread instead of one
+    if (C <= 4) {
+        // one thread per active target pixel, all its channels: a record is decoded once for the C blends it stands for (the
+        // channels differ in the pattern draw and in the pixel byte only)
+        for (int it = tid; it < s_nact; it += VR_NT) {
+            const int t = (int)act[it];
+            const int k0 = (int)offs[t], k1 = (int)offs[t + 1];
+            uint8_t *px = t < W ? l + (fr * W + t) * C : r + (fr * W + (t - W)) * C;
+            uint32_t v[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < C) v[j] = px[j];
+            for (int i = k0; i < k1; i++) {
+                const unsigned long long rec = recs[i];
+                const uint32_t key = (uint32_t)(rec >> 32);
+                const uint32_t type = key & 3u, stride = (key >> 6) & 255u;
+                float b32 = 0.0f;
+                double b = 0.0, omb = 1.0;
+                if (type != 2) {
+                    const float gv = hgv[key >> 14];
+                    const int d0 = (int)floorf(gv);
+                    b32 = __fsub_rn(gv, (float)d0);
+                    b = a.arith == 0 ? (double)b32 : __dsub_rn((double)gv, (double)d0);
+                    omb = __dsub_rn(1.0, b);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j < C) {
+                        const uint32_t idx = (uint32_t)rec + (uint32_t)j * stride;
+                        const uint32_t rv = pat ? (idx < pat_len ? pat[idx] : 0) : counter_pattern(frame_key, idx);
+                        const double mix = __dadd_rn(lut_c[rv], lut_o[v[j]]);           // colour + old * (1 - c)
+                        if (type == 2) {
+                            v[j] = tr8(mix);
+                        } else if (type == 0) {
+                            const double rb = a.arith == 0 ? (double)__fmul_rn((float)v[j], b32) : __dmul_rn((double)v[j], b);
+                            v[j] = tr8(__dadd_rn(__dmul_rn(mix, omb), rb));
+                        } else {
+                            v[j] = tr8(__dadd_rn(__dmul_rn(mix, b), __dmul_rn((double)v[j], omb)));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < C) px[j] = (uint8_t)v[j];
+        }
+        return;
+    }
+    // more than four channels: one thread per (pixel, channel) item, four pixel loads in flight per thread
     constexpr int RB = 4;
     for (int it0 = tid; it0 < items; it0 += VR_NT * RB) {
         uint8_t *px[RB];
