@@ -238,6 +238,10 @@ int launch_s_tile_to_xyd(const uint16_t *St, uint16_t *Sx, int W, int H, int D, 
 // ------------------------------------------------------------------------------------------------------------
 static constexpr int HWARPS = 4;   // warps per CTA
 static constexpr int HCROW = 16;   // bytes of a staged cost row: 8 columns x uint16 (16-byte pieces, dense)
+#ifndef VPP_HSROW_WTA
+#define VPP_HSROW_WTA 32
+#endif
+static constexpr int HSROW_WTA = VPP_HSROW_WTA;   // the same for the fused WTA sweep (read only)
 static constexpr int HSROW = 48;   // bytes of a staged S row: 8 columns x uint32 + 16 B pad (3 pieces: odd => LDS.128 conflict-free)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -321,7 +325,9 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
     const long row = (long)blockIdx.x * HWARPS + warp;
     if (row >= total_rows) return;
     const int K2 = t.K2, W = t.W, D = t.D;
-    const int stage_b = K2 * (HCROW + HSROW);
+    // (MODE 2: dense 32-byte S rows -- two-way bank conflicts on the six 16-byte accesses per chunk, but five CTAs per SM instead of four)
+    constexpr int SROW = MODE == 2 ? HSROW_WTA : HSROW;
+    const int stage_b = K2 * (HCROW + SROW);
     uint8_t *base = hsm + (size_t)warp * 2 * stage_b;
     const uint8_t *irow = img + row * W;
     const uint16_t *crow = cost + row * (long)t.G * K2 * 32;     // tiles of this row (rows run over all frames)
@@ -349,9 +355,9 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             }
             if (!STORE) {
                 const uint32_t *src = srow + toff + (lane >> 1) * 32 + (lane & 1) * 4;
-                const uint32_t dst = smem_u32(sb + K2 * HCROW) + (lane >> 1) * HSROW + (lane & 1) * 16;
+                const uint32_t dst = smem_u32(sb + K2 * HCROW) + (lane >> 1) * SROW + (lane & 1) * 16;
                 for (int r0 = 0; r0 < K2; r0 += 16)
-                    if (r0 + (lane >> 1) < K2) cp_async16(dst + r0 * HSROW, src + r0 * 32);
+                    if (r0 + (lane >> 1) < K2) cp_async16(dst + r0 * SROW, src + r0 * 32);
             }
         }
         cp_async_commit();
@@ -394,8 +400,8 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
             if (wv[j]) {
                 cv[j] = *reinterpret_cast<const uint4 *>(sb + (NW * lane + j) * HCROW);
                 if (!STORE) {
-                    s0[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW);
-                    s1[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * HSROW + 16);
+                    s0[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * SROW);
+                    s1[j] = *reinterpret_cast<const uint4 *>(ssb + (NW * lane + j) * SROW + 16);
                 }
             }
         }
@@ -490,8 +496,8 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 if (wv[j]) {
-                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW) = s0[j];
-                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW + 16) = s1[j];
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * SROW) = s0[j];
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * SROW + 16) = s1[j];
                 }
             }
             __syncwarp();
@@ -503,7 +509,7 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
                 if (x >= 1 && x <= W - 2) {
                     if (best > 0) {
                         auto at = [&](int d) -> int {
-                            return *reinterpret_cast<const uint16_t *>(ssb + (d < K2 ? d : d - K2) * HSROW + lane * 4 + (d < K2 ? 0 : 2));
+                            return *reinterpret_cast<const uint16_t *>(ssb + (d < K2 ? d : d - K2) * SROW + lane * 4 + (d < K2 ? 0 : 2));
                         };
                         const int c0 = at(best - 1), c1 = (int)(m >> 16);
                         // best = D-1 reads the next pixel's d = 0 (xyd stream order): column x+1, in the previous chunk for lane 7
@@ -523,18 +529,18 @@ __global__ void __launch_bounds__(HWARPS * 32) sgm_h_kernel(const uint8_t *__res
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 if (wv[j]) {
-                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW) = s0[j];
-                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * HSROW + 16) = s1[j];
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * SROW) = s0[j];
+                    *reinterpret_cast<uint4 *>(ssb + (NW * lane + j) * SROW + 16) = s1[j];
                 }
             }
             __syncwarp();
             // write the chunk's S rows back: two 16-byte pieces = one 32-byte sector per row
             const int toff = ((xlo >> 5) * K2) * 32 + (xlo & 31);
             uint32_t *dst = srow + toff + (lane >> 1) * 32 + (lane & 1) * 4;
-            const uint8_t *src = ssb + (lane >> 1) * HSROW + (lane & 1) * 16;
+            const uint8_t *src = ssb + (lane >> 1) * SROW + (lane & 1) * 16;
             for (int r0 = 0; r0 < K2; r0 += 16)
                 if (r0 + (lane >> 1) < K2)
-                    *reinterpret_cast<uint4 *>(dst + r0 * 32) = *reinterpret_cast<const uint4 *>(src + r0 * HSROW);
+                    *reinterpret_cast<uint4 *>(dst + r0 * 32) = *reinterpret_cast<const uint4 *>(src + r0 * SROW);
         }
         __syncwarp();
         issue(q + 2);
@@ -548,7 +554,7 @@ static int run_h_t(const uint8_t *img, const uint16_t *cost, uint32_t *S, const 
 {
     const long rows = (long)n * t.H;
     const int blocks = cdiv(rows, HWARPS);
-    const size_t stage = h_stage_bytes(t.K2);
+    const size_t stage = MODE == 2 ? (size_t)t.K2 * (HCROW + HSROW_WTA) : h_stage_bytes(t.K2);
     const size_t smem = (size_t)HWARPS * 2 * stage + (MODE == 2 ? (size_t)HWARPS * 16 * 4 : 0);
     auto kern = t.K2 == NW * 32 ? sgm_h_kernel<NW, MODE, DIR, true> : sgm_h_kernel<NW, MODE, DIR, false>;
     if (smem > 48 * 1024) VPP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
