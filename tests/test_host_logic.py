@@ -24,6 +24,22 @@ def test_library_exports_header_symbols():
     assert b"sm_100a" in lib.vppb200_version()
 
 
+def test_tuning_keys_match_header():
+    """every VPPB200_TUNE_* key of include/vppstereo_b200.h has the same value in the Python binding, and the library accepts it"""
+    import re
+    from vppstereo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vppstereo_b200.h")).read()
+    keys = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"#define\s+VPPB200_TUNE_(\w+)\s+(\d+)", hdr))
+    assert len(keys) >= 11 and len(set(keys.values())) == len(keys)
+    for name, value in keys.items():
+        assert getattr(_lib, "TUNE_" + name) == value, name
+    L = _lib.lib()
+    assert L.vppb200_set_tuning(max(keys.values()) + 1, 0) != 0          # unknown key: VPPB200_ERR_ARG
+    for name, value in keys.items():
+        default = 0 if name in ("SGM_MAX_STRIP", "SGM_CLUSTERS", "SGM_BYTE_SUMS", "SGM_FUSE_COST", "RCP_HOST") else 1
+        assert L.vppb200_set_tuning(value, default) == 0, name          # (host-side switches only: no GPU needed)
+
+
 def test_no_torch_types_in_header():
     header = open(os.path.join(ROOT, "include", "vppstereo_b200.h")).read()
     assert "torch" not in header.lower() and "at::" not in header and "#include <cuda" not in header
