@@ -60,7 +60,10 @@ static TL make_tl(int W, int H, int D)
 __device__ __forceinline__ int sw_adapt_p2(int ip, int ipr)
 {
     // (sint32)(-alpha * abs(I_p - I_pr) + gamma), clamped below by P2min  (RSGM/StereoSGM.hpp:92-99)
-    const int r = (int)__fadd_rn(__fmul_rn(-SW_ALPHA, (float)abs(ip - ipr)), (float)SW_GAMMA);
+    // With alpha = 1/4 and gamma = 50 the float expression is exact and its truncation is 50 - ceil(|dI| / 4) (checked for all 256
+    // differences against the float form): three integer instructions
+    static_assert(SW_ALPHA == 0.25f && SW_GAMMA == 50, "the closed form below is for alpha = 1/4, gamma = 50");
+    const int r = SW_GAMMA - ((abs(ip - ipr) + 3) >> 2);
     return r < SW_P2MIN ? SW_P2MIN : r;
 }
 
@@ -666,31 +669,38 @@ static constexpr uint32_t HALO_INVALID = 0xF0000000u;
 // P2 = adaptP2(I(p), I(p - r)) with I read from the FLAT byte stream of the guide (RSGM/StereoSGM.hpp:92-99,
 // StereoSGM_SSE.hpp:221,:238-243: on the row after the pass's first row the "previous line" is that same row).
 // Row bands: the table covers rows [row0, row0 + Hb) of frames of H rows (img_all = the full guide images).
+// One thread = 4 adjacent pixels of a row (one 16-byte store); grid.y = frame * Hb + band row.
 __global__ void __launch_bounds__(256) sgm_p2_kernel(const uint8_t *__restrict__ img_all, uint32_t *__restrict__ p2q, int W, int H,
-                                                     int G32, int pass, long total, int row0, int Hb)
+                                                     int G32, int pass, int row0, int Hb)
 {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int x = (int)(t % G32);
-    const long r = t / G32;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x0 >= G32) return;
+    const long r = blockIdx.y;                            // f * Hb + band row
     const int i = row0 + (int)(r % Hb);
     const long f = r / Hb;
     const int dj = pass == 0 ? 1 : -1, di = dj, i1 = pass == 0 ? 0 : H - 1;
-    uint32_t out = 0;
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
     if (i != i1) {
-        const long npx = (long)W * H;
-        const uint8_t *img = img_all + f * npx;
+        const int npx = W * H;                            // (a frame's tile volume fits 31 bits, so does its pixel count)
+        const uint8_t *img = img_all + f * (long)npx;
         const int s = (i - i1) * di;
         const int il = s == 1 ? i : i - di;
-        const int xr = min(x, W - 1);
-        long q1 = (long)il * W + xr - dj, q3 = (long)il * W + xr + dj;
-        q1 = q1 < 0 ? 0 : (q1 >= npx ? npx - 1 : q1);
-        q3 = q3 < 0 ? 0 : (q3 >= npx ? npx - 1 : q3);
-        const int ipc = img[(long)i * W + xr], ip1 = img[q1], ip2 = img[(long)il * W + xr], ip3 = img[q3];
-        out = (uint32_t)(sw_adapt_p2(ipc, ip1) - SW_P1) | ((uint32_t)(sw_adapt_p2(ipc, ip2) - SW_P1) << 8) |
-              ((uint32_t)(sw_adapt_p2(ipc, ip3) - SW_P1) << 16);
+        const uint8_t *rc = img + i * W, *rl = img + il * W;
+        const int lbase = il * W;
+        uint32_t o[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int xr = min(x0 + u, W - 1);
+            int q1 = lbase + xr - dj, q3 = lbase + xr + dj;
+            q1 = q1 < 0 ? 0 : (q1 >= npx ? npx - 1 : q1);
+            q3 = q3 < 0 ? 0 : (q3 >= npx ? npx - 1 : q3);
+            const int ipc = rc[xr], ip1 = img[q1], ip2 = rl[xr], ip3 = img[q3];
+            o[u] = (uint32_t)(sw_adapt_p2(ipc, ip1) - SW_P1) | ((uint32_t)(sw_adapt_p2(ipc, ip2) - SW_P1) << 8) |
+                   ((uint32_t)(sw_adapt_p2(ipc, ip3) - SW_P1) << 16);
+        }
+        out = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    p2q[t] = out;
+    *reinterpret_cast<uint4 *>(p2q + r * G32 + x0) = out;
 }
 
 // Raised by a hand-off wait that timed out (a CTA of the team not resident / not progressing: the protocol needs all CTAs of the
@@ -1330,9 +1340,15 @@ static int run_v(const uint8_t *img, const uint16_t *cost, uint32_t *S, void *ha
     VPP_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void **>(&abort_flag), g_sweep_abort));
     uint32_t *p2q = reinterpret_cast<uint32_t *>(static_cast<char *>(halo_ws) + HALO_LINES_BYTES + 256);
     const int G32 = t.G * 32;
-    const long total = (long)n * t.H * G32;
-    sgm_p2_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, p2q, t.W, band.Hfull, G32, pass, total, band.row0, t.H);
-    VPP_LAUNCH_CHECK("sgm_p2_kernel");
+    // grid.y = frame * rows (<= 65535 per launch: whole frames per launch)
+    if (t.H > 65535) return VPPB200_ERR_ARG;
+    const int fpl = 65535 / t.H;
+    for (int f0 = 0; f0 < n; f0 += fpl) {
+        const int nf = std::min(fpl, n - f0);
+        sgm_p2_kernel<<<dim3((unsigned)cdiv(G32 / 4, 256), (unsigned)(nf * t.H)), 256, 0, st>>>(
+            img + (long)f0 * t.W * band.Hfull, p2q + (long)f0 * t.H * G32, t.W, band.Hfull, G32, pass, band.row0, t.H);
+        VPP_LAUNCH_CHECK("sgm_p2_kernel");
+    }
     switch (p.GC) {
         case 1: return run_v_t<1>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, band, st);
         case 2: return run_v_t<2>(p2q, cost, S, halo, abort_flag, t, pass, n, p, norm, band, st);
